@@ -1,0 +1,184 @@
+// Parameter re-layout for the kernels (no reference counterpart: the reference keeps
+// nn.Linear weights [out,in] and lets ATen pick a GEMM; spline.py:113-125 then slices the
+// conditioner output by column blocks).  Here the slicing is folded into the weight layout once.
+#include <vector>
+
+#include "bgx_common.cuh"
+
+namespace bgx {
+
+thread_local cudaError_t g_last_error = cudaSuccess;
+long long g_launches = 0;
+
+// dst[k][n] = W[row(n)][k]   (K-padded rows / unmapped columns are zero)
+__global__ void pack_transpose_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                      const int* __restrict__ row_map, int K, int N, int Kp, int Np,
+                                      float* __restrict__ Wt, float* __restrict__ bias) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Kp * Np;
+  if (idx < total) {
+    int n = (int)(idx % Np), k = (int)(idx / Np);
+    int r = row_map ? row_map[n] : (n < N ? n : -1);
+    Wt[idx] = (r >= 0 && k < K) ? W[(long long)r * K + k] : 0.f;
+  }
+  if (idx < Np) {
+    int n = (int)idx;
+    int r = row_map ? row_map[n] : (n < N ? n : -1);
+    bias[n] = r >= 0 ? b[r] : 0.f;
+  }
+}
+
+// K-major tf32 split for the tensor-core path: hi = tf32-truncated W, lo = W - hi
+__global__ void pack_kmajor_split_kernel(const float* __restrict__ W, const int* __restrict__ row_map, int K,
+                                         int N, int Kp, int Np, float* __restrict__ hi,
+                                         float* __restrict__ lo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Kp * Np;
+  if (idx >= total) return;
+  int k = (int)(idx % Kp), n = (int)(idx / Kp);
+  int r = row_map ? row_map[n] : (n < N ? n : -1);
+  float w = (r >= 0 && k < K) ? W[(long long)r * K + k] : 0.f;
+  float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+  hi[idx] = h;
+  lo[idx] = w - h;
+}
+
+static int spline_dims_per_pass(int n_bins) { return 128 / (3 * n_bins + 1); }
+
+}  // namespace bgx
+
+using namespace bgx;
+
+extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline, float* dst, int64_t dst_floats,
+                            bgx_packed_mlp* out, void* stream) {
+  if (!src || !out || src->n_layers < 1 || src->n_layers > BGX_MAX_LAYERS) return BGX_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = src->n_layers;
+  bgx_packed_mlp pk{};
+  pk.n_layers = L;
+  pk.act = src->act;
+  const bool is_spline = spline && spline->d_t > 0;
+  int n_periodic = src->n_periodic > 0 ? src->n_periodic : 0;
+  pk.raw_width = n_periodic ? src->raw_width : src->dims[0];
+  if (src->dims[0] != pk.raw_width + n_periodic) return BGX_ERR_INVALID;
+  if (n_periodic && !src->periodic_idx) return BGX_ERR_INVALID;
+  for (int l = 0; l < L; ++l) {
+    if (src->dims[l] < 1 || src->dims[l + 1] < 1) return BGX_ERR_INVALID;
+    pk.K[l] = src->dims[l];
+    pk.N[l] = src->dims[l + 1];
+    pk.Kp[l] = round_up(pk.K[l], 16);
+    pk.Np[l] = round_up(pk.N[l], 128);
+  }
+  std::vector<int> last_map;  // packed column -> source row of the last Linear (or -1)
+  if (is_spline) {
+    const int K = spline->n_bins, dt = spline->d_t;
+    if (K < 1 || 3 * K + 1 > 128) return BGX_ERR_UNSUPPORTED;
+    int n_nc = 0;
+    std::vector<int> nc_rank(dt, -1);
+    for (int d = 0; d < dt; ++d) {
+      bool circ = spline->is_circular && spline->is_circular[d];
+      if (!circ) nc_rank[d] = n_nc++;
+    }
+    // spline.py:112-117: the conditioner width must be 3*K*d_t + n_noncircular
+    if (src->dims[L] != 3 * K * dt + n_nc) return BGX_ERR_INVALID;
+    const int dpp = spline_dims_per_pass(K), ps = 3 * K + 1;
+    pk.spline_dims_per_pass = dpp;
+    pk.spline_stride = ps;
+    pk.N[L - 1] = ceil_div(dt, dpp) * 128;  // packed width
+    pk.Np[L - 1] = pk.N[L - 1];
+    last_map.assign(pk.Np[L - 1], -1);
+    for (int n = 0; n < pk.Np[L - 1]; ++n) {
+      int p = n / 128, c = n % 128, slot = c / ps, j = c % ps, d = p * dpp + slot;
+      if (slot >= dpp || d >= dt) continue;
+      int r;
+      if (j < K) r = d * K + j;
+      else if (j < 2 * K) r = K * dt + d * K + (j - K);
+      else if (j < 3 * K) r = 2 * K * dt + d * K + (j - 2 * K);
+      else r = nc_rank[d] >= 0 ? 3 * K * dt + nc_rank[d] : 2 * K * dt + d * K;  // periodic: knot K := knot 0
+      last_map[n] = r;
+    }
+  }
+  // layout: [Wt_l | bias_l]* , [Wk_hi_l | Wk_lo_l]* (K-major, Kp rounded to 32), in_map, last_map
+  int64_t off = 0;
+  int64_t o_wt[BGX_MAX_LAYERS], o_b[BGX_MAX_LAYERS], o_hi[BGX_MAX_LAYERS], o_lo[BGX_MAX_LAYERS];
+  int kp32[BGX_MAX_LAYERS];
+  for (int l = 0; l < L; ++l) {
+    o_wt[l] = off; off += (int64_t)pk.Kp[l] * pk.Np[l];
+    o_b[l] = off; off += pk.Np[l];
+  }
+  for (int l = 0; l < L; ++l) {
+    kp32[l] = round_up(pk.K[l], 32);
+    o_hi[l] = off; off += (int64_t)kp32[l] * pk.Np[l];
+    o_lo[l] = off; off += (int64_t)kp32[l] * pk.Np[l];
+  }
+  int64_t o_inmap = off; off += round_up(pk.Kp[0], 4);
+  int64_t o_lastmap = off; off += (int64_t)last_map.size();
+  off = (off + 3) / 4 * 4;
+  pk.total_floats = off;
+  if (!dst) {
+    *out = pk;
+    return BGX_OK;
+  }
+  if (dst_floats < off) return BGX_ERR_WORKSPACE;
+  if (((uintptr_t)dst & 15) != 0) return BGX_ERR_INVALID;
+
+  // conditioner input map (periodic.py:30-37): cos block, sin block, then the other columns
+  std::vector<int> in_map(pk.Kp[0], 0);
+  {
+    std::vector<char> is_p(pk.raw_width, 0);
+    for (int i = 0; i < n_periodic; ++i) {
+      int c = src->periodic_idx[i];
+      if (c < 0 || c >= pk.raw_width) return BGX_ERR_INVALID;
+      is_p[c] = 1;
+      in_map[i] = c | (1 << 24);
+      in_map[n_periodic + i] = c | (2 << 24);
+    }
+    int k = 2 * n_periodic;
+    for (int c = 0; c < pk.raw_width; ++c)
+      if (!is_p[c]) {
+        if (k >= pk.K[0]) return BGX_ERR_INVALID;
+        in_map[k++] = c;
+      }
+    if (k != pk.K[0]) return BGX_ERR_INVALID;
+  }
+  int* d_inmap = reinterpret_cast<int*>(dst + o_inmap);
+  int* d_lastmap = last_map.empty() ? nullptr : reinterpret_cast<int*>(dst + o_lastmap);
+  int rc = check(cudaMemcpyAsync(d_inmap, in_map.data(), in_map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (rc) return rc;
+  if (d_lastmap) {
+    rc = check(cudaMemcpyAsync(d_lastmap, last_map.data(), last_map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (rc) return rc;
+  }
+  pk.in_map = d_inmap;
+  if (n_periodic) {
+    pk.periodic_left = src->periodic_left;
+    pk.periodic_scale = (float)(6.283185307179586 / ((double)src->periodic_right - (double)src->periodic_left));
+  }
+  for (int l = 0; l < L; ++l) {
+    if (!src->W[l] || !src->b[l]) return BGX_ERR_INVALID;
+    const int* rmap = (l == L - 1) ? d_lastmap : nullptr;
+    const int n_true = (l == L - 1 && is_spline) ? pk.Np[l] : pk.N[l];
+    float* wt = dst + o_wt[l];
+    float* bb = dst + o_b[l];
+    long long total = (long long)pk.Kp[l] * pk.Np[l];
+    pack_transpose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        src->W[l], src->b[l], rmap, pk.K[l], n_true, pk.Kp[l], pk.Np[l], wt, bb);
+    rc = post_launch();
+    if (rc) return rc;
+    long long total2 = (long long)kp32[l] * pk.Np[l];
+    pack_kmajor_split_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
+        src->W[l], rmap, pk.K[l], n_true, kp32[l], pk.Np[l], dst + o_hi[l], dst + o_lo[l]);
+    rc = post_launch();
+    if (rc) return rc;
+    pk.Wt[l] = wt;
+    pk.bias[l] = bb;
+    pk.Wk_hi[l] = dst + o_hi[l];
+    pk.Wk_lo[l] = dst + o_lo[l];
+  }
+  *out = pk;
+  return BGX_OK;
+}
+
+extern "C" const char* bgx_version(void) { return "bgflow_b200 0.1 (sm_100a)"; }
+extern "C" const char* bgx_last_cuda_error(void) { return cudaGetErrorString(g_last_error); }
+extern "C" int64_t bgx_launch_count(void) { return g_launches; }

@@ -1,0 +1,300 @@
+"""Tensor-facing launch layer over the C ABI: packs parameters (cached), builds the segment
+descriptors for the flow state and launches the fused kernels on torch's current stream.
+
+PyTorch is used here for device memory and streams only; all arithmetic of the hot path runs
+in ``libbgflow_b200.so``.  Everything requires CUDA fp32 tensors — there is no CPU fallback.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["PackedNet", "affine_coupling", "spline_coupling", "ic_to_xyz", "ic_from_xyz", "ZPlan",
+           "require_cuda_fp32"]
+
+
+def require_cuda_fp32(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "bgflow_b200 runs its flows on CUDA tensors only (got a CPU tensor); "
+                "there is no CPU fallback by design")
+        if t.dtype != torch.float32:
+            raise NotImplementedError(f"bgflow_b200 kernels are fp32; got {t.dtype}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ACT_CODES = {type(None): _lib.ACT_NONE, torch.nn.ReLU: _lib.ACT_RELU, torch.nn.SiLU: _lib.ACT_SILU,
+              torch.nn.Tanh: _lib.ACT_TANH, torch.nn.Identity: _lib.ACT_NONE}
+
+
+def activation_code(module):
+    """Map the DenseNet activation module to the kernel's code, or None if unsupported."""
+    return _ACT_CODES.get(type(module))
+
+
+class PackedNet:
+    """Device copy of one conditioner MLP in kernel layout, cached on parameter versions."""
+
+    def __init__(self):
+        self._key = None
+        self._buf = None
+        self.packed = _lib.bgx_packed_mlp()
+
+    def refresh(self, weights, biases, act_code, periodic=None, spline=None):
+        """weights[i]: [out,in] fp32 CUDA (nn.Linear.weight), biases[i]: [out].
+        periodic: None or (indices, left, right, raw_width); spline: None or (d_t, n_bins, circ mask)."""
+        key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
+        key = (key, act_code, repr(periodic), repr(spline), weights[0].device)
+        if key == self._key:
+            return self.packed
+        lib = _lib.load()
+        require_cuda_fp32(*weights, *biases)
+        n = len(weights)
+        if n > _lib.BGX_MAX_LAYERS:
+            raise NotImplementedError(f"at most {_lib.BGX_MAX_LAYERS} Linear layers per conditioner")
+        ws = [w.detach().contiguous() for w in weights]
+        bs = [b.detach().contiguous() for b in biases]
+        src = _lib.bgx_mlp()
+        src.n_layers = n
+        src.act = act_code
+        src.dims[0] = ws[0].shape[1]
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            if w.shape[1] != src.dims[i] or b.shape[0] != w.shape[0]:
+                raise ValueError("inconsistent DenseNet layer shapes")
+            src.dims[i + 1] = w.shape[0]
+            src.W[i] = w.data_ptr()
+            src.b[i] = b.data_ptr()
+        keep = []
+        if periodic is not None:
+            idx, left, right, raw_width = periodic
+            arr = (C.c_int32 * len(idx))(*[int(i) for i in idx])
+            keep.append(arr)
+            src.n_periodic = len(idx)
+            src.periodic_idx = C.cast(arr, C.POINTER(C.c_int32))
+            src.periodic_left = float(left)
+            src.periodic_right = float(right)
+            src.raw_width = int(raw_width)
+        else:
+            src.raw_width = src.dims[0]
+        lay = None
+        if spline is not None:
+            d_t, n_bins, circ = spline
+            lay = _lib.bgx_spline_layout()
+            lay.d_t = int(d_t)
+            lay.n_bins = int(n_bins)
+            if circ is not None:
+                carr = (C.c_uint8 * d_t)(*[1 if c else 0 for c in circ])
+                keep.append(carr)
+                lay.is_circular = C.cast(carr, C.POINTER(C.c_uint8))
+        out = _lib.bgx_packed_mlp()
+        lay_p = C.byref(lay) if lay is not None else None
+        rc = lib.bgx_pack_mlp(C.byref(src), lay_p, None, 0, C.byref(out), _stream())
+        if rc == -1 and spline is not None:
+            # mirrors the RuntimeError of spline.py:112-121 (split/reshape of a wrong-width output)
+            raise RuntimeError(
+                f"params_net output width {src.dims[n]} does not match "
+                f"3 * n_bins * {spline[0]} + n_noncircular")
+        _lib.check(rc, "bgx_pack_mlp(size)")
+        buf = torch.empty(int(out.total_floats), dtype=torch.float32, device=ws[0].device)
+        rc = lib.bgx_pack_mlp(C.byref(src), lay_p, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(out),
+                              _stream())
+        _lib.check(rc, "bgx_pack_mlp")
+        self._buf, self.packed, self._key = buf, out, key
+        return out
+
+
+def _as_rows(t):
+    """View a flow-state tensor as [B, w] with unit inner stride (copy only if it must)."""
+    w = t.shape[-1]
+    if t.dim() != 2:
+        t = t.reshape(-1, w)
+    if t.stride(-1) != 1 or (t.shape[0] > 1 and t.stride(0) < w):
+        t = t.contiguous()
+    return t
+
+
+def _fill_io(cond, tr, dlogp_in):
+    if len(cond) > _lib.BGX_MAX_SEGS or len(tr) > _lib.BGX_MAX_SEGS or len(tr) < 1:
+        raise NotImplementedError(f"at most {_lib.BGX_MAX_SEGS} tensors per side of a coupling")
+    require_cuda_fp32(*cond, *tr)
+    batch_shape = tr[0].shape[:-1]
+    cond2 = [_as_rows(t) for t in cond]
+    tr2 = [_as_rows(t) for t in tr]
+    B = tr2[0].shape[0]
+    for t in cond2 + tr2:
+        if t.shape[0] != B:
+            raise ValueError("all tensors of a coupling must share their batch shape")
+    widths = [t.shape[1] for t in tr2]
+    out = torch.empty(B, sum(widths), dtype=torch.float32, device=tr2[0].device)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=tr2[0].device)
+    io = _lib.bgx_coupling_io()
+    io.batch = B
+    io.n_cond = len(cond2)
+    for i, t in enumerate(cond2):
+        io.cond[i].ptr, io.cond[i].width, io.cond[i].stride = t.data_ptr(), t.shape[1], t.stride(0) if B > 1 else t.shape[1]
+    io.n_tr = len(tr2)
+    col = 0
+    outs = []
+    for i, t in enumerate(tr2):
+        io.tr_in[i].ptr, io.tr_in[i].width, io.tr_in[i].stride = t.data_ptr(), t.shape[1], t.stride(0) if B > 1 else t.shape[1]
+        o = out[:, col:col + widths[i]]
+        io.tr_out[i].ptr, io.tr_out[i].width, io.tr_out[i].stride = o.data_ptr(), widths[i], out.stride(0)
+        outs.append(o.reshape(*batch_shape, widths[i]) if len(batch_shape) != 1 else o)
+        col += widths[i]
+    keep = [cond2, tr2]
+    if dlogp_in is not None:
+        require_cuda_fp32(dlogp_in)
+        d = dlogp_in.reshape(-1)
+        if d.shape[0] != B:
+            raise ValueError("dlogp accumulator has the wrong batch size")
+        d = d.contiguous()
+        keep.append(d)
+        io.dlogp_in = d.data_ptr()
+    io.dlogp_out = dlogp.data_ptr()
+    return io, outs, dlogp.reshape(*batch_shape, 1), keep
+
+
+def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_volume=False,
+                    is_circular=False, dlogp_in=None, flags=0):
+    """cond / tr: lists of tensors (concatenated along the last dim by the kernel);
+    shift / scale: ``bgx_packed_mlp`` or None.  Returns (list of outputs, dlogp [.., 1])."""
+    lib = _lib.load()
+    io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
+    f = flags | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
+        | (_lib.FLAG_CIRCULAR if is_circular else 0)
+    rc = lib.bgx_affine_coupling(C.byref(io), C.byref(shift) if shift is not None else None,
+                                 C.byref(scale) if scale is not None else None, float(log_alpha), f, _stream())
+    _lib.check(rc, "bgx_affine_coupling")
+    return outs, dlogp
+
+
+def spline_coupling(cond, tr, net, n_bins, inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0,
+                    min_bin_width=1e-3, min_bin_height=1e-3, min_derivative=1e-3, identity_init=True,
+                    oob_counter=None, dlogp_in=None, flags=0):
+    lib = _lib.load()
+    io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
+    cfg = _lib.bgx_spline_cfg()
+    cfg.n_bins = n_bins
+    cfg.left, cfg.right, cfg.bottom, cfg.top = float(left), float(right), float(bottom), float(top)
+    cfg.min_bin_width, cfg.min_bin_height, cfg.min_derivative = min_bin_width, min_bin_height, min_derivative
+    cfg.identity_init = 1 if identity_init else 0
+    cfg.oob_counter = oob_counter.data_ptr() if oob_counter is not None else None
+    f = flags | (_lib.FLAG_INVERSE if inverse else 0)
+    rc = lib.bgx_spline_coupling(C.byref(io), C.byref(net), C.byref(cfg), f, _stream())
+    _lib.check(rc, "bgx_spline_coupling")
+    return outs, dlogp
+
+
+class ZPlan:
+    """Host staging of a global z-matrix (what ic.py:25-97 does with numpy) + its device copy."""
+
+    def __init__(self, z_matrix, normalize_angles=True, eps=1e-7):
+        z = np.asarray(z_matrix, dtype=np.int64)
+        if z.ndim != 2 or z.shape[1] != 4:
+            raise ValueError("z_matrix must have shape (n_atoms, 4)")
+        undefined = (z == -1).sum(axis=1)
+        seeds = []
+        for want in (3, 2, 1):
+            rows = np.flatnonzero(undefined == want)
+            if len(rows) != 1:
+                raise ValueError("a global z-matrix needs exactly one row with 3, 2 and 1 undefined references")
+            seeds.append(int(z[rows[0], 0]))
+        rel = z[undefined == 0]
+        if len(rel) != len(z) - 3:
+            raise ValueError("z-matrix rows must have 0, 1, 2 or 3 undefined (-1) references")
+        n_atoms = len(z)
+        if sorted(z[:, 0].tolist()) != list(range(n_atoms)):
+            raise ValueError("z-matrix must place every atom exactly once")
+        # topological order: a row is placeable once its three reference atoms are placed
+        placed = np.zeros(n_atoms, dtype=bool)
+        placed[seeds] = True
+        todo = list(range(len(rel)))
+        order = []
+        while todo:
+            ready = [r for r in todo if placed[rel[r, 1:]].all()]
+            if not ready:
+                raise ValueError(
+                    "Z-matrix decomposition failed. The following atoms were not reachable from "
+                    f"the fixed atoms: \n{rel[todo, 0]}")
+            order.extend(ready)
+            placed[rel[ready, 0]] = True
+            ready_set = set(ready)
+            todo = [r for r in todo if r not in ready_set]
+        self.z_matrix = z
+        self.seeds = seeds
+        self.rel = rel
+        self.order = order
+        self.n_atoms = n_atoms
+        self.normalize_angles = bool(normalize_angles)
+        self.eps = float(eps)
+        self._dev = {}
+
+    def device_plan(self, device):
+        key = str(device)
+        if key not in self._dev:
+            rel = torch.as_tensor(self.rel.astype(np.int32)).contiguous().to(device)
+            order = torch.as_tensor(np.asarray(self.order, dtype=np.int32)).to(device)
+            plan = _lib.bgx_zplan()
+            plan.n_atoms = self.n_atoms
+            for i in range(3):
+                plan.seeds[i] = self.seeds[i]
+            plan.n_rel = len(self.rel)
+            plan.rel = rel.data_ptr()
+            plan.order = order.data_ptr()
+            plan.normalize_angles = 1 if self.normalize_angles else 0
+            plan.eps = self.eps
+            self._dev[key] = (plan, rel, order)
+        return self._dev[key][0]
+
+
+def ic_to_xyz(plan, bonds, angles, torsions, x0, R, dlogp_in=None):
+    lib = _lib.load()
+    require_cuda_fp32(bonds, angles, torsions, x0, R)
+    n = plan.n_atoms
+    B = bonds.shape[0]
+    if bonds.shape != (B, n - 1) or angles.shape != (B, n - 2) or torsions.shape != (B, n - 3):
+        raise ValueError("bonds/angles/torsions must be [B, N-1], [B, N-2], [B, N-3]")
+    bonds, angles, torsions = bonds.contiguous(), angles.contiguous(), torsions.contiguous()
+    x0f = x0.reshape(-1, 3).contiguous()
+    Rf = R.reshape(-1, 3).contiguous()
+    if x0f.shape[0] not in (1, B) or Rf.shape[0] not in (1, B):
+        raise ValueError("x0 must be [B,1,3] (or [1,3]) and R [B,3]")
+    xyz = torch.empty(B, 3 * n, dtype=torch.float32, device=bonds.device)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
+    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    rc = lib.bgx_ic_to_xyz(C.byref(plan.device_plan(bonds.device)), B, bonds.data_ptr(), angles.data_ptr(),
+                           torsions.data_ptr(), x0f.data_ptr(), 3 if x0f.shape[0] == B else 0,
+                           Rf.data_ptr(), 3 if Rf.shape[0] == B else 0, xyz.data_ptr(),
+                           din.data_ptr() if din is not None else None, dlogp.data_ptr(), _stream())
+    _lib.check(rc, "bgx_ic_to_xyz")
+    return xyz, dlogp
+
+
+def ic_from_xyz(plan, xyz, dlogp_in=None):
+    lib = _lib.load()
+    require_cuda_fp32(xyz)
+    n = plan.n_atoms
+    B = xyz.shape[0]
+    x = xyz.reshape(B, -1).contiguous()
+    if x.shape[1] != 3 * n:
+        raise ValueError(f"xyz must have {3 * n} coordinates per sample")
+    dev = x.device
+    bonds = torch.empty(B, n - 1, dtype=torch.float32, device=dev)
+    angles = torch.empty(B, n - 2, dtype=torch.float32, device=dev)
+    torsions = torch.empty(B, n - 3, dtype=torch.float32, device=dev)
+    x0 = torch.empty(B, 1, 3, dtype=torch.float32, device=dev)
+    R = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
+    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    rc = lib.bgx_ic_from_xyz(C.byref(plan.device_plan(dev)), B, x.data_ptr(), bonds.data_ptr(), angles.data_ptr(),
+                             torsions.data_ptr(), x0.data_ptr(), R.data_ptr(),
+                             din.data_ptr() if din is not None else None, dlogp.data_ptr(), _stream())
+    _lib.check(rc, "bgx_ic_from_xyz")
+    return bonds, angles, torsions, x0, R, dlogp

@@ -1,0 +1,179 @@
+/*
+ * bgflow_b200 — C ABI of the B200-native coupling-flow engine.
+ *
+ * Drop-in boundary for the hot path of noegroup/bgflow (reference paths are relative to the
+ * reference checkout):
+ *
+ *   bgx_affine_coupling   replaces  CouplingFlow._forward/_inverse (bgflow/nn/flow/coupling.py:162-182)
+ *                                   + AffineTransformer (bgflow/nn/flow/transformer/affine.py:35-70)
+ *                                   + DenseNet.forward x2 (bgflow/nn/dense.py:47-48)
+ *   bgx_spline_coupling   replaces  CouplingFlow (coupling.py:162-182)
+ *                                   + ConditionalSplineTransformer._compute_params/_forward/_inverse
+ *                                     (bgflow/nn/flow/transformer/spline.py:87-188)
+ *                                   + nflows.transforms.splines.rational_quadratic_spline (3rd party)
+ *                                   + WrapPeriodic.forward (bgflow/nn/periodic.py:30-37)
+ *   bgx_ic_to_xyz         replaces  GlobalInternalCoordinateTransformation._inverse
+ *                                   (bgflow/nn/flow/crd_transform/ic.py:678-716, 209-265, 435-513,
+ *                                    ic_helper.py:372-452, 480-575)
+ *   bgx_ic_from_xyz       replaces  GlobalInternalCoordinateTransformation._forward
+ *                                   (ic.py:633-676, 162-206, 386-433, ic_helper.py:148-293, 578-680)
+ *   bgx_pack_mlp          (no reference counterpart) re-lays nn.Linear weights for the kernels
+ *
+ * Conventions: plain pointers and sizes only, no torch types.  All device pointers are fp32,
+ * row-major.  Every function returns BGX_OK (0) or a negative error code, never throws, never
+ * allocates device memory (callers pass outputs and workspaces) and never synchronises the
+ * host with the device.
+ * `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ * dlogp follows bgflow: log|det J| of the direction evaluated, one float per sample.
+ */
+#ifndef BGFLOW_B200_H
+#define BGFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGX_OK 0
+#define BGX_ERR_INVALID (-1)      /* bad argument / inconsistent shapes */
+#define BGX_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels support */
+#define BGX_ERR_WORKSPACE (-3)    /* workspace too small */
+#define BGX_ERR_CUDA (-4)         /* a CUDA runtime call failed: see bgx_last_cuda_error */
+
+#define BGX_MAX_LAYERS 8
+#define BGX_MAX_SEGS 8
+
+#define BGX_ACT_NONE 0
+#define BGX_ACT_RELU 1
+#define BGX_ACT_SILU 2
+#define BGX_ACT_TANH 3
+
+/* One DenseNet (bgflow/nn/dense.py:10-45): W[i] is nn.Linear.weight [dims[i+1], dims[i]]
+ * row-major, b[i] is [dims[i+1]]; `act` follows every layer but the last.  If n_periodic > 0 the
+ * net is wrapped in WrapPeriodic (periodic.py:30-37): the raw conditioner vector of width
+ * `raw_width` is mapped to [cos(2pi(x_c-l)/(r-l)) for c in periodic_idx,
+ * sin(...) likewise, x_others in original order], and dims[0] == raw_width + n_periodic. */
+typedef struct bgx_mlp {
+  int32_t n_layers;
+  int32_t act;
+  int32_t dims[BGX_MAX_LAYERS + 1];
+  const float* W[BGX_MAX_LAYERS];    /* device */
+  const float* b[BGX_MAX_LAYERS];    /* device */
+  int32_t raw_width;
+  int32_t n_periodic;
+  const int32_t* periodic_idx;       /* HOST array, n_periodic entries (may be NULL if 0) */
+  float periodic_left, periodic_right;
+} bgx_mlp;
+
+/* Re-laid parameters for the kernels.  Opaque to callers except `total_floats`. */
+typedef struct bgx_packed_mlp {
+  int32_t n_layers, act;
+  int32_t K[BGX_MAX_LAYERS], N[BGX_MAX_LAYERS];    /* true in / out widths */
+  int32_t Kp[BGX_MAX_LAYERS], Np[BGX_MAX_LAYERS];  /* padded */
+  const float* Wt[BGX_MAX_LAYERS];                 /* device, [Kp][Np] (SIMT layout) */
+  const float* bias[BGX_MAX_LAYERS];               /* device, [Np] */
+  const int32_t* in_map;                           /* device, Kp[0] entries: raw col | kind<<24 */
+  float periodic_scale, periodic_left;             /* arg = (x - left) * scale */
+  int32_t raw_width;
+  int32_t spline_dims_per_pass, spline_stride;     /* last-layer column layout (spline nets) */
+  int64_t total_floats;
+  /* tensor-core layout (tcgen05 path); NULL when not packed for it */
+  const float* Wk_hi[BGX_MAX_LAYERS];              /* device, [Np][Kp] K-major, tf32-truncated */
+  const float* Wk_lo[BGX_MAX_LAYERS];              /* device, residual W - hi */
+} bgx_packed_mlp;
+
+/* Last-layer re-layout request for a spline conditioner: the raw column layout of
+ * spline.py:113-125 ([W: d*K+b | H | S | S_last over non-circular dims]) becomes dim-major
+ * [W(K) H(K) S(K) S_end(1)] per transformed dim; circular dims get S_end := S[d][0]. */
+typedef struct bgx_spline_layout {
+  int32_t d_t;                 /* transformed width (0 = not a spline net) */
+  int32_t n_bins;
+  const uint8_t* is_circular;  /* HOST, d_t entries, NULL = none circular */
+} bgx_spline_layout;
+
+/* Pack `src` into `dst` (device, `dst_floats` floats).  With dst == NULL only the required
+ * size is computed (out->total_floats).  Launches small gather kernels on `stream` and does
+ * one small async host->device copy of index maps taken from `dst`'s tail. */
+int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline, float* dst,
+                 int64_t dst_floats, bgx_packed_mlp* out, void* stream);
+
+/* A column slice of the flow state: tensor `ptr` with `width` columns, row stride `stride`
+ * floats.  CouplingFlow concatenates several along the last dim (coupling.py:163-165). */
+typedef struct bgx_seg {
+  const float* ptr;
+  int32_t width;
+  int32_t stride;
+} bgx_seg;
+
+typedef struct bgx_coupling_io {
+  int64_t batch;
+  int32_t n_cond;
+  bgx_seg cond[BGX_MAX_SEGS];     /* conditioner inputs, concatenated in order */
+  int32_t n_tr;
+  bgx_seg tr_in[BGX_MAX_SEGS];    /* transformed inputs */
+  bgx_seg tr_out[BGX_MAX_SEGS];   /* outputs, same widths (ptr is written) */
+  const float* dlogp_in;          /* [batch] running log-det to add to, or NULL */
+  float* dlogp_out;               /* [batch] */
+} bgx_coupling_io;
+
+#define BGX_FLAG_INVERSE 1          /* evaluate bgflow's _inverse direction */
+#define BGX_FLAG_PRESERVE_VOLUME 2  /* affine.py:44-45 */
+#define BGX_FLAG_CIRCULAR 4         /* affine.py:56-57: y %= 1 (shift-only) */
+#define BGX_FLAG_TF32X1 8           /* tensor-core path: single-pass TF32 (default: 3xTF32 ~ fp32) */
+#define BGX_FLAG_FORCE_SIMT 16      /* always use the generic fp32 SIMT kernel */
+
+/* y' = y * exp(ls) + mu   (forward)   |   y' = (y - mu) * exp(-ls)   (inverse)
+ * mu = shift(cond), ls = tanh(scale(cond)) * exp(log_alpha);  dlogp = +-sum(ls).
+ * `shift` / `scale` may be NULL (zeros). */
+int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
+                        const bgx_packed_mlp* scale, float log_alpha, int flags, void* stream);
+
+typedef struct bgx_spline_cfg {
+  int32_t n_bins;
+  float left, right, bottom, top;
+  float min_bin_width, min_bin_height, min_derivative;
+  int32_t identity_init;   /* softplus beta = ln2/(1-min_derivative) (nflows PR #65) */
+  int32_t* oob_counter;    /* device int, incremented per out-of-domain input (or NULL) */
+} bgx_spline_cfg;
+
+/* bgflow forward  = nflows inverse=True  (quadratic-root branch, the sampling direction);
+ * bgflow inverse  = nflows inverse=False (direct rational-quadratic evaluation).
+ * Inputs outside [left, right] are clamped (== spline.py:145-155) and counted. */
+int bgx_spline_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* params_net,
+                        const bgx_spline_cfg* cfg, int flags, void* stream);
+
+/* ---- internal coordinates ------------------------------------------------------------- */
+
+/* Device-side plan of a global z-matrix (ic.py:25-97 staging done on the host). */
+typedef struct bgx_zplan {
+  int32_t n_atoms;
+  int32_t seeds[3];
+  int32_t n_rel;               /* n_atoms - 3 */
+  const int32_t* rel;          /* device, [n_rel][4] rows (i,j,k,l) in tensor column order */
+  const int32_t* order;        /* device, [n_rel] placement order (row ids) */
+  int32_t normalize_angles;
+  float eps;
+} bgx_zplan;
+
+/* x0: [batch,3] (x0_stride floats between rows; 0 broadcasts one origin), R: [batch,3] likewise */
+int bgx_ic_to_xyz(const bgx_zplan* plan, int64_t batch, const float* bonds, const float* angles,
+                  const float* torsions, const float* x0, int32_t x0_stride, const float* R,
+                  int32_t r_stride, float* xyz, const float* dlogp_in, float* dlogp_out,
+                  void* stream);
+
+int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, float* bonds,
+                    float* angles, float* torsions, float* x0, float* R, const float* dlogp_in,
+                    float* dlogp_out, void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+
+const char* bgx_version(void);
+const char* bgx_last_cuda_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t bgx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGFLOW_B200_H */

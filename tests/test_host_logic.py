@@ -1,0 +1,172 @@
+"""CPU-side tests: tuple plumbing (mirrors the reference's tests/nn/flow/test_coupling.py,
+test_sequential.py, test_inverted.py), z-matrix staging, the C ABI surface, and a 2-rank gloo
+run of the batch sharding used by bench.py.  No kernel is launched here."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import bgflow_b200 as bg
+from bgflow_b200 import _lib, engine
+from oracle import ic as oic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class DummyTransformer(bg.Transformer):
+    """tests/nn/flow/test_coupling.py:58-70: records what it was called with."""
+
+    def __init__(self):
+        super().__init__()
+        self.seen = None
+
+    def _forward(self, x, y, **kwargs):
+        self.seen = (x.shape, y.shape)
+        return y + 1.0, torch.ones(*y.shape[:-1], 1)
+
+    def _inverse(self, x, y, **kwargs):
+        return y - 1.0, -torch.ones(*y.shape[:-1], 1)
+
+
+def test_split_by_sizes_and_indices():
+    x = torch.arange(20.0).reshape(2, 10)
+    a, b, c, dlogp = bg.SplitFlow(2, 3)(x)
+    assert a.shape == (2, 2) and b.shape == (2, 3) and c.shape == (2, 5) and dlogp.shape == (2, 1)
+    y, d = bg.SplitFlow(2, 3)(a, b, c, inverse=True)
+    assert torch.equal(y, x) and torch.equal(d, torch.zeros(2, 1))
+    with pytest.raises(ValueError):
+        bg.SplitFlow(8, 3)(x)
+    split = bg.SplitFlow([0, 9], [1, 2, 3], [4, 5, 6, 7, 8])
+    a, b, c, _ = split(x)
+    assert torch.equal(a, x[:, [0, 9]])
+    y, _ = split(a, b, c, inverse=True)
+    assert torch.equal(y, x)
+    with pytest.raises(ValueError):
+        bg.SplitFlow([0, 1], [1, 2])(x)
+    with pytest.raises(ValueError):
+        bg.SplitFlow([0, 1], [2, 3])(x)
+
+
+def test_coupling_multiple_tensors_generic_transformer():
+    tr = DummyTransformer()
+    flow = bg.CouplingFlow(tr, transformed_indices=(0, 2), cond_indices=(1, 3))
+    xs = [torch.zeros(5, w) for w in (2, 3, 4, 1)]
+    *ys, dlogp = flow(*xs)
+    assert tr.seen == (torch.Size([5, 4]), torch.Size([5, 6]))
+    assert [y.shape[-1] for y in ys] == [2, 3, 4, 1]
+    assert torch.equal(ys[0], torch.ones(5, 2)) and torch.equal(ys[1], xs[1])
+    *zs, dinv = flow(*ys, inverse=True)
+    assert all(torch.equal(z, x) for z, x in zip(zs, xs)) and torch.equal(dlogp + dinv, torch.zeros(5, 1))
+    with pytest.raises(ValueError):
+        bg.CouplingFlow(tr, transformed_indices=(0, 1), cond_indices=(1,))
+
+
+def test_sequential_inverse_swap_wrap_setconstant():
+    tr = DummyTransformer()
+    flow = bg.SequentialFlow([bg.SplitFlow(3), bg.CouplingFlow(tr), bg.SwapFlow(), bg.CouplingFlow(tr),
+                              bg.SwapFlow(), bg.MergeFlow(3)])
+    x = torch.randn(4, 7)
+    y, dlogp = flow(x)
+    assert y.shape == (4, 7) and dlogp.shape == (4, 1) and torch.equal(dlogp, 2 * torch.ones(4, 1))
+    xb, dinv = flow(y, inverse=True)
+    torch.testing.assert_close(xb, x)
+    torch.testing.assert_close(dlogp + dinv, torch.zeros(4, 1))
+    inv = bg.InverseFlow(flow)
+    xb2, dinv2 = inv(y)
+    torch.testing.assert_close(xb2, x)
+    assert len(flow) == 6 and isinstance(flow[1], bg.CouplingFlow) and len(flow[1:3]) == 2
+    a, b, d = bg.SwapFlow()(torch.zeros(2, 1), torch.ones(2, 2))
+    assert a.shape == (2, 2) and d.shape == (2, 1)
+    with pytest.warns(UserWarning):
+        bg.SwapFlow()(torch.zeros(2, 1))
+    wrapped = bg.WrapFlow(bg.SwapFlow(), indices=(0, 2))
+    p, q, r, d = wrapped(torch.zeros(2, 1), torch.ones(2, 2), 2 * torch.ones(2, 3))
+    assert p.shape == (2, 3) and q.shape == (2, 2) and r.shape == (2, 1)
+    p2, q2, r2, _ = wrapped(p, q, r, inverse=True)
+    assert p2.shape == (2, 1) and r2.shape == (2, 3)
+    const = bg.SetConstantFlow([1], [torch.tensor([7.0, 8.0])])
+    a, c, d = const(torch.zeros(3, 2))
+    assert c.shape == (3, 2) and torch.equal(c[0], torch.tensor([7.0, 8.0])) and d.shape == (3, 1)
+    (a2, d2) = const(a, c, inverse=True)
+    assert a2.shape == (3, 2)
+
+
+def test_transformers_refuse_cpu_tensors():
+    tr = bg.AffineTransformer(bg.DenseNet([2, 4, 3], activation=torch.nn.ReLU()))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tr.forward(torch.zeros(4, 2), torch.zeros(4, 3))
+    sp = bg.ConditionalSplineTransformer(bg.DenseNet([2, 4, 3 * 25]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sp.forward(torch.zeros(4, 2), torch.zeros(4, 3))
+    with pytest.raises(ValueError):
+        bg.AffineTransformer(bg.DenseNet([2, 3]), bg.DenseNet([2, 3]), is_circular=True)
+
+
+def test_state_dict_layout_matches_reference_densenet():
+    net = bg.DenseNet([3, 8, 8, 5], activation=torch.nn.SiLU())
+    assert list(net.state_dict().keys()) == ["_layers.0.weight", "_layers.0.bias", "_layers.2.weight",
+                                             "_layers.2.bias", "_layers.4.weight", "_layers.4.bias"]
+    assert net(torch.zeros(2, 3)).shape == (2, 5)
+    wp = bg.WrapPeriodic(bg.DenseNet([5, 4]), indices=[0, 2])
+    assert wp(torch.zeros(2, 3)).shape == (2, 4)
+
+
+def test_zplan_staging():
+    plan = engine.ZPlan(oic.ALA2_GLOBAL_Z)
+    assert plan.seeds == [0, 1, 2] and len(plan.rel) == 19 and sorted(plan.order) == list(range(19))
+    placed = set(plan.seeds)
+    for r in plan.order:
+        i, j, k, l = plan.rel[r]
+        assert {j, k, l} <= placed
+        placed.add(i)
+    ref = oic.make_plan(oic.ALA2_GLOBAL_Z)
+    assert plan.seeds == ref.seeds and np.array_equal(plan.rel, ref.rel)
+    with pytest.raises(ValueError):
+        engine.ZPlan(np.array([[0, -1, -1, -1], [1, 0, -1, -1], [2, 1, 0, -1], [3, 4, 1, 0], [4, 3, 1, 0]]))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib = _lib.load()                       # builds the .so if it is missing; raises if it cannot
+    header = open(os.path.join(ROOT, "include", "bgflow_b200.h")).read()
+    declared = set(re.findall(r"\b(bgx_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.bgx_version().startswith(b"bgflow_b200")
+    assert lib.bgx_launch_count() >= 0
+    # size-only pack query runs without a GPU: 33 -> 128 -> 128 -> 825 spline conditioner
+    src = _lib.bgx_mlp()
+    src.n_layers = 3
+    for i, d in enumerate((33, 128, 128, 825)):
+        src.dims[i] = d
+    src.raw_width = 33
+    lay = _lib.bgx_spline_layout()
+    lay.d_t, lay.n_bins = 33, 8
+    out = _lib.bgx_packed_mlp()
+    assert lib.bgx_pack_mlp(ctypes.byref(src), ctypes.byref(lay), None, 0, ctypes.byref(out), None) == 0
+    assert out.spline_dims_per_pass == 5 and out.spline_stride == 25 and out.N[2] == 7 * 128
+    assert out.total_floats > 128 * 896
+    src.dims[3] = 826                       # wrong width: spline.py:112-121 raises
+    assert lib.bgx_pack_mlp(ctypes.byref(src), ctypes.byref(lay), None, 0, ctypes.byref(out), None) == -1
+
+
+def test_two_rank_gloo_sharding():
+    """bench.py's multi-GPU plumbing (rank-sharded batch, max-over-ranks timing) on 2 CPU ranks."""
+    env = dict(os.environ, BGX_BENCH_DRYRUN="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "bench.py"),
+           "--gpus", "2", "--steps", "2", "--warmup", "1"]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["n_gpus"] == 2 and rec["dryrun"] is True and rec["scaling"] == "weak"
+    assert rec["shard_rows"] == [rec["config"]["batch_per_gpu"]] * 2
