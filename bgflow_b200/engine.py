@@ -167,6 +167,8 @@ def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_v
     shift / scale: ``bgx_packed_mlp`` or None.  Returns (list of outputs, dlogp [.., 1])."""
     lib = _lib.load()
     io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
+    if io.batch == 0:
+        return outs, dlogp
     f = flags | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
         | (_lib.FLAG_CIRCULAR if is_circular else 0)
     rc = lib.bgx_affine_coupling(C.byref(io), C.byref(shift) if shift is not None else None,
@@ -180,6 +182,8 @@ def spline_coupling(cond, tr, net, n_bins, inverse=False, left=0.0, right=1.0, b
                     oob_counter=None, dlogp_in=None, flags=0):
     lib = _lib.load()
     io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
+    if io.batch == 0:
+        return outs, dlogp
     cfg = _lib.bgx_spline_cfg()
     cfg.n_bins = n_bins
     cfg.left, cfg.right, cfg.bottom, cfg.top = float(left), float(right), float(bottom), float(top)
@@ -269,6 +273,8 @@ def ic_to_xyz(plan, bonds, angles, torsions, x0, R, dlogp_in=None):
     xyz = torch.empty(B, 3 * n, dtype=torch.float32, device=bonds.device)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
     din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    if B == 0:
+        return xyz, dlogp
     rc = lib.bgx_ic_to_xyz(C.byref(plan.device_plan(bonds.device)), B, bonds.data_ptr(), angles.data_ptr(),
                            torsions.data_ptr(), x0f.data_ptr(), 3 if x0f.shape[0] == B else 0,
                            Rf.data_ptr(), 3 if Rf.shape[0] == B else 0, xyz.data_ptr(),
@@ -293,6 +299,8 @@ def ic_from_xyz(plan, xyz, dlogp_in=None):
     R = torch.empty(B, 3, dtype=torch.float32, device=dev)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
     din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    if B == 0:
+        return bonds, angles, torsions, x0, R, dlogp
     rc = lib.bgx_ic_from_xyz(C.byref(plan.device_plan(dev)), B, x.data_ptr(), bonds.data_ptr(), angles.data_ptr(),
                              torsions.data_ptr(), x0.data_ptr(), R.data_ptr(),
                              din.data_ptr() if din is not None else None, dlogp.data_ptr(), _stream())
