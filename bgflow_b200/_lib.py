@@ -88,6 +88,8 @@ SYMBOLS = {
     "bgx_ic_from_xyz": (C.c_int, [P(bgx_zplan), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "bgx_tc_selftest": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "bgx_version": (C.c_char_p, []),
     "bgx_last_cuda_error": (C.c_char_p, []),
     "bgx_launch_count": (C.c_int64, []),

@@ -1,0 +1,139 @@
+// Self-test of the tcgen05 building blocks used by the tensor-core coupling kernel:
+// one CTA computes out[128][128] = A[128][K] . W[128][K]^T with
+//   mode 0: A and B from shared memory (SS, both K-major SWIZZLE_128B tiles)
+//   mode 1: A from tensor memory (TS), B from shared memory
+// B tiles arrive through 1-D bulk TMA copies of pre-swizzled tiles, the accumulator lives in
+// TMEM and is read back with tcgen05.ld.  tests/test_gpu_tc.py checks it against exact integer
+// products, so every descriptor bit is validated before the big kernel relies on it.
+#include "bgx_common.cuh"
+#include "bgx_tc.cuh"
+
+namespace bgx {
+using namespace tc;
+
+constexpr int ST_ACC_COL = 0;
+constexpr int ST_A_COL = 128;
+
+// W [128][K] row-major -> K/32 tiles of [128 x 32] fp32, each 16 KB, 128-B swizzled
+__global__ void st_swizzle_w(const float* __restrict__ W, int K, float* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * K) return;
+  int n = idx / K, k = idx % K;
+  int tile = k / 32, kk = k % 32;
+  out[tile * 4096 + sw128_offset(n, kk) / 4] = W[idx];
+}
+
+__global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* __restrict__ A,
+                                                         const float* __restrict__ Wsw, int K,
+                                                         float* __restrict__ out, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // 1024-B aligned carve-up
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  float* Bs = (float*)base;                    // K/32 tiles x 16 KB
+  float* As = (float*)(base + 4 * 16384);      // K/32 tiles x 16 KB (SS mode)
+  uint64_t* bars = (uint64_t*)(base + 8 * 16384);
+  uint64_t* b_full = bars + 0;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* acc_full = bars + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = K / 32;
+  if (threadIdx.x == 0) {
+    mbar_init(b_full, 1);
+    mbar_init(a_ready, 4);
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)ntile * 16384u);
+      for (int t = 0; t < ntile; ++t) bulk_g2s(Bs + t * 4096, Wsw + t * 4096, 16384u, b_full);
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      bool ok = mbar_wait(b_full, 0, status) && mbar_wait(a_ready, 0, status);
+      tc_fence_after();
+      if (ok) {
+        const uint32_t idesc = idesc_tf32(128, 128);
+        for (int ks = 0; ks < K / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
+          const uint64_t bd = smem_desc_sw128(smem_u32(Bs) + off);
+          if (mode == 1) {
+            mma_tf32_ts(tmem + ST_ACC_COL, tmem + ST_A_COL + ks * 8, bd, idesc, ks > 0);
+          } else {
+            const uint64_t ad = smem_desc_sw128(smem_u32(As) + off);
+            mma_tf32_ss(tmem + ST_ACC_COL, ad, bd, idesc, ks > 0);
+          }
+        }
+      }
+      mma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // warps 0..3: TMEM lane quadrant = warp id
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    if (mode == 1) {
+      for (int c = 0; c < ntile; ++c) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(A[row * K + c * 32 + j]);
+        tmem_st32(tmem + lane_base + ST_A_COL + c * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    } else {
+      for (int k = 0; k < K; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(A + row * K + k);
+        *reinterpret_cast<float4*>((uint8_t*)As + (k / 32) * 16384 + sw128_offset(row, k % 32)) = v;
+      }
+      fence_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+    mbar_wait(acc_full, 0, status);
+    tc_fence_after();
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + lane_base + ST_ACC_COL + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) out[row * 128 + c * 32 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+}  // namespace bgx
+
+using namespace bgx;
+
+// A [128][K], W [128][K] (K multiple of 32, <= 128), scratch >= 128*K floats, out [128][128],
+// status: device int, set to 1 if an mbarrier wait timed out.
+extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
+                               int* status, void* stream) {
+  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode != 0 && mode != 1))
+    return BGX_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  st_swizzle_w<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, scratch);
+  int rc = post_launch();
+  if (rc) return rc;
+  const int smem_bytes = 8 * 16384 + 1024 + 256;
+  rc = check(cudaFuncSetAttribute(st_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (rc) return rc;
+  st_gemm_kernel<<<1, 192, smem_bytes, st>>>(mode, A, scratch, K, out, status);
+  return post_launch();
+}

@@ -168,6 +168,12 @@ int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, floa
 
 /* ---- misc -------------------------------------------------------------------------------- */
 
+/* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T
+ * on one CTA (mode 0: A from shared memory, mode 1: A from tensor memory).  K in {32,64,96,128};
+ * scratch >= 128*K floats; *status (device int) becomes 1 if a barrier wait timed out. */
+int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
+                    int* status, void* stream);
+
 const char* bgx_version(void);
 const char* bgx_last_cuda_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
