@@ -64,7 +64,7 @@ class bgx_spline_cfg(C.Structure):
     _fields_ = [("n_bins", C.c_int32), ("left", C.c_float), ("right", C.c_float),
                 ("bottom", C.c_float), ("top", C.c_float), ("min_bin_width", C.c_float),
                 ("min_bin_height", C.c_float), ("min_derivative", C.c_float),
-                ("identity_init", C.c_int32), ("oob_counter", C.c_void_p)]
+                ("identity_init", C.c_int32), ("oob_counter", C.c_void_p), ("status", C.c_void_p)]
 
 
 class bgx_zplan(C.Structure):

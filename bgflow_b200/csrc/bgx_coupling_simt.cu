@@ -9,7 +9,7 @@
 //
 // The tensor-core (tcgen05) kernel in bgx_coupling_tc.cu covers the headline shapes; this
 // kernel is the fallback for every other shape and the numerical cross-check of that one.
-#include "bgx_common.cuh"
+#include "bgx_coupling.cuh"
 
 namespace bgx {
 
@@ -19,46 +19,6 @@ constexpr int KC = 16;    // k-chunk
 constexpr int NT = 256;   // threads
 constexpr int LDA = TM + 4;
 constexpr int LDP = NC + 1;
-
-struct DevMlp {
-  int n_layers, act;
-  int K[BGX_MAX_LAYERS], N[BGX_MAX_LAYERS], Kp[BGX_MAX_LAYERS], Np[BGX_MAX_LAYERS];
-  const float* Wt[BGX_MAX_LAYERS];
-  const float* bias[BGX_MAX_LAYERS];
-  const int* in_map;
-  float pscale, pleft;
-};
-
-struct Segs {
-  int n;
-  const float* ptr[BGX_MAX_SEGS];
-  int width[BGX_MAX_SEGS];
-  int stride[BGX_MAX_SEGS];
-};
-
-struct CouplingArgs {
-  long long B;
-  Segs cond, tin, tout;
-  int D_t;
-  DevMlp net0, net1;  // affine: shift, scale ; spline: params_net, -
-  int has0, has1;
-  float alpha;
-  int flags;
-  int dpp, pstride;   // spline column layout
-  SplineParams sp;
-  const float* dlogp_in;
-  float* dlogp_out;
-  int hb;             // rows of each activation buffer
-};
-
-__device__ __forceinline__ const float* seg_addr(const Segs& s, long long row, int col) {
-  int i = 0;
-  while (i < s.n - 1 && col >= s.width[i]) {
-    col -= s.width[i];
-    ++i;
-  }
-  return s.ptr[i] + row * (long long)s.stride[i] + col;
-}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -88,17 +48,9 @@ __device__ __forceinline__ void load_w_chunk(float* dst, const float* __restrict
   }
 }
 
-// layer-0 input element (row m of the tile, input column k) with WrapPeriodic folded in
 __device__ __forceinline__ float load_input(const CouplingArgs& a, const DevMlp& net, long long row0, int m,
                                             int k) {
-  long long row = row0 + m;
-  if (row >= a.B || k >= net.K[0]) return 0.f;
-  int code = net.in_map[k];
-  int col = code & 0xffffff, kind = code >> 24;
-  float v = __ldg(seg_addr(a.cond, row, col));
-  if (kind == 0) return v;
-  float arg = (v - net.pleft) * net.pscale;
-  return kind == 1 ? cosf(arg) : sinf(arg);
+  return load_cond(a.cond, net, a.B, row0 + m, k);
 }
 
 // acc[4][8] (rows ty*4+i, cols n0 + {tx*4+j, 64+tx*4+j}) = A . Wt[:, n0:n0+128]
@@ -362,7 +314,7 @@ __global__ void __launch_bounds__(NT, 2) coupling_simt_kernel(const CouplingArgs
 
 // ------------------------------------------------------------------------------ host side
 
-static void to_dev(const bgx_packed_mlp* p, DevMlp& d) {
+void mlp_to_dev(const bgx_packed_mlp* p, DevMlp& d) {
   d.n_layers = p->n_layers;
   d.act = p->act;
   for (int i = 0; i < p->n_layers; ++i) {
@@ -374,7 +326,7 @@ static void to_dev(const bgx_packed_mlp* p, DevMlp& d) {
   d.pleft = p->periodic_left;
 }
 
-static int fill_io(const bgx_coupling_io* io, CouplingArgs& a, int& d_c, int& d_t) {
+int coupling_fill_io(const bgx_coupling_io* io, CouplingArgs& a, int& d_c, int& d_t) {
   if (!io || io->batch < 0 || io->n_cond < 0 || io->n_cond > BGX_MAX_SEGS || io->n_tr < 1 ||
       io->n_tr > BGX_MAX_SEGS || !io->dlogp_out)
     return BGX_ERR_INVALID;
@@ -395,6 +347,15 @@ static int fill_io(const bgx_coupling_io* io, CouplingArgs& a, int& d_c, int& d_
   a.dlogp_in = io->dlogp_in;
   a.dlogp_out = io->dlogp_out;
   return BGX_OK;
+}
+
+void spline_params_from_cfg(const bgx_spline_cfg* cfg, SplineParams& sp) {
+  sp.K = cfg->n_bins;
+  sp.left = cfg->left; sp.right = cfg->right; sp.bottom = cfg->bottom; sp.top = cfg->top;
+  sp.min_w = cfg->min_bin_width; sp.min_h = cfg->min_bin_height; sp.min_d = cfg->min_derivative;
+  sp.beta = cfg->identity_init ? (float)(0.6931471805599453 / (1.0 - (double)cfg->min_derivative)) : 1.f;
+  sp.inv_beta = 1.f / sp.beta;
+  sp.oob = cfg->oob_counter;
 }
 
 static int hidden_rows(const bgx_packed_mlp* p) {
@@ -430,7 +391,7 @@ int affine_coupling_simt(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
                          float log_alpha, int flags, cudaStream_t st) {
   CouplingArgs a{};
   int d_c, d_t;
-  int rc = fill_io(io, a, d_c, d_t);
+  int rc = coupling_fill_io(io, a, d_c, d_t);
   if (rc) return rc;
   a.has0 = shift != nullptr;
   a.has1 = scale != nullptr;
@@ -441,8 +402,8 @@ int affine_coupling_simt(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
     a.hb = max(a.hb, hidden_rows(p));
   }
   if ((flags & BGX_FLAG_CIRCULAR) && scale) return BGX_ERR_INVALID;  // affine.py:26-27
-  if (shift) to_dev(shift, a.net0);
-  if (scale) to_dev(scale, a.net1);
+  if (shift) mlp_to_dev(shift, a.net0);
+  if (scale) mlp_to_dev(scale, a.net1);
   a.alpha = expf(log_alpha);
   a.flags = flags;
   return (flags & BGX_FLAG_INVERSE) ? launch<false, true>(a, st) : launch<false, false>(a, st);
@@ -452,24 +413,19 @@ int spline_coupling_simt(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
                          int flags, cudaStream_t st) {
   CouplingArgs a{};
   int d_c, d_t;
-  int rc = fill_io(io, a, d_c, d_t);
+  int rc = coupling_fill_io(io, a, d_c, d_t);
   if (rc) return rc;
   if (!net || !cfg || net->n_layers < 1 || net->raw_width != d_c) return BGX_ERR_INVALID;
   const int K = cfg->n_bins;
   if (K < 1 || net->spline_stride != 3 * K + 1 || net->spline_dims_per_pass < 1) return BGX_ERR_INVALID;
   if (net->N[net->n_layers - 1] != ceil_div(d_t, net->spline_dims_per_pass) * NC) return BGX_ERR_INVALID;
   if (cfg->min_bin_width * K > 1.f || cfg->min_bin_height * K > 1.f) return BGX_ERR_INVALID;
-  to_dev(net, a.net0);
+  mlp_to_dev(net, a.net0);
   a.has0 = 1;
   a.hb = hidden_rows(net);
   a.dpp = net->spline_dims_per_pass;
   a.pstride = net->spline_stride;
-  a.sp.K = K;
-  a.sp.left = cfg->left; a.sp.right = cfg->right; a.sp.bottom = cfg->bottom; a.sp.top = cfg->top;
-  a.sp.min_w = cfg->min_bin_width; a.sp.min_h = cfg->min_bin_height; a.sp.min_d = cfg->min_derivative;
-  a.sp.beta = cfg->identity_init ? (float)(0.6931471805599453 / (1.0 - (double)cfg->min_derivative)) : 1.f;
-  a.sp.inv_beta = 1.f / a.sp.beta;
-  a.sp.oob = cfg->oob_counter;
+  spline_params_from_cfg(cfg, a.sp);
   a.flags = flags;
   return (flags & BGX_FLAG_INVERSE) ? launch<true, true>(a, st) : launch<true, false>(a, st);
 }

@@ -28,19 +28,25 @@ __global__ void pack_transpose_kernel(const float* __restrict__ W, const float* 
   }
 }
 
-// K-major tf32 split for the tensor-core path: hi = tf32-truncated W, lo = W - hi
-__global__ void pack_kmajor_split_kernel(const float* __restrict__ W, const int* __restrict__ row_map, int K,
-                                         int N, int Kp, int Np, float* __restrict__ hi,
-                                         float* __restrict__ lo) {
+// Tensor-core layout: per 128-row chunk of W and per 32-wide k-tile one 16 KB tile
+// [128 rows][32 k] fp32, K-major, rows of 128 B with the 16-B chunks XOR-swizzled by (row & 7)
+// (the UMMA SWIZZLE_128B canonical layout), so that ONE 1-D bulk copy lands a ready operand tile
+// in shared memory.  hi = W truncated to tf32, lo = W - hi (the 3xTF32 split).
+__global__ void pack_tc_tiles_kernel(const float* __restrict__ W, const int* __restrict__ row_map, int K,
+                                     int N, int ktiles, int Np, float* __restrict__ hi,
+                                     float* __restrict__ lo) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)Kp * Np;
+  long long total = (long long)Np * ktiles * 32;
   if (idx >= total) return;
-  int k = (int)(idx % Kp), n = (int)(idx / Kp);
+  int k = (int)(idx % (ktiles * 32)), n = (int)(idx / (ktiles * 32));
   int r = row_map ? row_map[n] : (n < N ? n : -1);
   float w = (r >= 0 && k < K) ? W[(long long)r * K + k] : 0.f;
   float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-  hi[idx] = h;
-  lo[idx] = w - h;
+  int chunk = n >> 7, nr = n & 127, t = k >> 5, kk = k & 31;
+  long long off = ((long long)chunk * ktiles + t) * 4096 +
+                  (nr * 32 + ((((kk >> 2) ^ (nr & 7)) << 2) | (kk & 3)));
+  hi[off] = h;
+  lo[off] = w - h;
 }
 
 static int spline_dims_per_pass(int n_bins) { return 128 / (3 * n_bins + 1); }
@@ -98,7 +104,7 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
       last_map[n] = r;
     }
   }
-  // layout: [Wt_l | bias_l]* , [Wk_hi_l | Wk_lo_l]* (K-major, Kp rounded to 32), in_map, last_map
+  // layout: [Wt_l | bias_l]* , [Wk_hi_l | Wk_lo_l]* (16 KB swizzled tiles), in_map, last_map
   int64_t off = 0;
   int64_t o_wt[BGX_MAX_LAYERS], o_b[BGX_MAX_LAYERS], o_hi[BGX_MAX_LAYERS], o_lo[BGX_MAX_LAYERS];
   int kp32[BGX_MAX_LAYERS];
@@ -106,6 +112,7 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
     o_wt[l] = off; off += (int64_t)pk.Kp[l] * pk.Np[l];
     o_b[l] = off; off += pk.Np[l];
   }
+  off = (off + 255) / 256 * 256;  // tiles are bulk-copied: keep them 1 KB aligned
   for (int l = 0; l < L; ++l) {
     kp32[l] = round_up(pk.K[l], 32);
     o_hi[l] = off; off += (int64_t)kp32[l] * pk.Np[l];
@@ -120,7 +127,7 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
     return BGX_OK;
   }
   if (dst_floats < off) return BGX_ERR_WORKSPACE;
-  if (((uintptr_t)dst & 15) != 0) return BGX_ERR_INVALID;
+  if (((uintptr_t)dst & 255) != 0) return BGX_ERR_INVALID;  // torch allocations are 512-B aligned
 
   // conditioner input map (periodic.py:30-37): cos block, sin block, then the other columns
   std::vector<int> in_map(pk.Kp[0], 0);
@@ -166,8 +173,8 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
     rc = post_launch();
     if (rc) return rc;
     long long total2 = (long long)kp32[l] * pk.Np[l];
-    pack_kmajor_split_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
-        src->W[l], rmap, pk.K[l], n_true, kp32[l], pk.Np[l], dst + o_hi[l], dst + o_lo[l]);
+    pack_tc_tiles_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
+        src->W[l], rmap, pk.K[l], n_true, kp32[l] / 32, pk.Np[l], dst + o_hi[l], dst + o_lo[l]);
     rc = post_launch();
     if (rc) return rc;
     pk.Wt[l] = wt;

@@ -36,8 +36,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout the flag is raised and the
 // caller carries on (results are garbage, the host reports BGX_ERR_CUDA-like failure).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* timeout_flag) {
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
     if (mbar_try_wait(bar, parity)) return true;
+    // once any wait has timed out the whole kernel drains quickly instead of timing out again
+    if ((it & 0x3ff) == 0x3ff && timeout_flag && *(volatile int*)timeout_flag) return false;
   }
   if (timeout_flag) atomicExch(timeout_flag, 1);
   return false;

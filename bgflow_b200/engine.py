@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 __all__ = ["PackedNet", "affine_coupling", "spline_coupling", "ic_to_xyz", "ic_from_xyz", "ZPlan",
-           "require_cuda_fp32"]
+           "require_cuda_fp32", "config", "pipeline_status", "check_pipeline_status"]
 
 
 def require_cuda_fp32(*tensors):
@@ -28,6 +28,40 @@ def require_cuda_fp32(*tensors):
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+#: kernel selection: ``precision`` "3xtf32" (default; fp32-accurate tensor-core math) or "tf32"
+#: (single-pass TF32, ~1e-3 relative error in the conditioner); ``force_simt`` runs the
+#: shape-general fp32 SIMT kernel even where the tensor-core kernel applies.
+config = {"precision": "3xtf32", "force_simt": False}
+
+_status = {}
+
+
+def pipeline_status(device):
+    """Device int32 flag the tensor-core kernels raise if their internal barrier protocol
+    times out (a bug, never an input property).  ``check_pipeline_status`` reads it back."""
+    key = torch.device(device)
+    if key not in _status:
+        _status[key] = torch.zeros(1, dtype=torch.int32, device=key)
+    return _status[key]
+
+
+def check_pipeline_status(device):
+    """Synchronising check used by tests / smoke: raises if a kernel flagged a pipeline timeout."""
+    if int(pipeline_status(device).item()) != 0:
+        raise _lib.BgxError("tensor-core coupling kernel reported an internal pipeline timeout")
+
+
+def _mode_flags():
+    f = 0
+    if config.get("force_simt"):
+        f |= _lib.FLAG_FORCE_SIMT
+    if config.get("precision") == "tf32":
+        f |= _lib.FLAG_TF32X1
+    elif config.get("precision") != "3xtf32":
+        raise ValueError("engine.config['precision'] must be '3xtf32' or 'tf32'")
+    return f
 
 
 _ACT_CODES = {type(None): _lib.ACT_NONE, torch.nn.ReLU: _lib.ACT_RELU, torch.nn.SiLU: _lib.ACT_SILU,
@@ -169,7 +203,7 @@ def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_v
     io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
     if io.batch == 0:
         return outs, dlogp
-    f = flags | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
+    f = flags | _mode_flags() | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
         | (_lib.FLAG_CIRCULAR if is_circular else 0)
     rc = lib.bgx_affine_coupling(C.byref(io), C.byref(shift) if shift is not None else None,
                                  C.byref(scale) if scale is not None else None, float(log_alpha), f, _stream())
@@ -190,7 +224,8 @@ def spline_coupling(cond, tr, net, n_bins, inverse=False, left=0.0, right=1.0, b
     cfg.min_bin_width, cfg.min_bin_height, cfg.min_derivative = min_bin_width, min_bin_height, min_derivative
     cfg.identity_init = 1 if identity_init else 0
     cfg.oob_counter = oob_counter.data_ptr() if oob_counter is not None else None
-    f = flags | (_lib.FLAG_INVERSE if inverse else 0)
+    cfg.status = pipeline_status(tr[0].device).data_ptr()
+    f = flags | _mode_flags() | (_lib.FLAG_INVERSE if inverse else 0)
     rc = lib.bgx_spline_coupling(C.byref(io), C.byref(net), C.byref(cfg), f, _stream())
     _lib.check(rc, "bgx_spline_coupling")
     return outs, dlogp

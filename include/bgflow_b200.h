@@ -79,8 +79,8 @@ typedef struct bgx_packed_mlp {
   int32_t spline_dims_per_pass, spline_stride;     /* last-layer column layout (spline nets) */
   int64_t total_floats;
   /* tensor-core layout (tcgen05 path); NULL when not packed for it */
-  const float* Wk_hi[BGX_MAX_LAYERS];              /* device, [Np][Kp] K-major, tf32-truncated */
-  const float* Wk_lo[BGX_MAX_LAYERS];              /* device, residual W - hi */
+  const float* Wk_hi[BGX_MAX_LAYERS];              /* device, 16 KB SWIZZLE_128B tiles [Np/128][ceil(K/32)][128x32], tf32-truncated W */
+  const float* Wk_lo[BGX_MAX_LAYERS];              /* device, same tiling, residual W - hi */
 } bgx_packed_mlp;
 
 /* Last-layer re-layout request for a spline conditioner: the raw column layout of
@@ -135,6 +135,8 @@ typedef struct bgx_spline_cfg {
   float min_bin_width, min_bin_height, min_derivative;
   int32_t identity_init;   /* softplus beta = ln2/(1-min_derivative) (nflows PR #65) */
   int32_t* oob_counter;    /* device int, incremented per out-of-domain input (or NULL) */
+  int32_t* status;         /* device int, set to 1 if the kernel's internal pipeline timed out
+                              (results invalid; never happens in a correct build) (or NULL) */
 } bgx_spline_cfg;
 
 /* bgflow forward  = nflows inverse=True  (quadratic-root branch, the sampling direction);

@@ -17,6 +17,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=["tc3x", "simt"], autouse=True)
+def kernel_mode(request):
+    """Every parity test runs on the tensor-core kernel (where the shape is eligible) and on the
+    shape-general SIMT kernel."""
+    from bgflow_b200 import engine
+    old = dict(engine.config)
+    engine.config.update(force_simt=(request.param == "simt"), precision="3xtf32")
+    yield request.param
+    engine.check_pipeline_status(DEV)
+    engine.config.update(old)
+
+
 def _t(a):
     return torch.from_numpy(np.asarray(a)).to(DEV)
 
@@ -180,3 +192,21 @@ def test_affine_transformer_api_like_reference_tests():
         bg.AffineTransformer(shift, scale_transformation=shift, is_circular=True)
     with pytest.raises(RuntimeError):
         tr.forward(x.cpu(), y.cpu())       # no CPU fallback, by design
+
+
+def test_single_pass_tf32_mode_has_the_stated_tolerance(kernel_mode):
+    """engine.config['precision'] = 'tf32': one TF32 MMA per product (10-bit mantissa inputs).
+    Stated tolerance over the 8-block stack: y 5e-3, dlogp 5e-2 (vs 1e-4 / 1e-3 for 3xTF32)."""
+    from bgflow_b200 import engine
+    if kernel_mode == "simt":
+        pytest.skip("tensor-core only")
+    g = load_golden("spline_d66_8blk")
+    blocks, split = of.make_stack("spline", 66, 8, hidden=(128, 128), seed=0)
+    flow = stack_from(blocks, split, DEV)
+    engine.config["precision"] = "tf32"
+    with torch.no_grad():
+        x, dlogp = flow(_t(g["z_f32"]))
+    _cmp(x, g["x_f64"], 5e-3, 5e-3)
+    _cmp(dlogp, g["dlogp_f64"], 5e-2, 1e-3)
+    err = (x.cpu().double() - torch.from_numpy(g["x_f64"])).abs().max().item()
+    assert err > 1e-7          # it really is the lower-precision path

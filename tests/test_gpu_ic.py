@@ -67,8 +67,10 @@ def test_large_molecule_global_memory_path():
     *ics, dlogp = ic(xyz.float().to(DEV))
     plan = oic.make_plan(z)
     ref = oic.xyz_to_ic(plan, xyz)
+    # a random-walk chain has some nearly collinear triples: torsions there are ill-conditioned
+    # (fp32 input rounding alone moves them by ~1e-4), hence 1e-3 here instead of 1e-4
     for got, want in zip(ics, ref):
-        np.testing.assert_allclose(got.cpu().double().numpy(), want.numpy(), atol=2e-4)
+        np.testing.assert_allclose(got.cpu().double().numpy(), want.numpy(), atol=1e-3)
     np.testing.assert_allclose(dlogp.cpu().double().numpy(), ref[-1].numpy(), rtol=1e-5, atol=5e-2)
     back, dinv = ic(*ics, inverse=True)
     # error accumulates along the 597-deep chain; the reference's own cuda-fp32 tolerance is 1e-2
