@@ -50,6 +50,9 @@ struct TcArgs {
   float* dlogp_out;
   int* status;       // device int: set to 1 when a barrier wait timed out
   long long ntiles;
+  int bias_floats;   // total bias floats staged in shared memory
+  int ldy;           // leading dimension of the staged y tile (odd: conflict-free per-row access)
+  int stages;        // weight ring depth
 };
 
 struct TcSmem {
@@ -60,6 +63,8 @@ struct TcSmem {
   uint64_t acc_full_h;   // hidden-layer accumulator complete
   uint64_t acc_full[2];  // last-layer chunk accumulator complete
   uint64_t acc_empty[2]; // 4 arrivals: chunk accumulator drained into registers
+  uint64_t y_full[2];    // 2 arrivals (I/O warps): transformed-input tile staged in shared memory
+  uint64_t y_done[2];    // 8 arrivals (epilogue warps): tile's outputs are in shared memory
   uint32_t tmem_base;
   uint32_t pad;
   float dl_part[TC_TM];
@@ -70,104 +75,139 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
-// One (sample, dim) spline evaluation with the 25 parameters in registers (NB = 8 bins).
-template <bool ROOT>
-__device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineParams& sp, float x, float& y,
-                                             float& lad) {
-  float mw = p[0], mh = p[NB];
-#pragma unroll
-  for (int k = 1; k < NB; ++k) {
-    mw = fmaxf(mw, p[k]);
-    mh = fmaxf(mh, p[NB + k]);
-  }
-  float ew[NB], eh[NB];
-  float sw = 0.f, sh = 0.f;
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    ew[k] = expf(p[k] - mw);
-    eh[k] = expf(p[NB + k] - mh);
-    sw += ew[k];
-    sh += eh[k];
-  }
-  const float cw_scale = (1.f - sp.min_w * NB) / sw;
-  const float ch_scale = (1.f - sp.min_h * NB) / sh;
-  const float wx = sp.right - sp.left, hy = sp.top - sp.bottom;
-  float cumw = 0.f, cumh = 0.f;
-  float kw_lo = sp.left, kh_lo = sp.bottom;
-  float bw_lo = sp.left, bw_hi = sp.right, bh_lo = sp.bottom, bh_hi = sp.top;
-  float s0 = p[2 * NB], s1 = p[2 * NB + 1];
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    cumw += sp.min_w + cw_scale * ew[k];
-    cumh += sp.min_h + ch_scale * eh[k];
-    const float kw_hi = (k == NB - 1) ? sp.right : fmaf(wx, cumw, sp.left);
-    const float kh_hi = (k == NB - 1) ? sp.top : fmaf(hy, cumh, sp.bottom);
-    const float knot = ROOT ? kh_lo : kw_lo;
-    if (k == 0 || x >= knot) {
-      bw_lo = kw_lo; bw_hi = kw_hi; bh_lo = kh_lo; bh_hi = kh_hi;
-      s0 = p[2 * NB + k];
-      s1 = p[2 * NB + k + 1];
-    }
-    kw_lo = kw_hi;
-    kh_lo = kh_hi;
-  }
-  const float w = bw_hi - bw_lo, h = bh_hi - bh_lo;
-  const float delta = h / w;
-  const float d0 = sp.min_d + softplus_beta(s0, sp.beta, sp.inv_beta);
-  const float d1 = sp.min_d + softplus_beta(s1, sp.beta, sp.inv_beta);
-  const float s = d0 + d1 - 2.f * delta;
-  if (ROOT) {
-    const float q = x - bh_lo;
-    const float a = q * s + h * (delta - d0);
-    const float b = h * d0 - q * s;
-    const float c = -delta * q;
-    const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
-    const float root = (2.f * c) / (-b - sqrtf(disc));
-    y = fmaf(root, w, bw_lo);
-    const float t1 = root * (1.f - root);
-    const float den = delta + s * t1;
-    const float omr = 1.f - root;
-    const float num = delta * delta * (d1 * root * root + 2.f * delta * t1 + d0 * omr * omr);
-    lad = -(logf(num) - 2.f * logf(den));
-  } else {
-    const float th = (x - bw_lo) / w;
-    const float t1 = th * (1.f - th);
-    const float den = delta + s * t1;
-    y = bh_lo + h * (delta * th * th + d0 * t1) / den;
-    const float omt = 1.f - th;
-    const float num = delta * delta * (d1 * th * th + 2.f * delta * t1 + d0 * omt * omt);
-    lad = logf(num) - 2.f * logf(den);
+// ---- fast special functions (MUFU): a few ulp, far inside the stated parity tolerance
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float act_fast(float x, int act) {
+  switch (act) {
+    case BGX_ACT_RELU: return fmaxf(x, 0.f);
+    case BGX_ACT_SILU: return x * rcp_fast(1.f + ex2_fast(-LOG2E * x));
+    case BGX_ACT_TANH: return 1.f - 2.f * rcp_fast(1.f + ex2_fast(2.f * LOG2E * x));
+    default: return x;
   }
 }
 
-// transform dim `d` of row `row` with the parameters v[0..24] (+ bias already added)
-__device__ __forceinline__ float do_dim(const TcArgs& a, const float (&p)[PS], long long row, int d) {
-  if (d >= a.D_t || row >= a.B) return 0.f;
-  float x = __ldg(seg_addr(a.tin, row, d));
-  if (x < a.sp.left || x > a.sp.right) {
+// per-kernel constants of the spline (uniform across threads)
+struct SplineK {
+  float left, right, bottom, top;
+  float wscale, hscale;   // (right-left)*(1-min_w*K), (top-bottom)*(1-min_h*K)
+  float wstep, hstep;     // (right-left)*min_w, (top-bottom)*min_h
+  float min_d, beta_l2e, ln2_over_beta, beta;
+};
+
+__device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
+  const float bs = c.beta * s;
+  const float v = lg2_fast(1.f + ex2_fast(fminf(s * c.beta_l2e, 64.f))) * c.ln2_over_beta;
+  return bs > 20.f ? s : v;
+}
+
+// One (sample, dim) spline evaluation with the 25 parameters in registers (NB = 8 bins).
+// Same algorithm as rqs_eval (bgx_common.cuh); the knots are formed from prefix sums of the
+// softmax numerators instead of a running sum of the normalised bins.
+template <bool ROOT>
+__device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK& c, float x, float& y,
+                                             float& lad) {
+  const float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
+  const float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
+  const float nmw = -mw * LOG2E, nmh = -mh * LOG2E;
+  float pw[NB], ph[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    pw[k] = ex2_fast(fmaf(p[k], LOG2E, nmw));
+    ph[k] = ex2_fast(fmaf(p[NB + k], LOG2E, nmh));
+  }
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    pw[k] += pw[k - 1];
+    ph[k] += ph[k - 1];
+  }
+  const float aw = c.wscale * rcp_fast(pw[NB - 1]);
+  const float ah = c.hscale * rcp_fast(ph[NB - 1]);
+  // knots 1..NB-1 (knot 0 = left/bottom, knot NB = right/top exactly)
+  float kw[NB + 1], kh[NB + 1];
+  kw[0] = c.left; kh[0] = c.bottom; kw[NB] = c.right; kh[NB] = c.top;
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    kw[k] = fmaf(aw, pw[k - 1], fmaf(c.wstep, (float)k, c.left));
+    kh[k] = fmaf(ah, ph[k - 1], fmaf(c.hstep, (float)k, c.bottom));
+  }
+  float w_lo = kw[0], w_hi = kw[1], h_lo = kh[0], h_hi = kh[1], s0 = p[2 * NB], s1 = p[2 * NB + 1];
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    const bool in = x >= (ROOT ? kh[k] : kw[k]);
+    w_lo = in ? kw[k] : w_lo;
+    w_hi = in ? kw[k + 1] : w_hi;
+    h_lo = in ? kh[k] : h_lo;
+    h_hi = in ? kh[k + 1] : h_hi;
+    s0 = in ? p[2 * NB + k] : s0;
+    s1 = in ? p[2 * NB + k + 1] : s1;
+  }
+  const float w = w_hi - w_lo, h = h_hi - h_lo;
+  const float rw = rcp_fast(w);
+  const float delta = h * rw;
+  const float d0 = c.min_d + softplus_fast(s0, c);
+  const float d1 = c.min_d + softplus_fast(s1, c);
+  const float s = d0 + d1 - 2.f * delta;
+  float th;
+  if (ROOT) {
+    const float q = x - h_lo;
+    const float qs = q * s;
+    const float a = fmaf(h, delta - d0, qs);
+    const float b = fmaf(h, d0, -qs);
+    const float cc = -delta * q;
+    const float disc = fmaxf(fmaf(b, b, -4.f * a * cc), 0.f);
+    th = 2.f * cc * rcp_fast(-b - sqrt_fast(disc));
+    y = fmaf(th, w, w_lo);
+  } else {
+    th = (x - w_lo) * rw;
+  }
+  const float omt = 1.f - th;
+  const float t1 = th * omt;
+  const float den = fmaf(s, t1, delta);
+  const float rden = rcp_fast(den);
+  if (!ROOT) y = fmaf(h * fmaf(delta * th, th, d0 * t1), rden, h_lo);
+  const float num = delta * delta * fmaf(d1 * th, th, fmaf(2.f * delta, t1, d0 * omt * omt));
+  const float l = logf(num * rden * rden);
+  lad = ROOT ? -l : l;
+}
+
+// transform dim `d` of this thread's sample: input from / output to the staged y tile
+template <bool INVERSE>
+__device__ __forceinline__ float do_dim(const TcArgs& a, const SplineK& ck, const float (&p)[PS], float* yrow,
+                                        int d) {
+  if (d >= a.D_t) return 0.f;
+  float x = yrow[d];
+  if (x < ck.left || x > ck.right) {
     if (a.sp.oob) atomicAdd(a.sp.oob, 1);
-    x = fminf(fmaxf(x, a.sp.left), a.sp.right);
+    x = fminf(fmaxf(x, ck.left), ck.right);
   }
   float y, lad;
-  if (a.inverse) rqs_eval_reg<false>(p, a.sp, x, y, lad);
-  else rqs_eval_reg<true>(p, a.sp, x, y, lad);
-  *const_cast<float*>(seg_addr(a.tout, row, d)) = y;
+  rqs_eval_reg<!INVERSE>(p, ck, x, y, lad);   // bgflow forward == root branch
+  yrow[d] = y;
   return lad;
 }
 
+template <bool INVERSE>
 __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = base;                                          // TC_STAGES x 16 KB
-  TcSmem* S = (TcSmem*)(base + TC_STAGES * TILE_BYTES);
+  uint8_t* ring = base;                                          // a.stages x 16 KB
+  TcSmem* S = (TcSmem*)(base + a.stages * TILE_BYTES);
   float* bias_s = (float*)(S + 1);                               // all layers' biases, concatenated
+  float* ybuf = bias_s + a.bias_floats;                          // 2 x [128][ldy] staged y tiles
+  const int NST = a.stages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.net.n_layers;
   const int nparts = a.x3 ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&S->full[s], 1);
       mbar_init(&S->empty[s], 1);
     }
@@ -178,6 +218,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     mbar_init(&S->acc_full[1], 1);
     mbar_init(&S->acc_empty[0], 4);
     mbar_init(&S->acc_empty[1], 4);
+    mbar_init(&S->y_full[0], 2);
+    mbar_init(&S->y_full[1], 2);
+    mbar_init(&S->y_done[0], 8);
+    mbar_init(&S->y_done[1], 8);
     fence_mbar_init();
   }
   {  // biases -> shared memory (layer l at offset boff[l])
@@ -209,7 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
                 const float* src = (part == 0 ? a.whi[l] : a.wlo[l]) + ((long long)c * kt + t) * 4096;
                 mbar_expect_tx(&S->full[stage], TILE_BYTES);
                 bulk_g2s(ring + stage * TILE_BYTES, src, TILE_BYTES, &S->full[stage]);
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == NST) { stage = 0; phase ^= 1; }
               }
         }
       }
@@ -247,12 +291,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
             for (int t = 0; t < kt; ++t) {
               const int s_hi = stage;
               mbar_wait(&S->full[s_hi], phase, a.status);
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == NST) { stage = 0; phase ^= 1; }
               int s_lo = -1;
               if (nparts == 2) {
                 s_lo = stage;
                 mbar_wait(&S->full[s_lo], phase, a.status);
-                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == NST) { stage = 0; phase ^= 1; }
               }
               tc_fence_after();
               const int nk = min(4, ksteps_total - t * 4);
@@ -278,6 +322,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       }
     }
     __syncwarp();
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ I/O warps: y tiles
+    // global <-> shared staging of the transformed inputs / outputs, coalesced, double buffered,
+    // so that the epilogue's dependency chain never waits on global memory
+    const int t64 = threadIdx.x - 64;
+    const int nelem = TC_TM * a.D_t;
+    auto load_tile = [&](long long tile, int b) {
+      float* Y = ybuf + b * TC_TM * a.ldy;
+#pragma unroll 8
+      for (int idx = t64; idx < nelem; idx += 64) {
+        const int r = idx / a.D_t, d = idx - r * a.D_t;
+        const long long row = tile * TC_TM + r;
+        Y[r * a.ldy + d] = row < a.B ? __ldg(seg_addr(a.tin, row, d)) : 0.5f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->y_full[b]);
+    };
+    long long n_my = (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    if (n_my > 0) load_tile(blockIdx.x, 0);
+    if (n_my > 1) load_tile(blockIdx.x + (long long)gridDim.x, 1);
+    for (long long it = 0; it < n_my; ++it) {
+      const int b = (int)(it & 1);
+      const long long tile = blockIdx.x + it * gridDim.x;
+      mbar_wait(&S->y_done[b], (uint32_t)((it >> 1) & 1), a.status);
+      const float* Y = ybuf + b * TC_TM * a.ldy;
+#pragma unroll 8
+      for (int idx = t64; idx < nelem; idx += 64) {
+        const int r = idx / a.D_t, d = idx - r * a.D_t;
+        const long long row = tile * TC_TM + r;
+        if (row < a.B) *const_cast<float*>(seg_addr(a.tout, row, d)) = Y[r * a.ldy + d];
+      }
+      if (it + 2 < n_my) {
+        asm volatile("bar.sync 3, 64;" ::: "memory");   // both I/O warps are done reading Y[b]
+        load_tile(tile + 2LL * gridDim.x, b);
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue groups
     const int g = (warp - 4) >> 2;            // 0 or 1
@@ -285,6 +365,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int gx = (a.npass - 1) & 1;         // the group that owns the last chunk stages x
+    SplineK ck;
+    {
+      const float wx = a.sp.right - a.sp.left, hy = a.sp.top - a.sp.bottom;
+      ck.left = a.sp.left; ck.right = a.sp.right; ck.bottom = a.sp.bottom; ck.top = a.sp.top;
+      ck.wscale = wx * (1.f - a.sp.min_w * NB); ck.hscale = hy * (1.f - a.sp.min_h * NB);
+      ck.wstep = wx * a.sp.min_w; ck.hstep = hy * a.sp.min_h;
+      ck.min_d = a.sp.min_d; ck.beta = a.sp.beta; ck.beta_l2e = a.sp.beta * LOG2E;
+      ck.ln2_over_beta = LN2 * a.sp.inv_beta;
+    }
     uint32_t ph_h = 0, ph_f = 0;
     const int last_off = [&] { int o = 0; for (int l = 0; l < L - 1; ++l) o += a.net.Np[l]; return o; }();
 
@@ -308,8 +397,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     };
 
     bool first = true;
-    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const long long row = tile * TC_TM + r_in_tile;
+      const int yb = (int)(it & 1);
+      float* yrow = ybuf + yb * TC_TM * a.ldy + r_in_tile * a.ldy;
       if (first && g == gx) stage_x(tile);
       first = false;
       // ---- hidden layers: ACC0 -> bias + activation -> A operand of the next layer
@@ -326,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float h = act_apply(__uint_as_float(v[j]) + bias_s[boff + col + j], a.net.act);
+            float h = act_fast(__uint_as_float(v[j]) + bias_s[boff + col + j], a.net.act);
             split_tf32(h, hi[j], lo[j]);
           }
           tmem_st32(tmem + lane_base + COL_AHI + col, hi);
@@ -340,6 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       }
       // ---- last layer: chunks c = g, g+2, ...  (5 dims x 25 parameters per 128 columns)
       float ld = 0.f;
+      mbar_wait(&S->y_full[yb], (uint32_t)((it >> 1) & 1), a.status);
       for (int c = g; c < a.npass; c += 2) {
         mbar_wait(&S->acc_full[g], ph_f, a.status);
         ph_f ^= 1;
@@ -354,12 +447,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         const int d0 = c * DPP;
 #pragma unroll
         for (int j = 0; j < 25; ++j) p[j] = __uint_as_float(A[j]) + bl[j];
-        ld += do_dim(a, p, row, d0 + 0);
+        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 0);
 #pragma unroll
         for (int j = 0; j < 7; ++j) p[j] = __uint_as_float(A[25 + j]) + bl[25 + j];
 #pragma unroll
         for (int j = 0; j < 18; ++j) p[7 + j] = __uint_as_float(Bv[j]) + bl[32 + j];
-        ld += do_dim(a, p, row, d0 + 1);
+        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 1);
         tmem_ld32(acc_addr + 64, C);
         tmem_ld32(acc_addr + 96, D);
         tmem_ld_wait();
@@ -378,16 +471,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         for (int j = 0; j < 14; ++j) p[j] = __uint_as_float(Bv[18 + j]) + bl[50 + j];
 #pragma unroll
         for (int j = 0; j < 11; ++j) p[14 + j] = __uint_as_float(C[j]) + bl[64 + j];
-        ld += do_dim(a, p, row, d0 + 2);
+        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 2);
 #pragma unroll
         for (int j = 0; j < 21; ++j) p[j] = __uint_as_float(C[11 + j]) + bl[75 + j];
 #pragma unroll
         for (int j = 0; j < 4; ++j) p[21 + j] = __uint_as_float(D[j]) + bl[96 + j];
-        ld += do_dim(a, p, row, d0 + 3);
+        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 3);
 #pragma unroll
         for (int j = 0; j < 25; ++j) p[j] = __uint_as_float(D[4 + j]) + bl[100 + j];
-        ld += do_dim(a, p, row, d0 + 4);
+        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 4);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->y_done[yb]);   // this warp's outputs of the tile are staged
       // ---- per-sample log-det: group 1 hands its partial sum to group 0
       if (g == 1) S->dl_part[r_in_tile] = ld;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -418,6 +513,12 @@ bool spline_tc_eligible(const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, in
   for (int l = 0; l < L; ++l)
     if (!net->Wk_hi[l] || !net->Wk_lo[l]) return false;
   if (net->spline_dims_per_pass != DPP || net->spline_stride != PS) return false;
+  // two staged y tiles + >= 4 ring stages must fit next to the biases in shared memory
+  const int d_t_max = net->N[L - 1] / 128 * DPP;
+  size_t bias = 0;
+  for (int l = 0; l < L; ++l) bias += net->Np[l];
+  if (1024 + sizeof(TcSmem) + 4 * (bias + 2 * TC_TM * (size_t)(d_t_max | 1)) + 64 + 4 * TILE_BYTES > 227 * 1024)
+    return false;
   return true;
 }
 
@@ -458,16 +559,22 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
     rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     if (rc) return rc;
   }
-  const size_t smem = 1024 + TC_STAGES * TILE_BYTES + sizeof(TcSmem) + sizeof(float) * bias_floats + 64;
+  a.bias_floats = bias_floats;
+  a.ldy = d_t | 1;
+  const size_t fixed = 1024 + sizeof(TcSmem) + sizeof(float) * ((size_t)bias_floats + 2 * TC_TM * a.ldy) + 64;
+  a.stages = TC_STAGES;
+  while (a.stages > 4 && fixed + (size_t)a.stages * TILE_BYTES > 227 * 1024) a.stages -= 2;
+  const size_t smem = fixed + (size_t)a.stages * TILE_BYTES;
   if (smem > 227 * 1024) return BGX_ERR_UNSUPPORTED;
-  static size_t configured = 0;
-  if (smem > configured) {
-    rc = check(cudaFuncSetAttribute(spline_coupling_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = a.inverse ? spline_coupling_tc_kernel<true> : spline_coupling_tc_kernel<false>;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[a.inverse]) {
+    rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
-    configured = smem;
+    configured[a.inverse] = smem;
   }
   const unsigned grid = (unsigned)std::min<long long>(a.ntiles, sm_count);
-  spline_coupling_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+  kern<<<grid, TC_THREADS, smem, st>>>(a);
   return post_launch();
 }
 

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* 
         for (int ks = 0; ks < K / 8; ++ks) {
           const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
           const uint64_t bd = smem_desc_sw128(smem_u32(Bs) + off);
-          if (mode == 1) {
+          if (mode >= 1) {
             mma_tf32_ts(tmem + ST_ACC_COL, tmem + ST_A_COL + ks * 8, bd, idesc, ks > 0);
           } else {
             const uint64_t ad = smem_desc_sw128(smem_u32(As) + off);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* 
     // warps 0..3: TMEM lane quadrant = warp id
     const int row = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    if (mode == 1) {
+    if (mode >= 1) {
       for (int c = 0; c < ntile; ++c) {
         uint32_t r[32];
 #pragma unroll
@@ -101,12 +101,23 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* 
     if (lane == 0) mbar_arrive(a_ready);
     mbar_wait(acc_full, 0, status);
     tc_fence_after();
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + lane_base + ST_ACC_COL + c * 32, r);
-      tmem_ld_wait();
+    if (mode == 2) {
+      // probe: 32-column load at a column offset that is not a multiple of 32 (25, then 75)
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + ST_ACC_COL + 25 + c * 50, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) out[row * 128 + c * 32 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) out[row * 128 + c * 32 + j] = __uint_as_float(r[j]);
+      }
+    } else {
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + ST_ACC_COL + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[row * 128 + c * 32 + j] = __uint_as_float(r[j]);
+      }
     }
     tc_fence_before();
   }
@@ -125,7 +136,7 @@ using namespace bgx;
 // status: device int, set to 1 if an mbarrier wait timed out.
 extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                                int* status, void* stream) {
-  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode != 0 && mode != 1))
+  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || mode < 0 || mode > 2)
     return BGX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   st_swizzle_w<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, scratch);

@@ -76,3 +76,14 @@ def test_tf32_truncation_and_3x_split(mode):
     out3 = _run(mode, a_hi, w_hi) + _run(mode, a_lo, w_hi) + _run(mode, a_hi, w_lo)
     err3 = (out3.double() - ref).abs().max().item()
     assert err3 < 2e-5, (err1, err3)
+
+
+def test_tmem_load_at_unaligned_column_offset():
+    """mode 2: tcgen05.ld 32x32b.x32 starting at columns 25 and 75 (not multiples of 32)."""
+    g = torch.Generator().manual_seed(11)
+    A = torch.randint(-3, 4, (128, 64), generator=g).float().to(DEV)
+    W = torch.randint(-3, 4, (128, 64), generator=g).float().to(DEV)
+    out = _run(2, A, W)
+    ref = A @ W.t()
+    assert torch.equal(out[:, :32], ref[:, 25:57]), "offset 25"
+    assert torch.equal(out[:, 32:64], ref[:, 75:107]), "offset 75"
