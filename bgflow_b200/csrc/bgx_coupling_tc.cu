@@ -8,13 +8,15 @@
 //   warp 1      tcgen05.mma issuer (kind::tf32, M=128 N=128 K=8): A operand = activations in
 //               TENSOR MEMORY (hi | lo halves), B operand = weight tiles in shared memory,
 //               fp32 accumulators in tensor memory
-//   warp 2      TMEM allocation (all 512 columns)
-//   warps 4-7   epilogue group 0, warps 8-11 epilogue group 1 (thread <-> sample row):
+//   warps 2-3   I/O warps (warp 2 also owns the TMEM allocation): stage the tile's transformed
+//               inputs / outputs through shared memory with coalesced global accesses
+//   warps 4-19  16 epilogue warps, thread <-> sample row; the 4 warps that share a TMEM lane
+//               quadrant split the columns (hidden layers) / the transformed dims (last layer):
 //               hidden layers: tcgen05.ld accumulator -> bias + activation -> hi/lo split ->
 //               tcgen05.st as the next layer's A operand (activations never leave the SM);
 //               last layer: 128-column chunks (5 transformed dims x 25 spline parameters)
-//               double-buffered in TMEM, groups alternate chunks: parameters go TMEM ->
-//               registers -> softmax/cumsum/bin search/RQ evaluation/log-det in registers.
+//               double-buffered in TMEM; a warp pulls the 25 parameters of one of its dims
+//               TMEM -> registers and does softmax/cumsum/bin search/RQ evaluation/log-det.
 //
 // TMEM columns: [0,128) ACC0, [128,256) ACC1, [256,384) A_hi, [384,512) A_lo.
 // Numerics: 3xTF32 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate) ~ fp32; BGX_FLAG_TF32X1
@@ -25,7 +27,8 @@
 namespace bgx {
 using namespace tc;
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 640;
+constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_TM = 128;
 constexpr int TC_STAGES = 8;
 constexpr uint32_t TILE_BYTES = 16384;
@@ -33,6 +36,14 @@ constexpr int COL_ACC0 = 0, COL_ACC1 = 128, COL_AHI = 256, COL_ALO = 384;
 constexpr int NB = 8;            // spline bins handled by this kernel
 constexpr int PS = 3 * NB + 1;   // parameters per transformed dim
 constexpr int DPP = 5;           // dims per 128-column chunk
+
+// per-kernel constants of the spline (uniform across threads)
+struct SplineK {
+  float left, right, bottom, top;
+  float wscale, hscale;   // (right-left)*(1-min_w*K), (top-bottom)*(1-min_h*K)
+  float wstep, hstep;     // (right-left)*min_w, (top-bottom)*min_h
+  float min_d, beta_l2e, ln2_over_beta, beta;
+};
 
 struct TcArgs {
   long long B;
@@ -46,6 +57,7 @@ struct TcArgs {
   int x3;            // 1: 3xTF32, 0: 1xTF32
   int inverse;
   SplineParams sp;
+  SplineK ck;
   const float* dlogp_in;
   float* dlogp_out;
   int* status;       // device int: set to 1 when a barrier wait timed out
@@ -58,16 +70,16 @@ struct TcArgs {
 struct TcSmem {
   uint64_t full[TC_STAGES];
   uint64_t empty[TC_STAGES];
-  uint64_t x_ready;      // 4 arrivals: layer-0 operand staged in TMEM
-  uint64_t a_ready;      // 8 arrivals: hidden activations staged in TMEM
+  uint64_t x_ready;      // 16 arrivals: layer-0 operand staged in TMEM
+  uint64_t a_ready;      // 16 arrivals: hidden activations staged in TMEM
   uint64_t acc_full_h;   // hidden-layer accumulator complete
   uint64_t acc_full[2];  // last-layer chunk accumulator complete
-  uint64_t acc_empty[2]; // 4 arrivals: chunk accumulator drained into registers
+  uint64_t acc_empty[2]; // 16 arrivals: every epilogue warp has pulled its dims of the chunk
   uint64_t y_full[2];    // 2 arrivals (I/O warps): transformed-input tile staged in shared memory
-  uint64_t y_done[2];    // 8 arrivals (epilogue warps): tile's outputs are in shared memory
+  uint64_t y_done[2];    // 16 arrivals (epilogue warps): tile's outputs are in shared memory
   uint32_t tmem_base;
   uint32_t pad;
-  float dl_part[TC_TM];
+  float dl_part[4][TC_TM];
 };
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
@@ -91,14 +103,6 @@ __device__ __forceinline__ float act_fast(float x, int act) {
     default: return x;
   }
 }
-
-// per-kernel constants of the spline (uniform across threads)
-struct SplineK {
-  float left, right, bottom, top;
-  float wscale, hscale;   // (right-left)*(1-min_w*K), (top-bottom)*(1-min_h*K)
-  float wstep, hstep;     // (right-left)*min_w, (top-bottom)*min_h
-  float min_d, beta_l2e, ln2_over_beta, beta;
-};
 
 __device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
   const float bs = c.beta * s;
@@ -178,17 +182,13 @@ __device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK
 
 // transform dim `d` of this thread's sample: input from / output to the staged y tile
 template <bool INVERSE>
-__device__ __forceinline__ float do_dim(const TcArgs& a, const SplineK& ck, const float (&p)[PS], float* yrow,
-                                        int d) {
-  if (d >= a.D_t) return 0.f;
-  float x = yrow[d];
-  if (x < ck.left || x > ck.right) {
-    if (a.sp.oob) atomicAdd(a.sp.oob, 1);
-    x = fminf(fmaxf(x, ck.left), ck.right);
-  }
+__device__ __forceinline__ float do_dim(const TcArgs& a, const float (&p)[PS], float* yslot, int& n_oob) {
+  float x = *yslot;
+  n_oob += (x < a.ck.left || x > a.ck.right) ? 1 : 0;
+  x = fminf(fmaxf(x, a.ck.left), a.ck.right);
   float y, lad;
-  rqs_eval_reg<!INVERSE>(p, ck, x, y, lad);   // bgflow forward == root branch
-  yrow[d] = y;
+  rqs_eval_reg<!INVERSE>(p, a.ck, x, y, lad);   // bgflow forward == root branch
+  *yslot = y;
   return lad;
 }
 
@@ -211,17 +211,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       mbar_init(&S->full[s], 1);
       mbar_init(&S->empty[s], 1);
     }
-    mbar_init(&S->x_ready, 4);
-    mbar_init(&S->a_ready, 8);
+    mbar_init(&S->x_ready, TC_EPI_WARPS);
+    mbar_init(&S->a_ready, TC_EPI_WARPS);
     mbar_init(&S->acc_full_h, 1);
     mbar_init(&S->acc_full[0], 1);
     mbar_init(&S->acc_full[1], 1);
-    mbar_init(&S->acc_empty[0], 4);
-    mbar_init(&S->acc_empty[1], 4);
+    mbar_init(&S->acc_empty[0], TC_EPI_WARPS);
+    mbar_init(&S->acc_empty[1], TC_EPI_WARPS);
     mbar_init(&S->y_full[0], 2);
     mbar_init(&S->y_full[1], 2);
-    mbar_init(&S->y_done[0], 8);
-    mbar_init(&S->y_done[1], 8);
+    mbar_init(&S->y_done[0], TC_EPI_WARPS);
+    mbar_init(&S->y_done[1], TC_EPI_WARPS);
     fence_mbar_init();
   }
   {  // biases -> shared memory (layer l at offset boff[l])
@@ -359,33 +359,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue groups
-    const int g = (warp - 4) >> 2;            // 0 or 1
+    // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                   // TMEM lane quadrant of this warp
+    const int j = (warp - 4) >> 2;            // 0..3: which of the quadrant's four warps
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int gx = (a.npass - 1) & 1;         // the group that owns the last chunk stages x
-    SplineK ck;
-    {
-      const float wx = a.sp.right - a.sp.left, hy = a.sp.top - a.sp.bottom;
-      ck.left = a.sp.left; ck.right = a.sp.right; ck.bottom = a.sp.bottom; ck.top = a.sp.top;
-      ck.wscale = wx * (1.f - a.sp.min_w * NB); ck.hscale = hy * (1.f - a.sp.min_h * NB);
-      ck.wstep = wx * a.sp.min_w; ck.hstep = hy * a.sp.min_h;
-      ck.min_d = a.sp.min_d; ck.beta = a.sp.beta; ck.beta_l2e = a.sp.beta * LOG2E;
-      ck.ln2_over_beta = LN2 * a.sp.inv_beta;
-    }
-    uint32_t ph_h = 0, ph_f = 0;
+    uint32_t ph_h = 0, ph_f0 = 0, ph_f1 = 0;
     const int last_off = [&] { int o = 0; for (int l = 0; l < L - 1; ++l) o += a.net.Np[l]; return o; }();
 
     auto stage_x = [&](long long tile) {
       const long long row = tile * TC_TM + r_in_tile;
       const int K0 = a.net.K[0];
-      for (int b0 = 0; b0 < K0; b0 += 8) {
+      for (int b0 = j * 8; b0 < K0; b0 += 32) {
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v = load_cond(a.cond, a.net, a.B, row, b0 + j);
-          split_tf32(v, hi[j], lo[j]);
+        for (int i = 0; i < 8; ++i) {
+          float v = load_cond(a.cond, a.net, a.B, row, b0 + i);
+          split_tf32(v, hi[i], lo[i]);
         }
         tmem_st8(tmem + lane_base + COL_AHI + b0, hi);
         if (a.x3) tmem_st8(tmem + lane_base + COL_ALO + b0, lo);
@@ -402,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       const long long row = tile * TC_TM + r_in_tile;
       const int yb = (int)(it & 1);
       float* yrow = ybuf + yb * TC_TM * a.ldy + r_in_tile * a.ldy;
-      if (first && g == gx) stage_x(tile);
+      if (first) stage_x(tile);
       first = false;
       // ---- hidden layers: ACC0 -> bias + activation -> A operand of the next layer
       int boff = 0;
@@ -410,18 +400,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         mbar_wait(&S->acc_full_h, ph_h, a.status);
         ph_h ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int col = g * 64 + i * 32;
-          uint32_t v[32], hi[32], lo[32];
+        {
+          const int col = j * 32;
+          uint32_t v[32], lo[32];
           tmem_ld32(tmem + lane_base + COL_ACC0 + col, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float h = act_fast(__uint_as_float(v[j]) + bias_s[boff + col + j], a.net.act);
-            split_tf32(h, hi[j], lo[j]);
+          for (int i = 0; i < 32; ++i) {
+            float h = act_fast(__uint_as_float(v[i]) + bias_s[boff + col + i], a.net.act);
+            split_tf32(h, v[i], lo[i]);
           }
-          tmem_st32(tmem + lane_base + COL_AHI + col, hi);
+          tmem_st32(tmem + lane_base + COL_AHI + col, v);
           if (a.x3) tmem_st32(tmem + lane_base + COL_ALO + col, lo);
         }
         tmem_st_wait();
@@ -430,67 +419,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         if (lane == 0) mbar_arrive(&S->a_ready);
         boff += a.net.Np[l];
       }
-      // ---- last layer: chunks c = g, g+2, ...  (5 dims x 25 parameters per 128 columns)
+      // ---- last layer: chunk c holds dims 5c..5c+4 (25 parameters each); this warp takes the
+      //      dims d with d % 4 == j
       float ld = 0.f;
+      int n_oob = 0;
       mbar_wait(&S->y_full[yb], (uint32_t)((it >> 1) & 1), a.status);
-      for (int c = g; c < a.npass; c += 2) {
-        mbar_wait(&S->acc_full[g], ph_f, a.status);
-        ph_f ^= 1;
+      for (int c = 0; c < a.npass; ++c) {
+        const int buf = c & 1;
+        if (buf == 0) { mbar_wait(&S->acc_full[0], ph_f0, a.status); ph_f0 ^= 1; }
+        else { mbar_wait(&S->acc_full[1], ph_f1, a.status); ph_f1 ^= 1; }
         tc_fence_after();
-        const uint32_t acc_addr = tmem + lane_base + (g ? COL_ACC1 : COL_ACC0);
+        const uint32_t acc_addr = tmem + lane_base + (buf ? COL_ACC1 : COL_ACC0);
         const float* bl = bias_s + last_off + c * 128;
-        uint32_t A[32], Bv[32], C[32], D[32];
-        tmem_ld32(acc_addr + 0, A);
-        tmem_ld32(acc_addr + 32, Bv);
-        tmem_ld_wait();
-        float p[PS];
-        const int d0 = c * DPP;
+        const int i0 = (j - 5 * c) & 3;                       // first slot of this chunk that is mine
+        const int n_mine = (i0 == 0 && 5 * c + 4 < a.D_t) ? 2 : ((5 * c + i0 < a.D_t) ? 1 : 0);
+        bool released = false;
+        for (int m = 0; m < n_mine; ++m) {
+          const int i = i0 + 4 * m;
+          uint32_t v[32];
+          tmem_ld32(acc_addr + i * PS, v);
+          tmem_ld_wait();
+          if (m == n_mine - 1) {                              // last pull from this accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->acc_empty[buf]);
+            released = true;
+          }
+          float p[PS];
 #pragma unroll
-        for (int j = 0; j < 25; ++j) p[j] = __uint_as_float(A[j]) + bl[j];
-        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 0);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) p[j] = __uint_as_float(A[25 + j]) + bl[25 + j];
-#pragma unroll
-        for (int j = 0; j < 18; ++j) p[7 + j] = __uint_as_float(Bv[j]) + bl[32 + j];
-        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 1);
-        tmem_ld32(acc_addr + 64, C);
-        tmem_ld32(acc_addr + 96, D);
-        tmem_ld_wait();
-        // accumulator is in registers: hand the TMEM buffer back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S->acc_empty[g]);
-        // the group that owns the tile's last chunk stages the next tile's conditioner input:
-        // the commit behind acc_full of the last chunk covers every MMA of this tile, so the
-        // A-operand columns are free
-        if (g == gx && c + 2 >= a.npass) {
+          for (int k = 0; k < PS; ++k) p[k] = __uint_as_float(v[k]) + bl[i * PS + k];
+          ld += do_dim<INVERSE>(a, p, yrow + 5 * c + i, n_oob);
+        }
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S->acc_empty[buf]);
+        }
+        // every MMA of this tile has completed once the last chunk's accumulator is full:
+        // the A-operand columns are free for the next tile's conditioner input
+        if (c == a.npass - 1) {
           const long long next = tile + gridDim.x;
           if (next < a.ntiles) stage_x(next);
         }
-#pragma unroll
-        for (int j = 0; j < 14; ++j) p[j] = __uint_as_float(Bv[18 + j]) + bl[50 + j];
-#pragma unroll
-        for (int j = 0; j < 11; ++j) p[14 + j] = __uint_as_float(C[j]) + bl[64 + j];
-        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 2);
-#pragma unroll
-        for (int j = 0; j < 21; ++j) p[j] = __uint_as_float(C[11 + j]) + bl[75 + j];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) p[21 + j] = __uint_as_float(D[j]) + bl[96 + j];
-        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 3);
-#pragma unroll
-        for (int j = 0; j < 25; ++j) p[j] = __uint_as_float(D[4 + j]) + bl[100 + j];
-        ld += do_dim<INVERSE>(a, ck, p, yrow, d0 + 4);
       }
+      if (n_oob && a.sp.oob) atomicAdd(a.sp.oob, n_oob);
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->y_done[yb]);   // this warp's outputs of the tile are staged
-      // ---- per-sample log-det: group 1 hands its partial sum to group 0
-      if (g == 1) S->dl_part[r_in_tile] = ld;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (g == 0 && row < a.B) {
+      // ---- per-sample log-det: the quadrant's four warps combine their partial sums
+      S->dl_part[j][r_in_tile] = ld;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (j == 0 && row < a.B) {
         const float base_dl = a.dlogp_in ? a.dlogp_in[row] : 0.f;
-        a.dlogp_out[row] = base_dl + ld + S->dl_part[r_in_tile];
+        a.dlogp_out[row] = base_dl + ((S->dl_part[0][r_in_tile] + S->dl_part[1][r_in_tile]) +
+                                      (S->dl_part[2][r_in_tile] + S->dl_part[3][r_in_tile]));
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");   // dl_part may be overwritten by the next tile
+      asm volatile("bar.sync 2, 512;" ::: "memory");   // dl_part is rewritten by the next tile
     }
   }
   tc_fence_before();
@@ -547,6 +530,14 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   a.x3 = (flags & BGX_FLAG_TF32X1) ? 0 : 1;
   a.inverse = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
   spline_params_from_cfg(cfg, a.sp);
+  {
+    const float wx = a.sp.right - a.sp.left, hy = a.sp.top - a.sp.bottom;
+    a.ck.left = a.sp.left; a.ck.right = a.sp.right; a.ck.bottom = a.sp.bottom; a.ck.top = a.sp.top;
+    a.ck.wscale = wx * (1.f - a.sp.min_w * NB); a.ck.hscale = hy * (1.f - a.sp.min_h * NB);
+    a.ck.wstep = wx * a.sp.min_w; a.ck.hstep = hy * a.sp.min_h;
+    a.ck.min_d = a.sp.min_d; a.ck.beta = a.sp.beta; a.ck.beta_l2e = a.sp.beta * LOG2E;
+    a.ck.ln2_over_beta = LN2 * a.sp.inv_beta;
+  }
   a.dlogp_in = ca.dlogp_in;
   a.dlogp_out = ca.dlogp_out;
   a.status = status;
