@@ -65,7 +65,21 @@ struct TcArgs {
   int bias_floats;   // total bias floats staged in shared memory
   int ldy;           // leading dimension of the staged y tile (odd: conflict-free per-row access)
   int stages;        // weight ring depth
+  unsigned long long* trace;   // debug timeline of CTA 0 (or NULL): [0] = count, then (clock, code) pairs
+  int trace_cap;
 };
+
+// debug timeline: code = role << 24 | event << 16 | (tile-local index & 0xff) << 8 | chunk/layer
+__device__ __forceinline__ void tc_trace(const TcArgs& a, int role, int ev, long long it, int x) {
+  if (a.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    unsigned long long slot = atomicAdd(a.trace, 1ULL);
+    if (slot < (unsigned long long)a.trace_cap) {
+      a.trace[1 + 2 * slot] = (unsigned long long)clock64();
+      a.trace[2 + 2 * slot] = ((unsigned long long)role << 24) | ((unsigned long long)ev << 16) |
+                              ((unsigned long long)(it & 0xff) << 8) | (unsigned long long)(x & 0xff);
+    }
+  }
+}
 
 struct TcSmem {
   uint64_t full[TC_STAGES];
@@ -267,10 +281,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       uint32_t phase = 0;
       uint32_t ph_x = 0, ph_a = 0, ph_e0 = 0, ph_e1 = 0;
       bool first = true;
+      long long mma_it = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           if (l == 0) { mbar_wait(&S->x_ready, ph_x, a.status); ph_x ^= 1; }
           else { mbar_wait(&S->a_ready, ph_a, a.status); ph_a ^= 1; }
+          tc_trace(a, 1, 1, mma_it, l);   // operand ready, layer l starts issuing
           const bool last = (l == L - 1);
           const int nch = last ? a.npass : 1;
           const int kt = a.ktiles[l];
@@ -316,9 +332,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
               if (s_lo >= 0) mma_commit(&S->empty[s_lo]);
             }
             mma_commit(last ? &S->acc_full[buf] : &S->acc_full_h);
+            tc_trace(a, 1, 2, mma_it, last ? 16 + c : l);   // chunk / layer issued
           }
         }
         first = false;
+        ++mma_it;
       }
     }
     __syncwarp();
@@ -400,6 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         mbar_wait(&S->acc_full_h, ph_h, a.status);
         ph_h ^= 1;
         tc_fence_after();
+        if (warp == 4) tc_trace(a, 2, 1, it, l);   // hidden accumulator observed
         {
           const int col = j * 32;
           uint32_t v[32], lo[32];
@@ -417,6 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->a_ready);
+        if (warp == 4) tc_trace(a, 2, 2, it, l);   // hidden activations handed over
         boff += a.net.Np[l];
       }
       // ---- last layer: chunk c holds dims 5c..5c+4 (25 parameters each); this warp takes the
@@ -424,11 +444,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       float ld = 0.f;
       int n_oob = 0;
       mbar_wait(&S->y_full[yb], (uint32_t)((it >> 1) & 1), a.status);
+      if (warp == 4) tc_trace(a, 2, 6, it, 0);   // y tile available
       for (int c = 0; c < a.npass; ++c) {
         const int buf = c & 1;
         if (buf == 0) { mbar_wait(&S->acc_full[0], ph_f0, a.status); ph_f0 ^= 1; }
         else { mbar_wait(&S->acc_full[1], ph_f1, a.status); ph_f1 ^= 1; }
         tc_fence_after();
+        if (warp == 4) tc_trace(a, 2, 3, it, c);   // chunk accumulator observed
         const uint32_t acc_addr = tmem + lane_base + (buf ? COL_ACC1 : COL_ACC0);
         const float* bl = bias_s + last_off + c * 128;
         const int i0 = (j - 5 * c) & 3;                       // first slot of this chunk that is mine
@@ -457,9 +479,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         }
         // every MMA of this tile has completed once the last chunk's accumulator is full:
         // the A-operand columns are free for the next tile's conditioner input
+        if (warp == 4) tc_trace(a, 2, 4, it, c);   // my dims of the chunk done
         if (c == a.npass - 1) {
           const long long next = tile + gridDim.x;
           if (next < a.ntiles) stage_x(next);
+          if (warp == 4) tc_trace(a, 2, 5, it, c); // next tile's x staged
         }
       }
       if (n_oob && a.sp.oob) atomicAdd(a.sp.oob, n_oob);
@@ -485,6 +509,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
 }
 
 // ------------------------------------------------------------------------------ host side
+
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cap = 0;
+void tc_set_trace(unsigned long long* buf, int cap) { g_trace = buf; g_trace_cap = cap; }
 
 bool spline_tc_eligible(const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, int d_c) {
   if (!net || !cfg || cfg->n_bins != NB) return false;
@@ -541,6 +569,8 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   a.dlogp_in = ca.dlogp_in;
   a.dlogp_out = ca.dlogp_out;
   a.status = status;
+  a.trace = g_trace;
+  a.trace_cap = g_trace_cap;
   a.ntiles = (a.B + TC_TM - 1) / TC_TM;
   static int sm_count = 0;
   if (!sm_count) {

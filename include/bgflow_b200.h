@@ -176,6 +176,10 @@ int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, floa
 int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                     int* status, void* stream);
 
+/* Debug: subsequent tensor-core launches record a timeline of CTA 0 into `device_buffer`
+ * ([0] = event count, then (clock64, code) pairs; 1 + 2*capacity uint64).  NULL disables. */
+int bgx_debug_set_trace(uint64_t* device_buffer, int capacity);
+
 const char* bgx_version(void);
 const char* bgx_last_cuda_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
