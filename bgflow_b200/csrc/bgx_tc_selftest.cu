@@ -23,7 +23,7 @@ __global__ void st_swizzle_w(const float* __restrict__ W, int K, float* __restri
   out[tile * 4096 + sw128_offset(n, kk) / 4] = W[idx];
 }
 
-__global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* __restrict__ A,
+__global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const float* __restrict__ A,
                                                          const float* __restrict__ Wsw, int K,
                                                          float* __restrict__ out, int* status) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* 
   uint64_t* acc_full = bars + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 4);
 
+  const int mode = mode_reps & 15, reps = max(1, mode_reps >> 4), nshape = (mode_reps >> 24) ? 256 : 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile = K / 32;
   if (threadIdx.x == 0) {
@@ -61,20 +62,26 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* 
     if (lane == 0) {
       bool ok = mbar_wait(b_full, 0, status) && mbar_wait(a_ready, 0, status);
       tc_fence_after();
+      long long t0 = clock64();
       if (ok) {
         const uint32_t idesc = idesc_tf32(128, 128);
-        for (int ks = 0; ks < K / 8; ++ks) {
-          const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
-          const uint64_t bd = smem_desc_sw128(smem_u32(Bs) + off);
-          if (mode >= 1) {
-            mma_tf32_ts(tmem + ST_ACC_COL, tmem + ST_A_COL + ks * 8, bd, idesc, ks > 0);
-          } else {
-            const uint64_t ad = smem_desc_sw128(smem_u32(As) + off);
-            mma_tf32_ss(tmem + ST_ACC_COL, ad, bd, idesc, ks > 0);
+        for (int rep = 0; rep < reps; ++rep)
+          for (int ks = 0; ks < K / 8; ++ks) {
+            const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
+            const uint64_t bd = smem_desc_sw128(smem_u32(Bs) + off);
+            if (mode >= 1) {
+              mma_tf32_ts(tmem + ST_ACC_COL, tmem + ST_A_COL + ks * 8, bd, idesc, (ks | rep) > 0);
+            } else {
+              const uint64_t ad = smem_desc_sw128(smem_u32(As) + off);
+              mma_tf32_ss(tmem + ST_ACC_COL, ad, bd, idesc, (ks | rep) > 0);
+            }
           }
-        }
       }
       mma_commit(acc_full);
+      if (reps > 1) {      // throughput probe: cycles from first issue to completion of all MMAs
+        mbar_wait(acc_full, 0, status);
+        status[1] = (int)(clock64() - t0);
+      }
     }
     __syncwarp();
   } else {
@@ -133,10 +140,11 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode, const float* 
 using namespace bgx;
 
 // A [128][K], W [128][K] (K multiple of 32, <= 128), scratch >= 128*K floats, out [128][128],
-// status: device int, set to 1 if an mbarrier wait timed out.
+// status: TWO device ints: [0] set to 1 if an mbarrier wait timed out, [1] = cycles spent by the MMA
+// loop when the mode carries a repeat count (mode | reps << 4; throughput probe, results then meaningless).
 extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                                int* status, void* stream) {
-  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || mode < 0 || mode > 2)
+  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 2 || mode < 0)
     return BGX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   st_swizzle_w<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, scratch);

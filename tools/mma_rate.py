@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""tcgen05.mma kind::tf32 M=128 N=128 K=8 issue rate on resident operands (debug aid)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bgflow_b200 import _lib
+
+lib = _lib.load()
+dev = "cuda:0"
+K = 128
+A = torch.randn(128, K, device=dev)
+W = torch.randn(128, K, device=dev)
+scratch = torch.empty(128 * K, device=dev)
+out = torch.empty(128, 128, device=dev)
+for mode, name in ((0, "SS (A in smem)"), (1, "TS (A in TMEM)")):
+    for reps in (16, 64, 256):
+        st = torch.zeros(2, dtype=torch.int32, device=dev)
+        rc = lib.bgx_tc_selftest(mode | (reps << 4), A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(),
+                                 st.data_ptr(), None)
+        torch.cuda.synchronize()
+        n = reps * K // 8
+        print(f"{name}: {n} MMAs in {int(st[1])} cycles -> {int(st[1]) / n:.1f} cycles/MMA (timeout={int(st[0])})")
