@@ -20,7 +20,7 @@ ERRORS = {-1: "BGX_ERR_INVALID (bad argument / inconsistent shapes)",
           -4: "BGX_ERR_CUDA"}
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3
-FLAG_INVERSE, FLAG_PRESERVE_VOLUME, FLAG_CIRCULAR, FLAG_TF32X1, FLAG_FORCE_SIMT = 1, 2, 4, 8, 16
+FLAG_INVERSE, FLAG_PRESERVE_VOLUME, FLAG_CIRCULAR, FLAG_BF16X3, FLAG_FORCE_SIMT = 1, 2, 4, 8, 16
 
 
 class bgx_mlp(C.Structure):
@@ -42,7 +42,7 @@ class bgx_packed_mlp(C.Structure):
                 ("raw_width", C.c_int32),
                 ("spline_dims_per_pass", C.c_int32), ("spline_stride", C.c_int32),
                 ("total_floats", C.c_int64),
-                ("Wk_hi", C.c_void_p * BGX_MAX_LAYERS), ("Wk_lo", C.c_void_p * BGX_MAX_LAYERS)]
+                ("Wb", (C.c_void_p * BGX_MAX_LAYERS) * 3)]
 
 
 class bgx_spline_layout(C.Structure):

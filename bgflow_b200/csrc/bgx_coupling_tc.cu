@@ -3,11 +3,13 @@
 // One persistent CTA per SM walks over tiles of 128 samples.  Per tile the whole block runs
 // on chip (replaces coupling.py:162-182 + spline.py:87-188 + dense.py:47-48 + nflows' RQS):
 //
-//   warp 0      bulk-TMA producer: streams pre-swizzled 16 KB weight tiles (hi and lo parts
-//               of the 3xTF32 split) from L2 through an 8-stage shared-memory ring
-//   warp 1      tcgen05.mma issuer (kind::tf32, M=128 N=128 K=8): A operand = activations in
-//               TENSOR MEMORY (hi | lo halves), B operand = weight tiles in shared memory,
-//               fp32 accumulators in tensor memory
+//   warp 0      bulk-TMA producer: streams pre-swizzled 16 KB bf16 weight tiles (the two or
+//               three terms of the exact split W = b1 + b2 + b3) from L2 through an 8-stage
+//               shared-memory ring
+//   warp 1      tcgen05.mma issuer (kind::f16 / bf16, M=128 N=128 K=16): A operand =
+//               activations in TENSOR MEMORY (bf16 terms a1 | a2 | a3, two elements per
+//               32-bit cell), B operand = weight tiles in shared memory, fp32 accumulators in
+//               tensor memory
 //   warps 2-3   I/O warps (warp 2 also owns the TMEM allocation): stage the tile's transformed
 //               inputs / outputs through shared memory with coalesced global accesses
 //   warps 4-19  16 epilogue warps, thread <-> sample row; the 4 warps that share a TMEM lane
@@ -18,9 +20,12 @@
 //               double-buffered in TMEM; a warp pulls the 25 parameters of one of its dims
 //               TMEM -> registers and does softmax/cumsum/bin search/RQ evaluation/log-det.
 //
-// TMEM columns: [0,128) ACC0, [128,256) ACC1, [256,384) A_hi, [384,512) A_lo.
-// Numerics: 3xTF32 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32 accumulate) ~ fp32; BGX_FLAG_TF32X1
-// keeps only the first product.
+// TMEM columns: [0,128) ACC0, [128,256) ACC1, [256,320) A1, [320,384) A2, [384,448) A3.
+// Numerics: every fp32 operand is split exactly into bf16 terms (x = x1 + x2 + x3, 24 mantissa
+// bits).  Default "bf16x6": a1b1 + a2b1 + a1b2 + a2b2 + a3b1 + a1b3 with fp32 accumulation (the
+// dropped products are < 2^-24 relative: fp32-equivalent).  BGX_FLAG_BF16X3: a1b1 + a2b1 + a1b2
+// (~2^-16 relative).  Measured on B200: a kind::tf32 128x128x8 MMA takes 136 cycles, a kind::f16
+// 128x128x16 MMA 64, so 6 bf16 products cost half of a 3xTF32 scheme and are more accurate.
 #include "bgx_coupling.cuh"
 #include "bgx_tc.cuh"
 
@@ -32,7 +37,7 @@ constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_TM = 128;
 constexpr int TC_STAGES = 8;
 constexpr uint32_t TILE_BYTES = 16384;
-constexpr int COL_ACC0 = 0, COL_ACC1 = 128, COL_AHI = 256, COL_ALO = 384;
+constexpr int COL_ACC0 = 0, COL_ACC1 = 128, COL_A = 256, COL_A_STRIDE = 64;   // A term t at COL_A + 64 t
 constexpr int NB = 8;            // spline bins handled by this kernel
 constexpr int PS = 3 * NB + 1;   // parameters per transformed dim
 constexpr int DPP = 5;           // dims per 128-column chunk
@@ -50,11 +55,10 @@ struct TcArgs {
   Segs cond, tin, tout;
   int D_t;
   DevMlp net;
-  const float* whi[BGX_MAX_LAYERS];
-  const float* wlo[BGX_MAX_LAYERS];
-  int ktiles[BGX_MAX_LAYERS];
+  const uint16_t* wb[3][BGX_MAX_LAYERS];   // bf16 term tiles
+  int ktiles[BGX_MAX_LAYERS];              // 64-wide k-tiles per layer
   int npass;         // 128-column chunks of the last layer
-  int x3;            // 1: 3xTF32, 0: 1xTF32
+  int nterms;        // 3: bf16x6 (fp32-equivalent), 2: bf16x3
   int inverse;
   SplineParams sp;
   SplineK ck;
@@ -96,9 +100,14 @@ struct TcSmem {
   float dl_part[4][TC_TM];
 };
 
-__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(v) & 0xffffe000u;
-  lo = __float_as_uint(v - __uint_as_float(hi));
+// exact split of two adjacent-k fp32 values into packed bf16x2 terms (element k in the low half)
+__device__ __forceinline__ void split_bf16(float x0, float x1, int nterms, uint32_t& t1, uint32_t& t2,
+                                           uint32_t& t3) {
+  t1 = pack_bf16x2(x0, x1);
+  const float r0 = x0 - bf16_lo_to_f32(t1), r1 = x1 - bf16_hi_to_f32(t1);
+  t2 = pack_bf16x2(r0, r1);
+  t3 = 0;
+  if (nterms == 3) t3 = pack_bf16x2(r0 - bf16_lo_to_f32(t2), r1 - bf16_hi_to_f32(t2));
 }
 
 // ---- fast special functions (MUFU): a few ulp, far inside the stated parity tolerance
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.net.n_layers;
-  const int nparts = a.x3 ? 2 : 1;
+  const int NT = a.nterms;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) {
@@ -262,9 +271,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
           const int kt = a.ktiles[l];
           for (int c = 0; c < nch; ++c)
             for (int t = 0; t < kt; ++t)
-              for (int part = 0; part < nparts; ++part) {
+              for (int part = 0; part < NT; ++part) {
                 mbar_wait(&S->empty[stage], phase ^ 1, a.status);
-                const float* src = (part == 0 ? a.whi[l] : a.wlo[l]) + ((long long)c * kt + t) * 4096;
+                const uint16_t* src = a.wb[part][l] + ((long long)c * kt + t) * 8192;
                 mbar_expect_tx(&S->full[stage], TILE_BYTES);
                 bulk_g2s(ring + stage * TILE_BYTES, src, TILE_BYTES, &S->full[stage]);
                 if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(128, 128);
+      const uint32_t idesc = idesc_bf16(128, 128);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ph_x = 0, ph_a = 0, ph_e0 = 0, ph_e1 = 0;
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
           const bool last = (l == L - 1);
           const int nch = last ? a.npass : 1;
           const int kt = a.ktiles[l];
-          const int ksteps_total = (a.net.K[l] + 7) / 8;
+          const int ksteps_total = (a.net.K[l] + 15) / 16;
           for (int c = 0; c < nch; ++c) {
             const int buf = last ? (c & 1) : 0;
             // accumulator free?  (hidden-layer reads are covered by a_ready / x ordering)
@@ -305,31 +314,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
             const uint32_t d_tmem = tmem + (buf ? COL_ACC1 : COL_ACC0);
             uint32_t acc = 0;
             for (int t = 0; t < kt; ++t) {
-              const int s_hi = stage;
-              mbar_wait(&S->full[s_hi], phase, a.status);
-              if (++stage == NST) { stage = 0; phase ^= 1; }
-              int s_lo = -1;
-              if (nparts == 2) {
-                s_lo = stage;
-                mbar_wait(&S->full[s_lo], phase, a.status);
+              int st_[3];
+              for (int part = 0; part < NT; ++part) {
+                st_[part] = stage;
+                mbar_wait(&S->full[stage], phase, a.status);
                 if (++stage == NST) { stage = 0; phase ^= 1; }
               }
               tc_fence_after();
               const int nk = min(4, ksteps_total - t * 4);
-              const uint32_t b_hi = smem_u32(ring + s_hi * TILE_BYTES);
-              const uint32_t b_lo = s_lo >= 0 ? smem_u32(ring + s_lo * TILE_BYTES) : 0;
+              const uint32_t b1 = smem_u32(ring + st_[0] * TILE_BYTES);
+              const uint32_t b2 = smem_u32(ring + st_[1] * TILE_BYTES);
+              const uint32_t b3 = NT == 3 ? smem_u32(ring + st_[2] * TILE_BYTES) : 0;
               for (int ks = 0; ks < nk; ++ks) {
-                const uint32_t kcol = (uint32_t)(t * 32 + ks * 8);
-                const uint64_t dh = smem_desc_sw128(b_hi + ks * 32);
-                mma_tf32_ts(d_tmem, tmem + COL_AHI + kcol, dh, idesc, acc);
-                acc = 1;
-                if (nparts == 2) {
-                  mma_tf32_ts(d_tmem, tmem + COL_ALO + kcol, dh, idesc, 1);
-                  mma_tf32_ts(d_tmem, tmem + COL_AHI + kcol, smem_desc_sw128(b_lo + ks * 32), idesc, 1);
+                const uint32_t kcol = (uint32_t)(t * 32 + ks * 8);          // 16 bf16 = 8 TMEM columns
+                const uint32_t a1 = tmem + COL_A + kcol, a2 = a1 + COL_A_STRIDE, a3 = a2 + COL_A_STRIDE;
+                const uint64_t d1 = smem_desc_sw128(b1 + ks * 32), d2 = smem_desc_sw128(b2 + ks * 32);
+                if (NT == 3) {   // smallest products first
+                  const uint64_t d3 = smem_desc_sw128(b3 + ks * 32);
+                  mma_bf16_ts(d_tmem, a1, d3, idesc, acc);
+                  mma_bf16_ts(d_tmem, a3, d1, idesc, 1);
+                  mma_bf16_ts(d_tmem, a2, d2, idesc, 1);
+                  acc = 1;
                 }
+                mma_bf16_ts(d_tmem, a1, d2, idesc, acc);
+                mma_bf16_ts(d_tmem, a2, d1, idesc, 1);
+                mma_bf16_ts(d_tmem, a1, d1, idesc, 1);
+                acc = 1;
               }
-              mma_commit(&S->empty[s_hi]);
-              if (s_lo >= 0) mma_commit(&S->empty[s_lo]);
+              for (int part = 0; part < NT; ++part) mma_commit(&S->empty[st_[part]]);
             }
             mma_commit(last ? &S->acc_full[buf] : &S->acc_full_h);
             tc_trace(a, 1, 2, mma_it, last ? 16 + c : l);   // chunk / layer issued
@@ -388,15 +400,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     auto stage_x = [&](long long tile) {
       const long long row = tile * TC_TM + r_in_tile;
       const int K0 = a.net.K[0];
-      for (int b0 = j * 8; b0 < K0; b0 += 32) {
-        uint32_t hi[8], lo[8];
+      for (int b0 = j * 16; b0 < K0; b0 += 64) {
+        uint32_t t1[8], t2[8], t3[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float v = load_cond(a.cond, a.net, a.B, row, b0 + i);
-          split_tf32(v, hi[i], lo[i]);
+          const float v0 = load_cond(a.cond, a.net, a.B, row, b0 + 2 * i);
+          const float v1 = load_cond(a.cond, a.net, a.B, row, b0 + 2 * i + 1);
+          split_bf16(v0, v1, NT, t1[i], t2[i], t3[i]);
         }
-        tmem_st8(tmem + lane_base + COL_AHI + b0, hi);
-        if (a.x3) tmem_st8(tmem + lane_base + COL_ALO + b0, lo);
+        const uint32_t col = tmem + lane_base + COL_A + b0 / 2;
+        tmem_st8(col, t1);
+        tmem_st8(col + COL_A_STRIDE, t2);
+        if (NT == 3) tmem_st8(col + 2 * COL_A_STRIDE, t3);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -421,16 +436,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         if (warp == 4) tc_trace(a, 2, 1, it, l);   // hidden accumulator observed
         {
           const int col = j * 32;
-          uint32_t v[32], lo[32];
+          uint32_t v[32];
           tmem_ld32(tmem + lane_base + COL_ACC0 + col, v);
           tmem_ld_wait();
+          uint32_t t1[16], t2[16], t3[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float h = act_fast(__uint_as_float(v[i]) + bias_s[boff + col + i], a.net.act);
-            split_tf32(h, v[i], lo[i]);
+          for (int i = 0; i < 16; ++i) {
+            const float h0 = act_fast(__uint_as_float(v[2 * i]) + bias_s[boff + col + 2 * i], a.net.act);
+            const float h1 = act_fast(__uint_as_float(v[2 * i + 1]) + bias_s[boff + col + 2 * i + 1], a.net.act);
+            split_bf16(h0, h1, NT, t1[i], t2[i], t3[i]);
           }
-          tmem_st32(tmem + lane_base + COL_AHI + col, v);
-          if (a.x3) tmem_st32(tmem + lane_base + COL_ALO + col, lo);
+          const uint32_t acol = tmem + lane_base + COL_A + col / 2;
+          tmem_st16(acol, t1);
+          tmem_st16(acol + COL_A_STRIDE, t2);
+          if (NT == 3) tmem_st16(acol + 2 * COL_A_STRIDE, t3);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -522,7 +541,7 @@ bool spline_tc_eligible(const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, in
   for (int l = 0; l + 1 < L; ++l)
     if (net->N[l] != 128) return false;
   for (int l = 0; l < L; ++l)
-    if (!net->Wk_hi[l] || !net->Wk_lo[l]) return false;
+    if (!net->Wb[0][l] || !net->Wb[1][l] || !net->Wb[2][l]) return false;
   if (net->spline_dims_per_pass != DPP || net->spline_stride != PS) return false;
   // two staged y tiles + >= 4 ring stages must fit next to the biases in shared memory
   const int d_t_max = net->N[L - 1] / 128 * DPP;
@@ -549,13 +568,12 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   mlp_to_dev(net, a.net);
   int bias_floats = 0;
   for (int l = 0; l < net->n_layers; ++l) {
-    a.whi[l] = net->Wk_hi[l];
-    a.wlo[l] = net->Wk_lo[l];
-    a.ktiles[l] = ceil_div(net->K[l], 32);
+    for (int term = 0; term < 3; ++term) a.wb[term][l] = (const uint16_t*)net->Wb[term][l];
+    a.ktiles[l] = ceil_div(net->K[l], 64);
     bias_floats += net->Np[l];
   }
   a.npass = net->N[net->n_layers - 1] / 128;
-  a.x3 = (flags & BGX_FLAG_TF32X1) ? 0 : 1;
+  a.nterms = (flags & BGX_FLAG_BF16X3) ? 2 : 3;
   a.inverse = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
   spline_params_from_cfg(cfg, a.sp);
   {

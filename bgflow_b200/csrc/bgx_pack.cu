@@ -28,25 +28,35 @@ __global__ void pack_transpose_kernel(const float* __restrict__ W, const float* 
   }
 }
 
-// Tensor-core layout: per 128-row chunk of W and per 32-wide k-tile one 16 KB tile
-// [128 rows][32 k] fp32, K-major, rows of 128 B with the 16-B chunks XOR-swizzled by (row & 7)
-// (the UMMA SWIZZLE_128B canonical layout), so that ONE 1-D bulk copy lands a ready operand tile
-// in shared memory.  hi = W truncated to tf32, lo = W - hi (the 3xTF32 split).
+// Tensor-core layout: W is split exactly into three bf16 terms, W = b1 + b2 + b3 (each the
+// round-to-nearest bf16 of the remaining residual: 24 mantissa bits in total).  Per term, per
+// 128-row chunk of W and per 64-wide k-tile one 16 KB tile [128 rows][64 k] bf16, K-major, rows
+// of 128 B with the 16-B chunks XOR-swizzled by (row & 7) (the UMMA SWIZZLE_128B canonical
+// layout), so that ONE 1-D bulk copy lands a ready B-operand tile in shared memory.
+__device__ __forceinline__ unsigned short f32_to_bf16_rn(float f) {
+  unsigned int u = __float_as_uint(f);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (unsigned short)(u >> 16);
+}
 __global__ void pack_tc_tiles_kernel(const float* __restrict__ W, const int* __restrict__ row_map, int K,
-                                     int N, int ktiles, int Np, float* __restrict__ hi,
-                                     float* __restrict__ lo) {
+                                     int N, int ktiles, int Np, unsigned short* __restrict__ t1,
+                                     unsigned short* __restrict__ t2, unsigned short* __restrict__ t3) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)Np * ktiles * 32;
+  long long total = (long long)Np * ktiles * 64;
   if (idx >= total) return;
-  int k = (int)(idx % (ktiles * 32)), n = (int)(idx / (ktiles * 32));
+  int k = (int)(idx % (ktiles * 64)), n = (int)(idx / (ktiles * 64));
   int r = row_map ? row_map[n] : (n < N ? n : -1);
   float w = (r >= 0 && k < K) ? W[(long long)r * K + k] : 0.f;
-  float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-  int chunk = n >> 7, nr = n & 127, t = k >> 5, kk = k & 31;
-  long long off = ((long long)chunk * ktiles + t) * 4096 +
-                  (nr * 32 + ((((kk >> 2) ^ (nr & 7)) << 2) | (kk & 3)));
-  hi[off] = h;
-  lo[off] = w - h;
+  unsigned short b1 = f32_to_bf16_rn(w);
+  float r1 = w - __uint_as_float((unsigned int)b1 << 16);
+  unsigned short b2 = f32_to_bf16_rn(r1);
+  float r2 = r1 - __uint_as_float((unsigned int)b2 << 16);
+  unsigned short b3 = f32_to_bf16_rn(r2);
+  int chunk = n >> 7, nr = n & 127, t = k >> 6, kk = k & 63;
+  long long off = ((long long)chunk * ktiles + t) * 8192 + (nr * 64 + ((((kk >> 3) ^ (nr & 7)) << 3) | (kk & 7)));
+  t1[off] = b1;
+  t2[off] = b2;
+  t3[off] = b3;
 }
 
 static int spline_dims_per_pass(int n_bins) { return 128 / (3 * n_bins + 1); }
@@ -104,19 +114,21 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
       last_map[n] = r;
     }
   }
-  // layout: [Wt_l | bias_l]* , [Wk_hi_l | Wk_lo_l]* (16 KB swizzled tiles), in_map, last_map
+  // layout: [Wt_l | bias_l]* , [Wb1_l | Wb2_l | Wb3_l]* (16 KB swizzled bf16 tiles), in_map, last_map
   int64_t off = 0;
-  int64_t o_wt[BGX_MAX_LAYERS], o_b[BGX_MAX_LAYERS], o_hi[BGX_MAX_LAYERS], o_lo[BGX_MAX_LAYERS];
-  int kp32[BGX_MAX_LAYERS];
+  int64_t o_wt[BGX_MAX_LAYERS], o_b[BGX_MAX_LAYERS], o_t[3][BGX_MAX_LAYERS];
+  int kp64[BGX_MAX_LAYERS];
   for (int l = 0; l < L; ++l) {
     o_wt[l] = off; off += (int64_t)pk.Kp[l] * pk.Np[l];
     o_b[l] = off; off += pk.Np[l];
   }
   off = (off + 255) / 256 * 256;  // tiles are bulk-copied: keep them 1 KB aligned
   for (int l = 0; l < L; ++l) {
-    kp32[l] = round_up(pk.K[l], 32);
-    o_hi[l] = off; off += (int64_t)kp32[l] * pk.Np[l];
-    o_lo[l] = off; off += (int64_t)kp32[l] * pk.Np[l];
+    kp64[l] = round_up(pk.K[l], 64);
+    for (int term = 0; term < 3; ++term) {      // bf16: two elements per float slot
+      o_t[term][l] = off;
+      off += (int64_t)kp64[l] * pk.Np[l] / 2;
+    }
   }
   int64_t o_inmap = off; off += round_up(pk.Kp[0], 4);
   int64_t o_lastmap = off; off += (int64_t)last_map.size();
@@ -172,15 +184,15 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
         src->W[l], src->b[l], rmap, pk.K[l], n_true, pk.Kp[l], pk.Np[l], wt, bb);
     rc = post_launch();
     if (rc) return rc;
-    long long total2 = (long long)kp32[l] * pk.Np[l];
+    long long total2 = (long long)kp64[l] * pk.Np[l];
     pack_tc_tiles_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
-        src->W[l], rmap, pk.K[l], n_true, kp32[l] / 32, pk.Np[l], dst + o_hi[l], dst + o_lo[l]);
+        src->W[l], rmap, pk.K[l], n_true, kp64[l] / 64, pk.Np[l], (unsigned short*)(dst + o_t[0][l]),
+        (unsigned short*)(dst + o_t[1][l]), (unsigned short*)(dst + o_t[2][l]));
     rc = post_launch();
     if (rc) return rc;
     pk.Wt[l] = wt;
     pk.bias[l] = bb;
-    pk.Wk_hi[l] = dst + o_hi[l];
-    pk.Wk_lo[l] = dst + o_lo[l];
+    for (int term = 0; term < 3; ++term) pk.Wb[term][l] = dst + o_t[term][l];
   }
   *out = pk;
   return BGX_OK;

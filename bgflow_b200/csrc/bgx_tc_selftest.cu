@@ -2,6 +2,8 @@
 // one CTA computes out[128][128] = A[128][K] . W[128][K]^T with
 //   mode 0: A and B from shared memory (SS, both K-major SWIZZLE_128B tiles)
 //   mode 1: A from tensor memory (TS), B from shared memory
+//   mode 2: as 1, accumulator read back at unaligned column offsets
+//   mode 3: kind::f16 (bf16), A = packed bf16 pairs in tensor memory, B = bf16 tiles (the production path)
 // B tiles arrive through 1-D bulk TMA copies of pre-swizzled tiles, the accumulator lives in
 // TMEM and is read back with tcgen05.ld.  tests/test_gpu_tc.py checks it against exact integer
 // products, so every descriptor bit is validated before the big kernel relies on it.
@@ -21,6 +23,14 @@ __global__ void st_swizzle_w(const float* __restrict__ W, int K, float* __restri
   int n = idx / K, k = idx % K;
   int tile = k / 32, kk = k % 32;
   out[tile * 4096 + sw128_offset(n, kk) / 4] = W[idx];
+}
+
+// bf16 variant: K/64 tiles of [128 x 64] bf16 (values must be exactly representable)
+__global__ void st_swizzle_w_bf16(const float* __restrict__ W, int K, unsigned short* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * K) return;
+  int n = idx / K, k = idx % K;
+  out[(k / 64) * 8192 + sw128_offset_bf16(n, k % 64)] = (unsigned short)(__float_as_uint(W[idx]) >> 16);
 }
 
 __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const float* __restrict__ A,
@@ -54,8 +64,9 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_expect_tx(b_full, (uint32_t)ntile * 16384u);
-      for (int t = 0; t < ntile; ++t) bulk_g2s(Bs + t * 4096, Wsw + t * 4096, 16384u, b_full);
+      const int nt = mode == 3 ? (K + 63) / 64 : ntile;     // bf16 tiles are 64 wide
+      mbar_expect_tx(b_full, (uint32_t)nt * 16384u);
+      for (int t = 0; t < nt; ++t) bulk_g2s(Bs + t * 4096, Wsw + t * 4096, 16384u, b_full);
     }
     __syncwarp();
   } else if (warp == 5) {
@@ -63,7 +74,15 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
       bool ok = mbar_wait(b_full, 0, status) && mbar_wait(a_ready, 0, status);
       tc_fence_after();
       long long t0 = clock64();
-      if (ok) {
+      if (ok && mode == 3) {
+        const uint32_t idesc = idesc_bf16(128, 128);
+        for (int rep = 0; rep < reps; ++rep)
+          for (int ks = 0; ks < K / 16; ++ks) {
+            const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
+            mma_bf16_ts(tmem + ST_ACC_COL, tmem + ST_A_COL + ks * 8, smem_desc_sw128(smem_u32(Bs) + off), idesc,
+                        (ks | rep) > 0);
+          }
+      } else if (ok) {
         const uint32_t idesc = idesc_tf32(128, 128);
         for (int rep = 0; rep < reps; ++rep)
           for (int ks = 0; ks < K / 8; ++ks) {
@@ -88,7 +107,16 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
     // warps 0..3: TMEM lane quadrant = warp id
     const int row = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    if (mode >= 1) {
+    if (mode == 3) {
+      for (int c = 0; c < K / 32; ++c) {       // 32 elements -> 16 packed columns
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = pack_bf16x2(A[row * K + c * 32 + 2 * j], A[row * K + c * 32 + 2 * j + 1]);
+        tmem_st16(tmem + lane_base + ST_A_COL + c * 16, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+    } else if (mode >= 1) {
       for (int c = 0; c < ntile; ++c) {
         uint32_t r[32];
 #pragma unroll
@@ -144,10 +172,11 @@ using namespace bgx;
 // loop when the mode carries a repeat count (mode | reps << 4; throughput probe, results then meaningless).
 extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                                int* status, void* stream) {
-  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 2 || mode < 0)
+  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 3 || mode < 0 || ((mode & 15) == 3 && K % 64))
     return BGX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  st_swizzle_w<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, scratch);
+  if ((mode & 15) == 3) st_swizzle_w_bf16<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, (unsigned short*)scratch);
+  else st_swizzle_w<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, scratch);
   int rc = post_launch();
   if (rc) return rc;
   const int smem_bytes = 8 * 16384 + 1024 + 256;

@@ -30,10 +30,11 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-#: kernel selection: ``precision`` "3xtf32" (default; fp32-accurate tensor-core math) or "tf32"
-#: (single-pass TF32, ~1e-3 relative error in the conditioner); ``force_simt`` runs the
+#: kernel selection: ``precision`` "bf16x6" (default: operands split exactly into three bf16
+#: terms, six tensor-core products, fp32 accumulate ~ fp32 accuracy) or "bf16x3" (two terms,
+#: three products, ~1e-5 relative error in the conditioner); ``force_simt`` runs the
 #: shape-general fp32 SIMT kernel even where the tensor-core kernel applies.
-config = {"precision": "3xtf32", "force_simt": False}
+config = {"precision": "bf16x6", "force_simt": False}
 
 _status = {}
 
@@ -57,10 +58,10 @@ def _mode_flags():
     f = 0
     if config.get("force_simt"):
         f |= _lib.FLAG_FORCE_SIMT
-    if config.get("precision") == "tf32":
-        f |= _lib.FLAG_TF32X1
-    elif config.get("precision") != "3xtf32":
-        raise ValueError("engine.config['precision'] must be '3xtf32' or 'tf32'")
+    if config.get("precision") == "bf16x3":
+        f |= _lib.FLAG_BF16X3
+    elif config.get("precision") != "bf16x6":
+        raise ValueError("engine.config['precision'] must be 'bf16x6' or 'bf16x3'")
     return f
 
 

@@ -78,9 +78,9 @@ typedef struct bgx_packed_mlp {
   int32_t raw_width;
   int32_t spline_dims_per_pass, spline_stride;     /* last-layer column layout (spline nets) */
   int64_t total_floats;
-  /* tensor-core layout (tcgen05 path); NULL when not packed for it */
-  const float* Wk_hi[BGX_MAX_LAYERS];              /* device, 16 KB SWIZZLE_128B tiles [Np/128][ceil(K/32)][128x32], tf32-truncated W */
-  const float* Wk_lo[BGX_MAX_LAYERS];              /* device, same tiling, residual W - hi */
+  /* tensor-core layout (tcgen05 path): W = b1 + b2 + b3 exactly, three bf16 terms; per term
+   * 16 KB SWIZZLE_128B tiles [Np/128][ceil(K/64)][128 x 64] bf16 (device pointers) */
+  const void* Wb[3][BGX_MAX_LAYERS];
 } bgx_packed_mlp;
 
 /* Last-layer re-layout request for a spline conditioner: the raw column layout of
@@ -120,7 +120,7 @@ typedef struct bgx_coupling_io {
 #define BGX_FLAG_INVERSE 1          /* evaluate bgflow's _inverse direction */
 #define BGX_FLAG_PRESERVE_VOLUME 2  /* affine.py:44-45 */
 #define BGX_FLAG_CIRCULAR 4         /* affine.py:56-57: y %= 1 (shift-only) */
-#define BGX_FLAG_TF32X1 8           /* tensor-core path: single-pass TF32 (default: 3xTF32 ~ fp32) */
+#define BGX_FLAG_BF16X3 8           /* tensor-core path: 3 bf16 products (~1e-5); default 6 products ~ fp32 */
 #define BGX_FLAG_FORCE_SIMT 16      /* always use the generic fp32 SIMT kernel */
 
 /* y' = y * exp(ls) + mu   (forward)   |   y' = (y - mu) * exp(-ls)   (inverse)
