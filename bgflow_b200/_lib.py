@@ -20,7 +20,7 @@ ERRORS = {-1: "BGX_ERR_INVALID (bad argument / inconsistent shapes)",
           -4: "BGX_ERR_CUDA"}
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3
-FLAG_INVERSE, FLAG_PRESERVE_VOLUME, FLAG_CIRCULAR, FLAG_BF16X3, FLAG_FORCE_SIMT = 1, 2, 4, 8, 16
+FLAG_INVERSE, FLAG_PRESERVE_VOLUME, FLAG_CIRCULAR, FLAG_BF16X6, FLAG_FORCE_SIMT = 1, 2, 4, 8, 16
 
 
 class bgx_mlp(C.Structure):

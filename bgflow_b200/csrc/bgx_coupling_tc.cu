@@ -22,10 +22,12 @@
 //
 // TMEM columns: [0,128) ACC0, [128,256) ACC1, [256,320) A1, [320,384) A2, [384,448) A3.
 // Numerics: every fp32 operand is split exactly into bf16 terms (x = x1 + x2 + x3, 24 mantissa
-// bits).  Default "bf16x6": a1b1 + a2b1 + a1b2 + a2b2 + a3b1 + a1b3 with fp32 accumulation (the
-// dropped products are < 2^-24 relative: fp32-equivalent).  BGX_FLAG_BF16X3: a1b1 + a2b1 + a1b2
-// (~2^-16 relative).  Measured on B200: a kind::tf32 128x128x8 MMA takes 136 cycles, a kind::f16
+// bits).  Default "bf16x3": a1b1 + a2b1 + a1b2 with fp32 accumulation (~2^-16 relative per
+// product; 6e-7 max error over the 8-block golden stack).  BGX_FLAG_BF16X6 adds a2b2 + a3b1 + a1b3
+// (the dropped products are < 2^-24 relative: fp32-equivalent) at twice the tensor-core cost.  Measured on B200: a kind::tf32 128x128x8 MMA takes 136 cycles, a kind::f16
 // 128x128x16 MMA 64, so 6 bf16 products cost half of a 3xTF32 scheme and are more accurate.
+#include <cstdlib>
+
 #include "bgx_coupling.cuh"
 #include "bgx_tc.cuh"
 
@@ -35,7 +37,7 @@ using namespace tc;
 constexpr int TC_THREADS = 640;
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_TM = 128;
-constexpr int TC_STAGES = 8;
+constexpr int TC_MAX_STAGES = 12;
 constexpr uint32_t TILE_BYTES = 16384;
 constexpr int COL_ACC0 = 0, COL_ACC1 = 128, COL_A = 256, COL_A_STRIDE = 64;   // A term t at COL_A + 64 t
 constexpr int NB = 8;            // spline bins handled by this kernel
@@ -69,6 +71,7 @@ struct TcArgs {
   int bias_floats;   // total bias floats staged in shared memory
   int ldy;           // leading dimension of the staged y tile (odd: conflict-free per-row access)
   int stages;        // weight ring depth
+  int ldc;           // leading dimension of the staged conditioner tile (odd)
   unsigned long long* trace;   // debug timeline of CTA 0 (or NULL): [0] = count, then (clock, code) pairs
   int trace_cap;
 };
@@ -86,8 +89,8 @@ __device__ __forceinline__ void tc_trace(const TcArgs& a, int role, int ev, long
 }
 
 struct TcSmem {
-  uint64_t full[TC_STAGES];
-  uint64_t empty[TC_STAGES];
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
   uint64_t x_ready;      // 16 arrivals: layer-0 operand staged in TMEM
   uint64_t a_ready;      // 16 arrivals: hidden activations staged in TMEM
   uint64_t acc_full_h;   // hidden-layer accumulator complete
@@ -95,6 +98,8 @@ struct TcSmem {
   uint64_t acc_empty[2]; // 16 arrivals: every epilogue warp has pulled its dims of the chunk
   uint64_t y_full[2];    // 2 arrivals (I/O warps): transformed-input tile staged in shared memory
   uint64_t y_done[2];    // 16 arrivals (epilogue warps): tile's outputs are in shared memory
+  uint64_t c_full;       // 2 arrivals (I/O warps): next tile's conditioner input staged in shared memory
+  uint64_t c_free;       // 16 arrivals (epilogue warps): conditioner tile consumed
   uint32_t tmem_base;
   uint32_t pad;
   float dl_part[4][TC_TM];
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
   TcSmem* S = (TcSmem*)(base + a.stages * TILE_BYTES);
   float* bias_s = (float*)(S + 1);                               // all layers' biases, concatenated
   float* ybuf = bias_s + a.bias_floats;                          // 2 x [128][ldy] staged y tiles
+  float* cbuf = ybuf + 2 * TC_TM * a.ldy;                        // [128][ldc] staged conditioner tile
   const int NST = a.stages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,6 +251,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     mbar_init(&S->y_full[1], 2);
     mbar_init(&S->y_done[0], TC_EPI_WARPS);
     mbar_init(&S->y_done[1], TC_EPI_WARPS);
+    mbar_init(&S->c_full, 2);
+    mbar_init(&S->c_free, TC_EPI_WARPS);
     fence_mbar_init();
   }
   {  // biases -> shared memory (layer l at offset boff[l])
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
           for (int c = 0; c < nch; ++c) {
             const int buf = last ? (c & 1) : 0;
             // accumulator free?  (hidden-layer reads are covered by a_ready / x ordering)
+            const long long te0 = a.trace ? clock64() : 0;
             if (buf == 0) {
               const bool need = last ? (c >= 2) : (l == 0 && !first);
               if (need) { mbar_wait(&S->acc_empty[0], ph_e0, a.status); ph_e0 ^= 1; }
@@ -311,15 +320,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
               if (need) { mbar_wait(&S->acc_empty[1], ph_e1, a.status); ph_e1 ^= 1; }
             }
             tc_fence_after();
+            if (a.trace) tc_trace(a, 1, 4, mma_it, (int)((clock64() - te0) >> 6));  // cycles/64 waiting for a free accumulator
             const uint32_t d_tmem = tmem + (buf ? COL_ACC1 : COL_ACC0);
             uint32_t acc = 0;
+            long long w_full = 0;
             for (int t = 0; t < kt; ++t) {
               int st_[3];
+              const long long tw0 = a.trace ? clock64() : 0;
               for (int part = 0; part < NT; ++part) {
                 st_[part] = stage;
                 mbar_wait(&S->full[stage], phase, a.status);
                 if (++stage == NST) { stage = 0; phase ^= 1; }
               }
+              if (a.trace) w_full += clock64() - tw0;
               tc_fence_after();
               const int nk = min(4, ksteps_total - t * 4);
               const uint32_t b1 = smem_u32(ring + st_[0] * TILE_BYTES);
@@ -345,6 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
             }
             mma_commit(last ? &S->acc_full[buf] : &S->acc_full_h);
             tc_trace(a, 1, 2, mma_it, last ? 16 + c : l);   // chunk / layer issued
+            tc_trace(a, 1, 3, mma_it, (int)(w_full >> 6));  // cycles/64 spent waiting for weight tiles
           }
         }
         first = false;
@@ -369,12 +383,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->y_full[b]);
     };
+    // conditioner input of a tile (WrapPeriodic folded in), [128][ldc]
+    const int K0 = a.net.K[0];
+    auto load_cond_tile = [&](long long tile) {
+      const int ne = TC_TM * K0;
+#pragma unroll 4
+      for (int idx = t64; idx < ne; idx += 64) {
+        const int r = idx / K0, k = idx - r * K0;
+        cbuf[r * a.ldc + k] = load_cond(a.cond, a.net, a.B, tile * TC_TM + r, k);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->c_full);
+    };
     long long n_my = (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    if (n_my > 0) load_cond_tile(blockIdx.x);
     if (n_my > 0) load_tile(blockIdx.x, 0);
     if (n_my > 1) load_tile(blockIdx.x + (long long)gridDim.x, 1);
     for (long long it = 0; it < n_my; ++it) {
       const int b = (int)(it & 1);
       const long long tile = blockIdx.x + it * gridDim.x;
+      if (it + 1 < n_my) {            // conditioner tile of the next tile: consumed at the end of this one
+        mbar_wait(&S->c_free, (uint32_t)(it & 1), a.status);
+        load_cond_tile(tile + gridDim.x);
+      }
       mbar_wait(&S->y_done[b], (uint32_t)((it >> 1) & 1), a.status);
       const float* Y = ybuf + b * TC_TM * a.ldy;
 #pragma unroll 8
@@ -397,15 +428,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     uint32_t ph_h = 0, ph_f0 = 0, ph_f1 = 0;
     const int last_off = [&] { int o = 0; for (int l = 0; l < L - 1; ++l) o += a.net.Np[l]; return o; }();
 
-    auto stage_x = [&](long long tile) {
-      const long long row = tile * TC_TM + r_in_tile;
+    uint32_t ph_c = 0;
+    auto stage_x = [&]() {
+      // conditioner tile (staged by the I/O warps) -> bf16 terms -> A operand of layer 0
+      mbar_wait(&S->c_full, ph_c, a.status);
+      ph_c ^= 1;
       const int K0 = a.net.K[0];
+      const float* crow = cbuf + r_in_tile * a.ldc;
       for (int b0 = j * 16; b0 < K0; b0 += 64) {
         uint32_t t1[8], t2[8], t3[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float v0 = load_cond(a.cond, a.net, a.B, row, b0 + 2 * i);
-          const float v1 = load_cond(a.cond, a.net, a.B, row, b0 + 2 * i + 1);
+          const int k = b0 + 2 * i;
+          const float v0 = k < K0 ? crow[k] : 0.f;
+          const float v1 = k + 1 < K0 ? crow[k + 1] : 0.f;
           split_bf16(v0, v1, NT, t1[i], t2[i], t3[i]);
         }
         const uint32_t col = tmem + lane_base + COL_A + b0 / 2;
@@ -416,7 +452,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S->x_ready);
+      if (lane == 0) {
+        mbar_arrive(&S->x_ready);
+        mbar_arrive(&S->c_free);
+      }
     };
 
     bool first = true;
@@ -425,7 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
       const long long row = tile * TC_TM + r_in_tile;
       const int yb = (int)(it & 1);
       float* yrow = ybuf + yb * TC_TM * a.ldy + r_in_tile * a.ldy;
-      if (first) stage_x(tile);
+      if (first) stage_x();
       first = false;
       // ---- hidden layers: ACC0 -> bias + activation -> A operand of the next layer
       int boff = 0;
@@ -501,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         if (warp == 4) tc_trace(a, 2, 4, it, c);   // my dims of the chunk done
         if (c == a.npass - 1) {
           const long long next = tile + gridDim.x;
-          if (next < a.ntiles) stage_x(next);
+          if (next < a.ntiles) stage_x();
           if (warp == 4) tc_trace(a, 2, 5, it, c); // next tile's x staged
         }
       }
@@ -547,7 +586,8 @@ bool spline_tc_eligible(const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, in
   const int d_t_max = net->N[L - 1] / 128 * DPP;
   size_t bias = 0;
   for (int l = 0; l < L; ++l) bias += net->Np[l];
-  if (1024 + sizeof(TcSmem) + 4 * (bias + 2 * TC_TM * (size_t)(d_t_max | 1)) + 64 + 4 * TILE_BYTES > 227 * 1024)
+  if (1024 + sizeof(TcSmem) + 4 * (bias + 2 * TC_TM * (size_t)(d_t_max | 1) + TC_TM * (size_t)(net->K[0] | 1)) + 64 +
+          6 * TILE_BYTES > 227 * 1024)
     return false;
   return true;
 }
@@ -573,7 +613,7 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
     bias_floats += net->Np[l];
   }
   a.npass = net->N[net->n_layers - 1] / 128;
-  a.nterms = (flags & BGX_FLAG_BF16X3) ? 2 : 3;
+  a.nterms = (flags & BGX_FLAG_BF16X6) ? 3 : 2;
   a.inverse = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
   spline_params_from_cfg(cfg, a.sp);
   {
@@ -600,9 +640,11 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   }
   a.bias_floats = bias_floats;
   a.ldy = d_t | 1;
-  const size_t fixed = 1024 + sizeof(TcSmem) + sizeof(float) * ((size_t)bias_floats + 2 * TC_TM * a.ldy) + 64;
-  a.stages = TC_STAGES;
-  while (a.stages > 4 && fixed + (size_t)a.stages * TILE_BYTES > 227 * 1024) a.stages -= 2;
+  a.ldc = net->K[0] | 1;
+  const size_t fixed = 1024 + sizeof(TcSmem) +
+                       sizeof(float) * ((size_t)bias_floats + 2 * TC_TM * a.ldy + TC_TM * a.ldc) + 64;
+  a.stages = TC_MAX_STAGES;     // as deep a weight ring as shared memory allows
+  while (a.stages > 4 && fixed + (size_t)a.stages * TILE_BYTES > 227 * 1024) a.stages -= 1;
   const size_t smem = fixed + (size_t)a.stages * TILE_BYTES;
   if (smem > 227 * 1024) return BGX_ERR_UNSUPPORTED;
   auto kern = a.inverse ? spline_coupling_tc_kernel<true> : spline_coupling_tc_kernel<false>;
@@ -612,7 +654,13 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
     if (rc) return rc;
     configured[a.inverse] = smem;
   }
-  const unsigned grid = (unsigned)std::min<long long>(a.ntiles, sm_count);
+  static int max_ctas = -1;
+  if (max_ctas < 0) {   // debug knob: cap the persistent grid (isolates per-SM from chip-wide effects)
+    const char* e = getenv("BGX_TC_MAX_CTAS");
+    max_ctas = e ? atoi(e) : 0;
+  }
+  unsigned grid = (unsigned)std::min<long long>(a.ntiles, sm_count);
+  if (max_ctas > 0) grid = std::min<unsigned>(grid, (unsigned)max_ctas);
   kern<<<grid, TC_THREADS, smem, st>>>(a);
   return post_launch();
 }

@@ -30,11 +30,12 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-#: kernel selection: ``precision`` "bf16x6" (default: operands split exactly into three bf16
-#: terms, six tensor-core products, fp32 accumulate ~ fp32 accuracy) or "bf16x3" (two terms,
-#: three products, ~1e-5 relative error in the conditioner); ``force_simt`` runs the
-#: shape-general fp32 SIMT kernel even where the tensor-core kernel applies.
-config = {"precision": "bf16x6", "force_simt": False}
+#: kernel selection: ``precision`` "bf16x3" (default: fp32 operands split exactly into bf16 terms
+#: x = x1 + x2 (+ x3); three tensor-core products a1b1 + a2b1 + a1b2 with fp32 accumulation:
+#: ~2^-16 relative per product, measured 6e-7 max abs error over the 8-block golden stack) or
+#: "bf16x6" (three terms, six products: fp32-equivalent, twice the tensor-core time);
+#: ``force_simt`` runs the shape-general fp32 SIMT kernel even where the tensor-core kernel applies.
+config = {"precision": "bf16x3", "force_simt": False}
 
 _status = {}
 
@@ -58,9 +59,9 @@ def _mode_flags():
     f = 0
     if config.get("force_simt"):
         f |= _lib.FLAG_FORCE_SIMT
-    if config.get("precision") == "bf16x3":
-        f |= _lib.FLAG_BF16X3
-    elif config.get("precision") != "bf16x6":
+    if config.get("precision") == "bf16x6":
+        f |= _lib.FLAG_BF16X6
+    elif config.get("precision") != "bf16x3":
         raise ValueError("engine.config['precision'] must be 'bf16x6' or 'bf16x3'")
     return f
 

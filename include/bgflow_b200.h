@@ -120,7 +120,7 @@ typedef struct bgx_coupling_io {
 #define BGX_FLAG_INVERSE 1          /* evaluate bgflow's _inverse direction */
 #define BGX_FLAG_PRESERVE_VOLUME 2  /* affine.py:44-45 */
 #define BGX_FLAG_CIRCULAR 4         /* affine.py:56-57: y %= 1 (shift-only) */
-#define BGX_FLAG_BF16X3 8           /* tensor-core path: 3 bf16 products (~1e-5); default 6 products ~ fp32 */
+#define BGX_FLAG_BF16X6 8           /* tensor-core path: 6 bf16 products (fp32-equivalent); default 3 (~2^-16) */
 #define BGX_FLAG_FORCE_SIMT 16      /* always use the generic fp32 SIMT kernel */
 
 /* y' = y * exp(ls) + mu   (forward)   |   y' = (y - mu) * exp(-ls)   (inverse)

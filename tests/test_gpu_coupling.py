@@ -17,13 +17,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=["tc", "simt"], autouse=True)
+@pytest.fixture(params=["tc", "tc6", "simt"], autouse=True)
 def kernel_mode(request):
     """Every parity test runs on the tensor-core kernel (where the shape is eligible) and on the
     shape-general SIMT kernel."""
     from bgflow_b200 import engine
     old = dict(engine.config)
-    engine.config.update(force_simt=(request.param == "simt"), precision="bf16x6")
+    engine.config.update(force_simt=(request.param == "simt"),
+                         precision="bf16x6" if request.param == "tc6" else "bf16x3")
     yield request.param
     engine.check_pipeline_status(DEV)
     engine.config.update(old)
@@ -194,25 +195,27 @@ def test_affine_transformer_api_like_reference_tests():
         tr.forward(x.cpu(), y.cpu())       # no CPU fallback, by design
 
 
-def test_bf16x3_fast_mode_has_the_stated_tolerance(kernel_mode):
-    """engine.config['precision'] = 'bf16x3': two bf16 terms per operand, three tensor-core products
-    (~2^-16 relative error per product).  Stated tolerance over the 8-block stack: y 5e-4,
-    dlogp 5e-3 (vs 1e-4 / 1e-3 for the default fp32-equivalent bf16x6 mode)."""
+def test_precision_modes_report(kernel_mode):
+    """Both tensor-core precisions against the reference's fp64 run of the 8-block golden stack
+    (the numbers quoted in DESIGN.md); both sit far inside the 1e-4 / 1e-3 parity tolerance."""
     from bgflow_b200 import engine
-    if kernel_mode == "simt":
-        pytest.skip("tensor-core only")
+    if kernel_mode != "tc":
+        pytest.skip("runs once")
     g = load_golden("spline_d66_8blk")
     blocks, split = of.make_stack("spline", 66, 8, hidden=(128, 128), seed=0)
     flow = stack_from(blocks, split, DEV)
-    engine.config["precision"] = "bf16x3"
+    errs = {}
+    for prec in ("bf16x3", "bf16x6"):
+        engine.config["precision"] = prec
+        with torch.no_grad():
+            x, dlogp = flow(_t(g["z_f32"]))
+        errs[prec] = ((x.cpu().double() - torch.from_numpy(g["x_f64"])).abs().max().item(),
+                      (dlogp.cpu().double() - torch.from_numpy(g["dlogp_f64"])).abs().max().item())
+    engine.config.update(force_simt=True)
     with torch.no_grad():
         x, dlogp = flow(_t(g["z_f32"]))
-    _cmp(x, g["x_f64"], 5e-4, 5e-4)
-    _cmp(dlogp, g["dlogp_f64"], 5e-3, 1e-3)
-    err3 = (x.cpu().double() - torch.from_numpy(g["x_f64"])).abs().max().item()
-    engine.config["precision"] = "bf16x6"
-    with torch.no_grad():
-        x6, _ = flow(_t(g["z_f32"]))
-    err6 = (x6.cpu().double() - torch.from_numpy(g["x_f64"])).abs().max().item()
-    print(f"max |x - ref_fp64|: bf16x3 {err3:.2e}, bf16x6 {err6:.2e}")
-    assert err6 <= err3 + 1e-6
+    errs["simt fp32"] = ((x.cpu().double() - torch.from_numpy(g["x_f64"])).abs().max().item(),
+                         (dlogp.cpu().double() - torch.from_numpy(g["dlogp_f64"])).abs().max().item())
+    print("max abs error vs reference fp64 (x, dlogp):", {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in errs.items()})
+    for k, (ex, ed) in errs.items():
+        assert ex < 1e-4 and ed < 1e-3, (k, ex, ed)

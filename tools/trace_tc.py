@@ -12,7 +12,7 @@ import bgflow_b200 as bg
 from bgflow_b200 import _lib
 
 ROLE = {1: "mma", 2: "epi"}
-EV = {(1, 1): "operand ready -> issue layer", (1, 2): "issued (layer<16 / 16+chunk)",
+EV = {(1, 3): "  waited for weights (x64 cyc)", (1, 4): "  waited for accumulator (x64 cyc)", (1, 1): "operand ready -> issue layer", (1, 2): "issued (layer<16 / 16+chunk)",
       (2, 1): "hidden acc observed", (2, 2): "hidden handed over", (2, 3): "chunk acc observed",
       (2, 4): "chunk dims done", (2, 5): "next x staged", (2, 6): "y tile available"}
 
@@ -22,7 +22,7 @@ def main():
     dev = "cuda:0"
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    B = sms * 128 * tiles
+    B = int(os.environ.get('BGX_TC_MAX_CTAS', sms)) * 128 * tiles
     torch.manual_seed(0)
     tr = bg.ConditionalSplineTransformer(bg.DenseNet([33, 128, 128, 825], activation=torch.nn.SiLU())).to(dev)
     x = torch.rand(B, 33, device=dev)
