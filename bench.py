@@ -258,7 +258,13 @@ def main():
         return 0
 
     import bgflow_b200 as bg
-    from bgflow_b200 import _lib
+    from bgflow_b200 import _lib, engine
+    if os.environ.get("BGX_PRECISION"):
+        engine.config["precision"] = os.environ["BGX_PRECISION"]
+    if os.environ.get("BGX_FORCE_SIMT"):
+        engine.config["force_simt"] = True
+    config["kernel"] = ("fp32 SIMT" if engine.config["force_simt"] else
+                        f"tcgen05 kind::f16, operands split into bf16 terms ({engine.config['precision']})")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     flow = build_flow(kind, dim, n_blocks, hidden, dev)

@@ -88,6 +88,13 @@ __device__ __forceinline__ void tc_trace(const TcArgs& a, int role, int ev, long
   }
 }
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_drain() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 struct TcSmem {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -375,11 +382,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     auto load_tile = [&](long long tile, int b) {
       float* Y = ybuf + b * TC_TM * a.ldy;
 #pragma unroll 8
+      // asynchronous 4-byte copies: the whole tile is in flight at once (the I/O warps are
+      // latency-, not bandwidth-limited, and the rows come from DRAM)
       for (int idx = t64; idx < nelem; idx += 64) {
         const int r = idx / a.D_t, d = idx - r * a.D_t;
         const long long row = tile * TC_TM + r;
-        Y[r * a.ldy + d] = row < a.B ? __ldg(seg_addr(a.tin, row, d)) : 0.5f;
+        if (row < a.B) cp_async4(&Y[r * a.ldy + d], seg_addr(a.tin, row, d));
+        else Y[r * a.ldy + d] = 0.5f;
       }
+      cp_async_drain();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->y_full[b]);
     };
@@ -387,11 +398,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     const int K0 = a.net.K[0];
     auto load_cond_tile = [&](long long tile) {
       const int ne = TC_TM * K0;
-#pragma unroll 4
       for (int idx = t64; idx < ne; idx += 64) {
         const int r = idx / K0, k = idx - r * K0;
-        cbuf[r * a.ldc + k] = load_cond(a.cond, a.net, a.B, tile * TC_TM + r, k);
+        const long long row = tile * TC_TM + r;
+        const int code = a.net.in_map[k];
+        float* dst = &cbuf[r * a.ldc + k];
+        if (row >= a.B) *dst = 0.f;
+        else if ((code >> 24) == 0) cp_async4(dst, seg_addr(a.cond, row, code & 0xffffff));
+        else *dst = load_cond(a.cond, a.net, a.B, row, k);      // periodic input: cos / sin
       }
+      cp_async_drain();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->c_full);
     };
