@@ -175,6 +175,63 @@ def time_cpu_port(blocks, kind, dim, rows, reps, threads):
     return times
 
 
+def time_gpu_torch_port(blocks, kind, dim, rows, dev):
+    """The reference's single-GPU PyTorch path, restated: the same op-by-op ATen sequence as the
+    CPU baseline (oracle/flows.py) on CUDA tensors, fp32, no_grad, CUDA events."""
+    from oracle import flows as of
+    dblocks = []
+    for b in blocks:
+        nb = dict(b)
+        for key in ("shift", "scale", "params_net"):
+            if nb.get(key) is not None:
+                m = nb[key]
+                nb[key] = of.MLP([w.to(dev) for w in m.weights], [x.to(dev) for x in m.biases], m.act, m.periodic)
+        dblocks.append(nb)
+    g = torch.Generator().manual_seed(1)
+    z = (torch.rand(rows, dim, generator=g) if kind == "spline" else torch.randn(rows, dim, generator=g)).to(dev)
+    with torch.no_grad():
+        for _ in range(2):
+            of.coupling_stack(dblocks, z, dim // 2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            of.coupling_stack(dblocks, z, dim // 2)
+        e1.record()
+        torch.cuda.synchronize()
+    return rows * 3 / (e0.elapsed_time(e1) * 1e-3)
+
+
+def bench_ic(args, dev):
+    """Secondary measurement: the Z-matrix <-> Cartesian kernels on Ala2 (532 algorithmic bytes/sample)."""
+    import bgflow_b200 as bg
+    from oracle import ic as oic
+    B = args.batch_per_gpu
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    g = torch.Generator().manual_seed(1)
+    xyz = (torch.as_tensor(oic.ALA2_XYZ, dtype=torch.float32).reshape(1, -1)
+           + 0.01 * torch.randn(B, 66, generator=g)).to(dev)
+    out = {}
+    pk = peaks()
+    with torch.no_grad():
+        ics = ic(xyz)[:-1]
+        for name, fn in (("xyz_to_ic", lambda: ic(xyz)), ("ic_to_xyz", lambda: ic(*ics, inverse=True))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            gbs = 532 * B / (ms * 1e-3) / 1e9
+            out[name] = {"samples_per_s": B / (ms * 1e-3), "ms": ms, "hbm_GBps_algorithmic": gbs,
+                         "hbm_frac": gbs / pk["hbm_gbs"]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,6 +243,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time the IC kernels and the restated single-GPU PyTorch path (adds to the JSON line)")
     args = ap.parse_args()
     if args.warmup < 3 and not DRYRUN:
         args.warmup = 3
@@ -357,6 +416,13 @@ def main():
         out["cpu_baseline"] = {"value": rows / best, "unit": "samples/s", "cores": threads,
                                "host_cpus": os.cpu_count(), "kind": "port",
                                "sample": f"{rows} rows of the same workload, best of 2 after 1 warm-up"}
+    if rank == 0 and world == 1 and args.extras:
+        blocks = oracle_blocks_from(flow)
+        out["extras"] = {
+            "gpu_pytorch_port": {"value": time_gpu_torch_port(blocks, kind, dim, 65536, dev), "unit": "samples/s",
+                                 "sample": "65536 rows; oracle/flows.py op sequence on CUDA tensors (the reference's "
+                                           "single-GPU PyTorch path, restated)"},
+            "ic_ala2": bench_ic(args, dev)}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -287,10 +287,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
           for (int c = 0; c < nch; ++c)
             for (int t = 0; t < kt; ++t)
               for (int part = 0; part < NT; ++part) {
+                const long long tp0 = a.trace ? clock64() : 0;
                 mbar_wait(&S->empty[stage], phase ^ 1, a.status);
                 const uint16_t* src = a.wb[part][l] + ((long long)c * kt + t) * 8192;
                 mbar_expect_tx(&S->full[stage], TILE_BYTES);
                 bulk_g2s(ring + stage * TILE_BYTES, src, TILE_BYTES, &S->full[stage]);
+                if (a.trace) tc_trace(a, 0, 1 + (l == L - 1 ? c : 0), (clock64() - tp0) >> 6, stage);
                 if (++stage == NST) { stage = 0; phase ^= 1; }
               }
         }
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
             if (a.trace) tc_trace(a, 1, 4, mma_it, (int)((clock64() - te0) >> 6));  // cycles/64 waiting for a free accumulator
             const uint32_t d_tmem = tmem + (buf ? COL_ACC1 : COL_ACC0);
             uint32_t acc = 0;
-            long long w_full = 0;
+            long long w_full = 0, w_issue = 0;
             for (int t = 0; t < kt; ++t) {
               int st_[3];
               const long long tw0 = a.trace ? clock64() : 0;
@@ -341,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
               }
               if (a.trace) w_full += clock64() - tw0;
               tc_fence_after();
+              const long long ti0 = a.trace ? clock64() : 0;
               const int nk = min(4, ksteps_total - t * 4);
               const uint32_t b1 = smem_u32(ring + st_[0] * TILE_BYTES);
               const uint32_t b2 = smem_u32(ring + st_[1] * TILE_BYTES);
@@ -362,10 +365,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
                 acc = 1;
               }
               for (int part = 0; part < NT; ++part) mma_commit(&S->empty[st_[part]]);
+              if (a.trace) w_issue += clock64() - ti0;
             }
             mma_commit(last ? &S->acc_full[buf] : &S->acc_full_h);
             tc_trace(a, 1, 2, mma_it, last ? 16 + c : l);   // chunk / layer issued
             tc_trace(a, 1, 3, mma_it, (int)(w_full >> 6));  // cycles/64 spent waiting for weight tiles
+            tc_trace(a, 1, 5, mma_it, (int)(w_issue >> 6)); // cycles/64 spent issuing MMAs + commits
           }
         }
         first = false;

@@ -65,8 +65,12 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
   if (warp == 4) {
     if (lane == 0) {
       const int nt = mode == 3 ? (K + 63) / 64 : ntile;     // bf16 tiles are 64 wide
+      const long long tb0 = clock64();
       mbar_expect_tx(b_full, (uint32_t)nt * 16384u);
       for (int t = 0; t < nt; ++t) bulk_g2s(Bs + t * 4096, Wsw + t * 4096, 16384u, b_full);
+      mbar_wait(b_full, 0, status);
+      status[2] = (int)(clock64() - tb0);     // cycles until all operand tiles have landed
+      status[3] = nt;
     }
     __syncwarp();
   } else if (warp == 5) {
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
 using namespace bgx;
 
 // A [128][K], W [128][K] (K multiple of 32, <= 128), scratch >= 128*K floats, out [128][128],
-// status: TWO device ints: [0] set to 1 if an mbarrier wait timed out, [1] = cycles spent by the MMA
+// status: FOUR device ints ([2] = cycles for the bulk copies of [3] 16 KB tiles to land): [0] set to 1 if an mbarrier wait timed out, [1] = cycles spent by the MMA
 // loop when the mode carries a repeat count (mode | reps << 4; throughput probe, results then meaningless).
 extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                                int* status, void* stream) {

@@ -16,7 +16,7 @@ def _run(mode, A, W):
     K = A.shape[1]
     scratch = torch.empty(128 * K, device=DEV)
     out = torch.full((128, 128), float("nan"), device=DEV)
-    status = torch.zeros(2, dtype=torch.int32, device=DEV)
+    status = torch.zeros(4, dtype=torch.int32, device=DEV)
     rc = lib.bgx_tc_selftest(mode, A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(),
                              status.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "bgx_tc_selftest")

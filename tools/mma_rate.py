@@ -18,9 +18,10 @@ scratch = torch.empty(128 * K, device=dev)
 out = torch.empty(128, 128, device=dev)
 for mode, name in ((0, "tf32 SS (A in smem)"), (1, "tf32 TS (A in TMEM)"), (3, "bf16 TS (A in TMEM)")):
     for reps in (16, 64, 256):
-        st = torch.zeros(2, dtype=torch.int32, device=dev)
+        st = torch.zeros(4, dtype=torch.int32, device=dev)
         rc = lib.bgx_tc_selftest(mode | (reps << 4), A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(),
                                  st.data_ptr(), None)
         torch.cuda.synchronize()
         n = reps * K // (16 if mode == 3 else 8)
+        print(f"  bulk copies: {int(st[3])} x 16 KB landed after {int(st[2])} cycles")
         print(f"{name}: {n} MMAs in {int(st[1])} cycles -> {int(st[1]) / n:.1f} cycles/MMA (timeout={int(st[0])})")

@@ -11,8 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bgflow_b200 as bg
 from bgflow_b200 import _lib
 
-ROLE = {1: "mma", 2: "epi"}
-EV = {(1, 3): "  waited for weights (x64 cyc)", (1, 4): "  waited for accumulator (x64 cyc)", (1, 1): "operand ready -> issue layer", (1, 2): "issued (layer<16 / 16+chunk)",
+ROLE = {0: "tma", 1: "mma", 2: "epi"}
+EV = {(1, 5): "  issuing MMAs+commits (x64 cyc)", (1, 3): "  waited for weights (x64 cyc)", (1, 4): "  waited for accumulator (x64 cyc)", (1, 1): "operand ready -> issue layer", (1, 2): "issued (layer<16 / 16+chunk)",
       (2, 1): "hidden acc observed", (2, 2): "hidden handed over", (2, 3): "chunk acc observed",
       (2, 4): "chunk dims done", (2, 5): "next x staged", (2, 6): "y tile available"}
 
@@ -46,7 +46,7 @@ def main():
         key = role
         dt = clk - last.get(key, clk)
         last[key] = clk
-        print(f"{clk - t0:9d} (+{dt:7d}) {ROLE.get(role, role):4s} tile#{it} {EV.get((role, e), e):32s} {x_}")
+        print(f"{clk - t0:9d} (+{dt:7d}) {ROLE.get(role, role):4s} tile#{it} {str(EV.get((role, e), e)):32s} {x_}")
 
 
 if __name__ == "__main__":
