@@ -47,13 +47,20 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
   uint64_t* acc_full = bars + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 4);
 
-  const int mode = mode_reps & 15, reps = max(1, mode_reps >> 4), nshape = (mode_reps >> 24) ? 256 : 128;
+  // probe variants (bits 28..30 of the mode word): commit every 12 MMAs / alternate A column
+  // ranges / epilogue warps hammer tcgen05.ld while the MMAs run
+  const int mode = mode_reps & 15, reps = max(1, (mode_reps >> 4) & 0xffff);
+  const bool v_commit = (mode_reps >> 28) & 1, v_alt = (mode_reps >> 29) & 1, v_ld = (mode_reps >> 30) & 1;
+  uint64_t* dummy_bar = bars + 3;
+  volatile int* done_flag = (volatile int*)(bars + 6);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile = K / 32;
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
     mbar_init(a_ready, 4);
     mbar_init(acc_full, 1);
+    mbar_init(dummy_bar, 1 << 20);
+    *done_flag = 0;
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc<256>(tmem_slot);
@@ -80,11 +87,13 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
       long long t0 = clock64();
       if (ok && mode == 3) {
         const uint32_t idesc = idesc_bf16(128, 128);
+        int n = 0;
         for (int rep = 0; rep < reps; ++rep)
           for (int ks = 0; ks < K / 16; ++ks) {
             const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
-            mma_bf16_ts(tmem + ST_ACC_COL, tmem + ST_A_COL + ks * 8, smem_desc_sw128(smem_u32(Bs) + off), idesc,
-                        (ks | rep) > 0);
+            const uint32_t acol = ST_A_COL + ks * 8 + ((v_alt && (n & 1)) ? 64 : 0);
+            mma_bf16_ts(tmem + ST_ACC_COL, tmem + acol, smem_desc_sw128(smem_u32(Bs) + off), idesc, (ks | rep) > 0);
+            if (v_commit && (++n % 12) == 0) mma_commit(dummy_bar);
           }
       } else if (ok) {
         const uint32_t idesc = idesc_tf32(128, 128);
@@ -105,6 +114,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
         mbar_wait(acc_full, 0, status);
         status[1] = (int)(clock64() - t0);
       }
+      *done_flag = 1;
     }
     __syncwarp();
   } else {
@@ -138,6 +148,16 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(a_ready);
+    if (v_ld) {          // concurrent TMEM reads of the accumulator while the MMAs run
+      uint32_t sink = 0;
+      while (!*done_flag) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + ST_ACC_COL + 64, r);
+        tmem_ld_wait();
+        sink ^= r[lane & 31];
+      }
+      if (sink == 0x12345678u) out[0] = 1.f;
+    }
     mbar_wait(acc_full, 0, status);
     tc_fence_after();
     if (mode == 2) {

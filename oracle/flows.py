@@ -278,7 +278,7 @@ def coupling_stack(blocks, x, split, inverse=False):
     (including the last, as in notebooks/alanine_dipeptide_basics.py:209-218).
     """
     xs = list(torch.split(x, [split, x.shape[-1] - split], dim=-1))
-    dlogp = torch.zeros(*x.shape[:-1], 1, dtype=x.dtype)
+    dlogp = torch.zeros(*x.shape[:-1], 1, dtype=x.dtype, device=x.device)
     if not inverse:
         for blk in blocks:
             xs, d = coupling_block(blk, xs, inverse=False)

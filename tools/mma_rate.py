@@ -25,3 +25,16 @@ for mode, name in ((0, "tf32 SS (A in smem)"), (1, "tf32 TS (A in TMEM)"), (3, "
         n = reps * K // (16 if mode == 3 else 8)
         print(f"  bulk copies: {int(st[3])} x 16 KB landed after {int(st[2])} cycles")
         print(f"{name}: {n} MMAs in {int(st[1])} cycles -> {int(st[1]) / n:.1f} cycles/MMA (timeout={int(st[0])})")
+
+print("--- bf16 TS variants (2048 MMAs)")
+for label, bits in (("baseline", 0), ("commit every 12", 1 << 28), ("alternate A cols", 1 << 29),
+                    ("concurrent tcgen05.ld", 1 << 30), ("all three", 7 << 28)):
+    st = torch.zeros(4, dtype=torch.int32, device=dev)
+    reps = 256
+    word = 3 | (reps << 4) | bits
+    if word >= 1 << 31:
+        word -= 1 << 32
+    rc = lib.bgx_tc_selftest(word, A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(), st.data_ptr(), None)
+    torch.cuda.synchronize()
+    n = reps * K // 16
+    print(f"{label:24s}: {int(st[1]) / n:.1f} cycles/MMA (rc={rc}, timeout={int(st[0])})")
