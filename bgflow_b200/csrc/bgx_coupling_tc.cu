@@ -4,8 +4,8 @@
 // on chip (replaces coupling.py:162-182 + spline.py:87-188 + dense.py:47-48 + nflows' RQS):
 //
 //   warp 0      bulk-TMA producer: streams pre-swizzled 16 KB bf16 weight tiles (the two or
-//               three terms of the exact split W = b1 + b2 + b3) from L2 through an 8-stage
-//               shared-memory ring
+//               three terms of the exact split W = b1 + b2 + b3) from L2 through a ring of
+//               k-tile slots in shared memory
 //   warp 1      tcgen05.mma issuer (kind::f16 / bf16, M=128 N=128 K=16): A operand =
 //               activations in TENSOR MEMORY (bf16 terms a1 | a2 | a3, two elements per
 //               32-bit cell), B operand = weight tiles in shared memory, fp32 accumulators in
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = base;                                          // a.stages x 16 KB
-  TcSmem* S = (TcSmem*)(base + a.stages * TILE_BYTES);
+  TcSmem* S = (TcSmem*)(base + (size_t)a.stages * a.nterms * TILE_BYTES);
   float* bias_s = (float*)(S + 1);                               // all layers' biases, concatenated
   float* ybuf = bias_s + a.bias_floats;                          // 2 x [128][ldy] staged y tiles
   float* cbuf = ybuf + 2 * TC_TM * a.ldy;                        // [128][ldc] staged conditioner tile
@@ -277,26 +277,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer
+    // Ring of NST slots; a slot holds the NT bf16 term tiles of ONE 64-wide k-tile (one `full`
+    // barrier, expect_tx = NT x 16 KB).  Slots are not released one by one: tcgen05.commit costs
+    // ~700 cycles of tensor-pipe time (measured, tools/mma_rate.py), so the only commits are the
+    // per-unit accumulator commits the epilogue needs anyway (unit = hidden layer or 128-column
+    // chunk), and the producer frees all slots of a unit when it observes that same barrier.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int slot = 0;
+      long long filled = 0, released = 0;
+      // event cursor: walks the same (tile, layer, chunk) sequence as the fill cursor, behind it
+      long long e_tile = blockIdx.x;
+      int e_l = 0, e_c = 0;
+      uint32_t eph_h = 0, eph_f0 = 0, eph_f1 = 0;
       for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           const int nch = (l == L - 1) ? a.npass : 1;
           const int kt = a.ktiles[l];
           for (int c = 0; c < nch; ++c)
-            for (int t = 0; t < kt; ++t)
-              for (int part = 0; part < NT; ++part) {
-                const long long tp0 = a.trace ? clock64() : 0;
-                mbar_wait(&S->empty[stage], phase ^ 1, a.status);
-                const uint16_t* src = a.wb[part][l] + ((long long)c * kt + t) * 8192;
-                mbar_expect_tx(&S->full[stage], TILE_BYTES);
-                bulk_g2s(ring + stage * TILE_BYTES, src, TILE_BYTES, &S->full[stage]);
-                if (a.trace) tc_trace(a, 0, 1 + (l == L - 1 ? c : 0), (clock64() - tp0) >> 6, stage);
-                if (++stage == NST) { stage = 0; phase ^= 1; }
+            for (int t = 0; t < kt; ++t) {
+              while (filled - released >= NST) {
+                // wait for the oldest not yet observed unit to complete; free its slots
+                if (e_l == L - 1) {
+                  if (e_c & 1) { mbar_wait(&S->acc_full[1], eph_f1, a.status); eph_f1 ^= 1; }
+                  else { mbar_wait(&S->acc_full[0], eph_f0, a.status); eph_f0 ^= 1; }
+                } else {
+                  mbar_wait(&S->acc_full_h, eph_h, a.status);
+                  eph_h ^= 1;
+                }
+                released += a.ktiles[e_l];
+                if (e_l == L - 1 && ++e_c < a.npass) continue;
+                e_c = 0;
+                if (++e_l == L) { e_l = 0; e_tile += gridDim.x; }
               }
+              uint8_t* dst = ring + (size_t)slot * NT * TILE_BYTES;
+              mbar_expect_tx(&S->full[slot], (uint32_t)NT * TILE_BYTES);
+              for (int part = 0; part < NT; ++part)
+                bulk_g2s(dst + part * TILE_BYTES, a.wb[part][l] + ((long long)c * kt + t) * 8192, TILE_BYTES,
+                         &S->full[slot]);
+              ++filled;
+              if (++slot == NST) slot = 0;
+            }
         }
       }
+      (void)e_tile;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -334,20 +357,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
             uint32_t acc = 0;
             long long w_full = 0, w_issue = 0;
             for (int t = 0; t < kt; ++t) {
-              int st_[3];
               const long long tw0 = a.trace ? clock64() : 0;
-              for (int part = 0; part < NT; ++part) {
-                st_[part] = stage;
-                mbar_wait(&S->full[stage], phase, a.status);
-                if (++stage == NST) { stage = 0; phase ^= 1; }
-              }
+              mbar_wait(&S->full[stage], phase, a.status);
+              const uint32_t sbase = smem_u32(ring + (size_t)stage * NT * TILE_BYTES);
+              if (++stage == NST) { stage = 0; phase ^= 1; }
               if (a.trace) w_full += clock64() - tw0;
               tc_fence_after();
               const long long ti0 = a.trace ? clock64() : 0;
               const int nk = min(4, ksteps_total - t * 4);
-              const uint32_t b1 = smem_u32(ring + st_[0] * TILE_BYTES);
-              const uint32_t b2 = smem_u32(ring + st_[1] * TILE_BYTES);
-              const uint32_t b3 = NT == 3 ? smem_u32(ring + st_[2] * TILE_BYTES) : 0;
+              const uint32_t b1 = sbase, b2 = sbase + TILE_BYTES, b3 = sbase + 2 * TILE_BYTES;
               for (int ks = 0; ks < nk; ++ks) {
                 const uint32_t kcol = (uint32_t)(t * 32 + ks * 8);          // 16 bf16 = 8 TMEM columns
                 const uint32_t a1 = tmem + COL_A + kcol, a2 = a1 + COL_A_STRIDE, a3 = a2 + COL_A_STRIDE;
@@ -364,7 +382,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
                 mma_bf16_ts(d_tmem, a1, d1, idesc, 1);
                 acc = 1;
               }
-              for (int part = 0; part < NT; ++part) mma_commit(&S->empty[st_[part]]);
               if (a.trace) w_issue += clock64() - ti0;
             }
             mma_commit(last ? &S->acc_full[buf] : &S->acc_full_h);
@@ -608,7 +625,7 @@ bool spline_tc_eligible(const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, in
   size_t bias = 0;
   for (int l = 0; l < L; ++l) bias += net->Np[l];
   if (1024 + sizeof(TcSmem) + 4 * (bias + 2 * TC_TM * (size_t)(d_t_max | 1) + TC_TM * (size_t)(net->K[0] | 1)) + 64 +
-          6 * TILE_BYTES > 227 * 1024)
+          9 * TILE_BYTES > 227 * 1024)
     return false;
   return true;
 }
@@ -664,9 +681,10 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   a.ldc = net->K[0] | 1;
   const size_t fixed = 1024 + sizeof(TcSmem) +
                        sizeof(float) * ((size_t)bias_floats + 2 * TC_TM * a.ldy + TC_TM * a.ldc) + 64;
-  a.stages = TC_MAX_STAGES;     // as deep a weight ring as shared memory allows
-  while (a.stages > 4 && fixed + (size_t)a.stages * TILE_BYTES > 227 * 1024) a.stages -= 1;
-  const size_t smem = fixed + (size_t)a.stages * TILE_BYTES;
+  a.stages = TC_MAX_STAGES;     // ring slots (one k-tile = nterms x 16 KB each): as many as fit
+  const size_t slot_bytes = (size_t)a.nterms * TILE_BYTES;
+  while (a.stages > 3 && fixed + (size_t)a.stages * slot_bytes > 227 * 1024) a.stages -= 1;
+  const size_t smem = fixed + (size_t)a.stages * slot_bytes;
   if (smem > 227 * 1024) return BGX_ERR_UNSUPPORTED;
   auto kern = a.inverse ? spline_coupling_tc_kernel<true> : spline_coupling_tc_kernel<false>;
   static size_t configured[2] = {0, 0};
