@@ -72,6 +72,8 @@ struct TcArgs {
   int ldy;           // leading dimension of the staged y tile (odd: conflict-free per-row access)
   int stages;        // weight ring depth
   int ldc;           // leading dimension of the staged conditioner tile (odd)
+  int y_dense;       // transformed in/out tensors are single dense 16-B aligned blocks: bulk TMA
+  int c_dense;       // conditioner likewise (and no input map): bulk TMA
   unsigned long long* trace;   // debug timeline of CTA 0 (or NULL): [0] = count, then (clock, code) pairs
   int trace_cap;
 };
@@ -95,7 +97,16 @@ __device__ __forceinline__ void cp_async_drain() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-struct TcSmem {
+// shared -> global bulk copy (TMA engine); completion tracked with bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct alignas(16) TcSmem {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t x_ready;      // 16 arrivals: layer-0 operand staged in TMEM
@@ -402,39 +413,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
     // global <-> shared staging of the transformed inputs / outputs, coalesced, double buffered,
     // so that the epilogue's dependency chain never waits on global memory
     const int t64 = threadIdx.x - 512;
-    const int nelem = TC_TM * a.D_t;
+    const int Dt = a.D_t, K0 = a.net.K[0];
+    // (row, column) walk of this thread over a [128 x W] tile with stride 64, without divisions
+    auto walk = [&](int W, auto&& body) {
+      int r = t64 / W, d = t64 - r * W;
+      const int dr = 64 / W, dd = 64 - dr * W;
+      for (; r < TC_TM; ) {
+        body(r, d);
+        r += dr; d += dd;
+        if (d >= W) { d -= W; ++r; }
+      }
+    };
+    auto full_rows = [&](long long tile) { return (tile + 1) * TC_TM <= a.B; };
+
     auto load_tile = [&](long long tile, int b) {
       float* Y = ybuf + b * TC_TM * a.ldy;
-#pragma unroll 8
-      // asynchronous 4-byte copies: the whole tile is in flight at once (the I/O warps are
-      // latency-, not bandwidth-limited, and the rows come from DRAM)
-      for (int idx = t64; idx < nelem; idx += 64) {
-        const int r = idx / a.D_t, d = idx - r * a.D_t;
+      if (a.y_dense && full_rows(tile)) {
+        // one 1-D bulk TMA copy: the [128 x D_t] block is contiguous in global memory
+        if (warp == 16 && lane == 0) {
+          mbar_expect_tx(&S->y_full[b], (uint32_t)(TC_TM * Dt * 4));
+          bulk_g2s(Y, a.tin.ptr[0] + tile * TC_TM * (long long)Dt, (uint32_t)(TC_TM * Dt * 4), &S->y_full[b]);
+        } else if (warp == 17 && lane == 0) {
+          mbar_arrive(&S->y_full[b]);
+        }
+        return;
+      }
+      walk(Dt, [&](int r, int d) {
         const long long row = tile * TC_TM + r;
         if (row < a.B) cp_async4(&Y[r * a.ldy + d], seg_addr(a.tin, row, d));
         else Y[r * a.ldy + d] = 0.5f;
-      }
+      });
       cp_async_drain();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->y_full[b]);
     };
-    // conditioner input of a tile (WrapPeriodic folded in), [128][ldc]
-    const int K0 = a.net.K[0];
     auto load_cond_tile = [&](long long tile) {
-      const int ne = TC_TM * K0;
-      for (int idx = t64; idx < ne; idx += 64) {
-        const int r = idx / K0, k = idx - r * K0;
+      if (a.c_dense && full_rows(tile)) {
+        if (warp == 16 && lane == 0) {
+          mbar_expect_tx(&S->c_full, (uint32_t)(TC_TM * K0 * 4));
+          bulk_g2s(cbuf, a.cond.ptr[0] + tile * TC_TM * (long long)K0, (uint32_t)(TC_TM * K0 * 4), &S->c_full);
+        } else if (warp == 17 && lane == 0) {
+          mbar_arrive(&S->c_full);
+        }
+        return;
+      }
+      walk(K0, [&](int r, int k) {
         const long long row = tile * TC_TM + r;
         const int code = a.net.in_map[k];
         float* dst = &cbuf[r * a.ldc + k];
         if (row >= a.B) *dst = 0.f;
         else if ((code >> 24) == 0) cp_async4(dst, seg_addr(a.cond, row, code & 0xffffff));
         else *dst = load_cond(a.cond, a.net, a.B, row, k);      // periodic input: cos / sin
-      }
+      });
       cp_async_drain();
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->c_full);
     };
+    auto store_tile = [&](long long tile, int b) {
+      const float* Y = ybuf + b * TC_TM * a.ldy;
+      if (a.y_dense && full_rows(tile)) {
+        if (warp == 16 && lane == 0) {
+          bulk_s2g(const_cast<float*>(a.tout.ptr[0]) + tile * TC_TM * (long long)Dt, Y, (uint32_t)(TC_TM * Dt * 4));
+          bulk_store_wait_read();      // the buffer may be refilled once the TMA engine has read it
+        }
+        return;
+      }
+      walk(Dt, [&](int r, int d) {
+        const long long row = tile * TC_TM + r;
+        if (row < a.B) *const_cast<float*>(seg_addr(a.tout, row, d)) = Y[r * a.ldy + d];
+      });
+    };
+
     long long n_my = (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     if (n_my > 0) load_cond_tile(blockIdx.x);
     if (n_my > 0) load_tile(blockIdx.x, 0);
@@ -447,13 +496,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         load_cond_tile(tile + gridDim.x);
       }
       mbar_wait(&S->y_done[b], (uint32_t)((it >> 1) & 1), a.status);
-      const float* Y = ybuf + b * TC_TM * a.ldy;
-#pragma unroll 8
-      for (int idx = t64; idx < nelem; idx += 64) {
-        const int r = idx / a.D_t, d = idx - r * a.D_t;
-        const long long row = tile * TC_TM + r;
-        if (row < a.B) *const_cast<float*>(seg_addr(a.tout, row, d)) = Y[r * a.ldy + d];
-      }
+      store_tile(tile, b);
       if (it + 2 < n_my) {
         asm volatile("bar.sync 3, 64;" ::: "memory");   // both I/O warps are done reading Y[b]
         load_tile(tile + 2LL * gridDim.x, b);
@@ -585,6 +628,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
         }
       }
       if (n_oob && a.sp.oob) atomicAdd(a.sp.oob, n_oob);
+      fence_async_smem();     // outputs in shared memory -> visible to the TMA store
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->y_done[yb]);   // this warp's outputs of the tile are staged
       // ---- per-sample log-det: the quadrant's four warps combine their partial sums
@@ -679,8 +723,13 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
     if (rc) return rc;
   }
   a.bias_floats = bias_floats;
-  a.ldy = d_t | 1;
-  a.ldc = net->K[0] | 1;
+  auto dense16 = [](const Segs& sg) {
+    return sg.n == 1 && sg.stride[0] == sg.width[0] && ((uintptr_t)sg.ptr[0] & 15) == 0;
+  };
+  a.y_dense = dense16(a.tin) && dense16(a.tout);
+  a.c_dense = dense16(a.cond) && net->periodic_scale == 0.f && net->raw_width == net->K[0];
+  a.ldy = a.y_dense ? d_t : (d_t | 1);
+  a.ldc = a.c_dense ? net->K[0] : (net->K[0] | 1);
   const size_t fixed = 1024 + sizeof(TcSmem) +
                        sizeof(float) * ((size_t)bias_floats + 2 * TC_TM * a.ldy + TC_TM * a.ldc) + 64;
   a.stages = TC_MAX_STAGES;     // ring slots (one k-tile = nterms x 16 KB each): as many as fit
