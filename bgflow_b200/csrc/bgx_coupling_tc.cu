@@ -141,13 +141,12 @@ __device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
-__device__ __forceinline__ float act_fast(float x, int act) {
-  switch (act) {
-    case BGX_ACT_RELU: return fmaxf(x, 0.f);
-    case BGX_ACT_SILU: return x * rcp_fast(1.f + ex2_fast(-LOG2E * x));
-    case BGX_ACT_TANH: return 1.f - 2.f * rcp_fast(1.f + ex2_fast(2.f * LOG2E * x));
-    default: return x;
-  }
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if (ACT == BGX_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == BGX_ACT_SILU) return x * rcp_fast(1.f + ex2_fast(-LOG2E * x));
+  if (ACT == BGX_ACT_TANH) return 1.f - 2.f * rcp_fast(1.f + ex2_fast(2.f * LOG2E * x));
+  return x;
 }
 
 __device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
@@ -238,7 +237,7 @@ __device__ __forceinline__ float do_dim(const TcArgs& a, const float (&p)[PS], f
   return lad;
 }
 
-template <bool INVERSE>
+template <bool INVERSE, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -562,11 +561,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
           tmem_ld32(tmem + lane_base + COL_ACC0 + col, v);
           tmem_ld_wait();
           uint32_t t1[16], t2[16], t3[16];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + boff + col);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float h0 = act_fast(__uint_as_float(v[2 * i]) + bias_s[boff + col + 2 * i], a.net.act);
-            const float h1 = act_fast(__uint_as_float(v[2 * i + 1]) + bias_s[boff + col + 2 * i + 1], a.net.act);
-            split_bf16(h0, h1, NT, t1[i], t2[i], t3[i]);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
+            const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
+            const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
+            const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
+            split_bf16(h0, h1, NT, t1[2 * i], t2[2 * i], t3[2 * i]);
+            split_bf16(h2, h3, NT, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
           }
           const uint32_t acol = tmem + lane_base + COL_A + col / 2;
           tmem_st16(acol, t1);
@@ -737,12 +741,19 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   while (a.stages > 3 && fixed + (size_t)a.stages * slot_bytes > 227 * 1024) a.stages -= 1;
   const size_t smem = fixed + (size_t)a.stages * slot_bytes;
   if (smem > 227 * 1024) return BGX_ERR_UNSUPPORTED;
-  auto kern = a.inverse ? spline_coupling_tc_kernel<true> : spline_coupling_tc_kernel<false>;
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[a.inverse]) {
+  using KernT = void (*)(const TcArgs);
+  static const KernT kerns[2][4] = {
+      {spline_coupling_tc_kernel<false, 0>, spline_coupling_tc_kernel<false, 1>, spline_coupling_tc_kernel<false, 2>,
+       spline_coupling_tc_kernel<false, 3>},
+      {spline_coupling_tc_kernel<true, 0>, spline_coupling_tc_kernel<true, 1>, spline_coupling_tc_kernel<true, 2>,
+       spline_coupling_tc_kernel<true, 3>}};
+  if (net->act < 0 || net->act > 3) return BGX_ERR_INVALID;
+  KernT kern = kerns[a.inverse][net->act];
+  static size_t configured[2][4] = {};
+  if (smem > configured[a.inverse][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
-    configured[a.inverse] = smem;
+    configured[a.inverse][net->act] = smem;
   }
   static int max_ctas = -1;
   if (max_ctas < 0) {   // debug knob: cap the persistent grid (isolates per-SM from chip-wide effects)
