@@ -69,7 +69,8 @@ class bgx_spline_cfg(C.Structure):
 
 class bgx_zplan(C.Structure):
     _fields_ = [("n_atoms", C.c_int32), ("seeds", C.c_int32 * 3), ("n_rel", C.c_int32),
-                ("rel", C.c_void_p), ("order", C.c_void_p), ("normalize_angles", C.c_int32),
+                ("rel", C.c_void_p), ("order", C.c_void_p), ("slot_of_col", C.c_void_p),
+                ("normalize_angles", C.c_int32),
                 ("eps", C.c_float)]
 
 

@@ -282,6 +282,12 @@ class ZPlan:
         if key not in self._dev:
             rel = torch.as_tensor(self.rel.astype(np.int32)).contiguous().to(device)
             order = torch.as_tensor(np.asarray(self.order, dtype=np.int32)).to(device)
+            # IC column -> slot of the atom that owns it (bonds | angles | torsions column order)
+            s0, s1, s2 = self.seeds
+            atoms = [int(a) for a in self.rel[:, 0]]
+            slots = ([3 * s1, 3 * s2] + [3 * a for a in atoms] + [3 * s2 + 1] + [3 * a + 1 for a in atoms]
+                     + [3 * a + 2 for a in atoms])
+            slot_of_col = torch.as_tensor(np.asarray(slots, dtype=np.int32)).to(device)
             plan = _lib.bgx_zplan()
             plan.n_atoms = self.n_atoms
             for i in range(3):
@@ -289,9 +295,10 @@ class ZPlan:
             plan.n_rel = len(self.rel)
             plan.rel = rel.data_ptr()
             plan.order = order.data_ptr()
+            plan.slot_of_col = slot_of_col.data_ptr()
             plan.normalize_angles = 1 if self.normalize_angles else 0
             plan.eps = self.eps
-            self._dev[key] = (plan, rel, order)
+            self._dev[key] = (plan, rel, order, slot_of_col)
         return self._dev[key][0]
 
 

@@ -154,6 +154,8 @@ typedef struct bgx_zplan {
   int32_t n_rel;               /* n_atoms - 3 */
   const int32_t* rel;          /* device, [n_rel][4] rows (i,j,k,l) in tensor column order */
   const int32_t* order;        /* device, [n_rel] placement order (row ids) */
+  const int32_t* slot_of_col;  /* device, [3*n_atoms-6]: for the columns of bonds | angles | torsions the
+                                  shared-memory slot 3*atom + {0 bond, 1 angle, 2 torsion} (or NULL) */
   int32_t normalize_angles;
   float eps;
 } bgx_zplan;
