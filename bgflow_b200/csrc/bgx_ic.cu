@@ -194,34 +194,53 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
 }
 
 // ---------------------------------------------------------------- Cartesian -> IC
+// All z-matrix rows of a sample are independent, so FOUR threads share a sample (rows r = g, g+4, ...;
+// thread g = 3 also does the reference frame): 32 samples per 128-thread CTA, 16.6 KB of shared
+// memory per CTA (13 CTAs / 52 warps per SM) instead of one thread walking 19 rows.
+constexpr int FS = 32;        // samples per CTA (from_xyz)
+constexpr int LDF = FS + 1;
+
+template <typename F>
+__device__ __forceinline__ void walk_block_f(int t, int W, int rows, F&& body) {
+  int m = t / W, c = t - m * W;
+  const int dm = BT / W, dc = BT - dm * W;
+  while (m < rows) {
+    body(m, c);
+    m += dm; c += dc;
+    if (c >= W) { c -= W; ++m; }
+  }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
   extern __shared__ float sm[];
   const int t = threadIdx.x;
-  const long long row0 = (long long)blockIdx.x * BT;
-  const long long row = row0 + t;
-  const bool live = row < a.B;
   const int N = a.n_atoms, nb = N - 1, na = N - 2, nt = N - 3;
-  const int nrow = (int)min((long long)BT, a.B - row0);
   const int W = 3 * N;
-  float* Q = sm + W * LDT + t;          // staged outputs: column c of bonds|angles|torsions at Q[c * LDT]
+  const int spb = SMEM ? FS : BT;                    // samples per CTA
+  const long long row0 = (long long)blockIdx.x * spb;
+  const int s_loc = SMEM ? (t >> 2) : t, g = SMEM ? (t & 3) : 0, ng = SMEM ? 4 : 1;
+  const long long row = row0 + s_loc;
+  const bool live = row < a.B;
+  const int nrow = (int)min((long long)spb, a.B - row0);
+  float* Qs = sm + W * LDF + s_loc;     // staged outputs: column c of bonds|angles|torsions at Qs[c * LDF]
   PosStore<SMEM> pos;
   if (SMEM) {
-    const float* g = a.xyz_in + row0 * W;
-    walk_block(t, W, nrow, [&](int m, int c) { sm[c * LDT + m] = __ldg(g + m * W + c); });
+    const float* gx = a.xyz_in + row0 * W;
+    walk_block_f(t, W, nrow, [&](int m, int c) { sm[c * LDF + m] = __ldg(gx + m * W + c); });
     __syncthreads();
-    pos.base = sm + t;
-    pos.stride_c = LDT;
+    pos.base = sm + s_loc;
+    pos.stride_c = LDF;
   } else {
     pos.base = const_cast<float*>(a.xyz_in) + row * (long long)(3 * N);
     pos.stride_c = 1;
   }
+  float dl = 0.f;
   if (live) {
     float* bo = a.o_bonds + row * nb;
     float* an = a.o_angles + row * na;
     float* to = a.o_torsions + row * nt;
-    float dl = 0.f;
-    for (int r = 0; r < a.n_rel; ++r) {
+    for (int r = g; r < a.n_rel; r += ng) {
       const int4 z = *reinterpret_cast<const int4*>(a.rel + 4 * r);
       const V3 xi = pos.get(z.x), xj = pos.get(z.y), xk = pos.get(z.z), xl = pos.get(z.w);
       const V3 r12 = xi - xj, r32 = xk - xj;
@@ -242,13 +261,13 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
         tor = (tor + PI_F) * (1.f / TWO_PI_F);
       }
       if (SMEM) {
-        Q[(2 + r) * LDT] = n12; Q[(nb + 1 + r) * LDT] = ang; Q[(nb + na + r) * LDT] = tor;
+        Qs[(2 + r) * LDF] = n12; Qs[(nb + 1 + r) * LDF] = ang; Qs[(nb + na + r) * LDF] = tor;
       } else {
         bo[2 + r] = n12; an[1 + r] = ang; to[r] = tor;
       }
       dl -= __logf(n12 * n12 * sqrtf(sin2));     // 2 ln b + ln sin a
     }
-    {
+    if (g == ng - 1) {
       const V3 p0 = pos.get(a.s0), p1 = pos.get(a.s1), p2 = pos.get(a.s2);
       const V3 e01 = p1 - p0, e12 = p2 - p1;
       const float d01 = norm_c(e01, a.eps), d12 = norm_c(e12, a.eps);
@@ -275,7 +294,7 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
         dl -= (float)((double)na * 1.1447298858494002 + (double)(nt + 2) * 1.8378770664093453);
       }
       if (SMEM) {
-        Q[0] = d01; Q[LDT] = d12; Q[nb * LDT] = a012;
+        Qs[0] = d01; Qs[LDF] = d12; Qs[nb * LDF] = a012;
       } else {
         bo[0] = d01; bo[1] = d12; an[0] = a012;
       }
@@ -286,17 +305,21 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
       a.o_R[row * 3 + 1] = beta;
       a.o_R[row * 3 + 2] = gamma;
     }
-    a.dlogp_out[row] = (a.dlogp_in ? a.dlogp_in[row] : 0.f) + dl;
   }
+  if (SMEM) {   // the four threads of a sample are adjacent lanes
+    dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+    dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+  }
+  if (live && g == 0) a.dlogp_out[row] = (a.dlogp_in ? a.dlogp_in[row] : 0.f) + dl;
   if (SMEM) {
     __syncthreads();
-    const float* Qb = sm + W * LDT;
+    const float* Qb = sm + W * LDF;
     float* gb = a.o_bonds + row0 * nb;
     float* ga = a.o_angles + row0 * na;
     float* gt = a.o_torsions + row0 * nt;
-    walk_block(t, nb, nrow, [&](int m, int c) { gb[m * nb + c] = Qb[c * LDT + m]; });
-    walk_block(t, na, nrow, [&](int m, int c) { ga[m * na + c] = Qb[(nb + c) * LDT + m]; });
-    walk_block(t, nt, nrow, [&](int m, int c) { gt[m * nt + c] = Qb[(nb + na + c) * LDT + m]; });
+    walk_block_f(t, nb, nrow, [&](int m, int c) { gb[m * nb + c] = Qb[c * LDF + m]; });
+    walk_block_f(t, na, nrow, [&](int m, int c) { ga[m * na + c] = Qb[(nb + c) * LDF + m]; });
+    walk_block_f(t, nt, nrow, [&](int m, int c) { gt[m * nt + c] = Qb[(nb + na + c) * LDF + m]; });
   }
 }
 
@@ -319,18 +342,20 @@ static int fill_plan(const bgx_zplan* plan, long long batch, IcArgs& a) {
 }
 
 template <typename KS, typename KG>
-static int launch_ic(KS ksm, KG kgl, const IcArgs& a, int extra_cols, cudaStream_t st) {
+static int launch_ic(KS ksm, KG kgl, const IcArgs& a, int extra_cols, int samples_per_cta, cudaStream_t st) {
   if (a.B == 0) return BGX_OK;
   long long grid = (a.B + BT - 1) / BT;
   if (grid > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
-  size_t sb = sizeof(float) * (size_t)(3 * a.n_atoms + extra_cols) * LDT;
+  size_t sb = sizeof(float) * (size_t)(3 * a.n_atoms + extra_cols) * (samples_per_cta + 1);
   if (!a.slot_of_col) sb = (size_t)1 << 30;      // plans without a slot map use the global-memory path
   if (sb <= 200 * 1024) {
     if (sb > 48 * 1024) {  // (both kernels share this instantiation: no static cache here)
       int rc = check(cudaFuncSetAttribute(ksm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
       if (rc) return rc;
     }
-    ksm<<<(unsigned)grid, BT, sb, st>>>(a);
+    const long long grid_s = (a.B + samples_per_cta - 1) / samples_per_cta;
+    if (grid_s > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
+    ksm<<<(unsigned)grid_s, BT, sb, st>>>(a);
   } else {
     kgl<<<(unsigned)grid, BT, 0, st>>>(a);
   }
@@ -352,7 +377,7 @@ extern "C" int bgx_ic_to_xyz(const bgx_zplan* plan, int64_t batch, const float* 
   a.bonds = bonds; a.angles = angles; a.torsions = torsions;
   a.x0 = x0; a.R = R; a.x0_stride = x0_stride; a.r_stride = r_stride;
   a.xyz = xyz; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, 0, (cudaStream_t)stream);
+  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, 0, BT, (cudaStream_t)stream);
 }
 
 extern "C" int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, float* bonds,
@@ -364,5 +389,5 @@ extern "C" int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float
   if (!xyz || !bonds || !angles || !torsions || !x0 || !R || !dlogp_out) return BGX_ERR_INVALID;
   a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions;
   a.o_x0 = x0; a.o_R = R; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_atoms - 6, (cudaStream_t)stream);
+  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_atoms - 6, FS, (cudaStream_t)stream);
 }
