@@ -288,7 +288,10 @@ def main():
     # ------------------------------------------------------------------ this repo's arm
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group("gloo" if DRYRUN else "nccl")
+        if DRYRUN:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     B = args.batch_per_gpu
 
     def max_over_ranks(x):
@@ -386,7 +389,7 @@ def main():
                 pipe.run(z_host)
             ms_e2e = run_timed(lambda: pipe.run(z_host), args.steps)
             e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
-                   "h2d_bytes_per_step": B * dim * 4, "d2h_bytes_per_step": B * dim * 4 + B * 4,
+                   "h2d_bytes_per_step": world * B * dim * 4, "d2h_bytes_per_step": world * (B * dim * 4 + B * 4),
                    "ms_per_step": ms_e2e / args.steps, "api": "bgflow_b200.host.HostPipeline.run (pinned host in/out)"}
 
     pk = peaks()

@@ -138,7 +138,12 @@ class SplitFlow(Flow):
     def _apply_tuple(self, xs, inverse):
         if not inverse:
             (x,) = xs
-            return tuple(self._split(x))
+            parts = tuple(self._split(x))
+            if x.is_cuda:
+                # dense halves let the coupling kernels move whole [128 x D] tiles with one bulk TMA
+                # copy each (strided views would fall back to element-wise staging); costs one pass
+                parts = tuple(p.contiguous() for p in parts)
+            return parts
         return (self._merge(*xs),)
 
     def _split(self, x):
