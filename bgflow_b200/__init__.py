@@ -16,6 +16,6 @@ from .ic import GlobalInternalCoordinateTransformation
 from .bg import (BoltzmannGenerator, NormalDistribution, UniformDistribution, unnormalized_kl_div,
                  unormalized_nll, log_weights, log_weights_given_latent, effective_sample_size,
                  sampling_efficiency)
-from . import engine, _lib
+from . import engine, _lib, distributed
 
 __version__ = "0.1.0"

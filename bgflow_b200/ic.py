@@ -83,8 +83,17 @@ class GlobalInternalCoordinateTransformation(Flow):
     def _forward(self, x, *args, **kwargs):
         """xyz ``[B, 3N]`` -> bonds ``[B, N-1]``, angles ``[B, N-2]``, torsions ``[B, N-3]``,
         x0 ``[B, 1, 3]``, R ``[B, 3]``, dlogp ``[B, 1]`` (ic.py:633-676)."""
+        self._no_grad_yet(x)
         return engine.ic_from_xyz(self._plan, x)
 
     def _inverse(self, bonds, angles, torsions, x0, R, *args, **kwargs):
         """(ic.py:678-716) -> xyz ``[B, 3N]``, dlogp ``[B, 1]``."""
+        self._no_grad_yet(bonds, angles, torsions, x0, R)
         return engine.ic_to_xyz(self._plan, bonds, angles, torsions, x0, R)
+
+    @staticmethod
+    def _no_grad_yet(*tensors):
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+            raise NotImplementedError(
+                "the internal-coordinate kernels are inference-only in this version: call them under "
+                "torch.no_grad() / detach their inputs (backward kernels are listed as next in DESIGN.md)")

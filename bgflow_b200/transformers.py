@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import engine
+from .autograd import fused_coupling_with_grad, needs_grad
 from .flows import Flow
 from .nets import DenseNet, MeanFreeDenseNet, WrapPeriodic
 
@@ -106,6 +107,12 @@ class AffineTransformer(_FusedMixin, Transformer):
 
     def _coupling(self, cond, tr, inverse=False, dlogp_acc=None, **kwargs):
         engine.require_cuda_fp32(*cond, *tr)
+        if needs_grad([*cond, *tr], self):
+            outs, dlogp = fused_coupling_with_grad(self, "affine", list(cond), list(tr), inverse)
+            return outs, (dlogp if dlogp_acc is None else dlogp_acc + dlogp)
+        return self._launch(cond, tr, inverse=inverse, dlogp_acc=dlogp_acc)
+
+    def _launch(self, cond, tr, inverse=False, dlogp_acc=None):
         d_c = sum(t.shape[-1] for t in cond)
         d_t = sum(t.shape[-1] for t in tr)
         shift = scale = None
@@ -182,6 +189,12 @@ class ConditionalSplineTransformer(_FusedMixin, Transformer):
 
     def _coupling(self, cond, tr, inverse=False, dlogp_acc=None, **kwargs):
         engine.require_cuda_fp32(*cond, *tr)
+        if needs_grad([*cond, *tr], self):
+            outs, dlogp = fused_coupling_with_grad(self, "spline", list(cond), list(tr), inverse)
+            return outs, (dlogp if dlogp_acc is None else dlogp_acc + dlogp)
+        return self._launch(cond, tr, inverse=inverse, dlogp_acc=dlogp_acc)
+
+    def _launch(self, cond, tr, inverse=False, dlogp_acc=None):
         d_c = sum(t.shape[-1] for t in cond)
         d_t = sum(t.shape[-1] for t in tr)
         mask = self._circular_mask(d_t)

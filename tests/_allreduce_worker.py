@@ -1,0 +1,29 @@
+"""2-rank gloo worker for tests/test_host_logic.py::test_gradient_allreduce_two_ranks."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bgflow_b200 import distributed as bd
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+full = torch.randn(16, 5, generator=torch.Generator().manual_seed(1))
+lo, hi = bd.shard_rows(16, rank, world)
+loss = net(full[lo:hi]).pow(2).sum() / 16          # shard of a mean over the global batch
+loss.backward()
+n = bd.allreduce_gradients(net.parameters(), average=False)
+# reference: the same loss on the whole batch in one process
+ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+ref.load_state_dict(net.state_dict())
+(ref(full).pow(2).sum() / 16).backward()
+err = max((p.grad - q.grad).abs().max().item() for p, q in zip(net.parameters(), ref.parameters()))
+assert n == sum(p.numel() for p in net.parameters()), n
+assert err < 1e-6, err
+if rank == 0:
+    print(f"ALLREDUCE_OK world={world} elements={n} err={err:.2e}")
+dist.destroy_process_group()

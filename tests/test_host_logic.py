@@ -170,3 +170,19 @@ def test_two_rank_gloo_sharding():
     rec = json.loads(lines[0])
     assert rec["n_gpus"] == 2 and rec["dryrun"] is True and rec["scaling"] == "weak"
     assert rec["shard_rows"] == [rec["config"]["batch_per_gpu"]] * 2
+
+
+def test_gradient_allreduce_two_ranks():
+    """bgflow_b200.distributed.allreduce_gradients on 2 gloo ranks == single-process gradient."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(ROOT, "tests", "_allreduce_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ALLREDUCE_OK world=2" in res.stdout
+
+
+def test_shard_rows():
+    from bgflow_b200.distributed import shard_rows
+    assert [shard_rows(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard_rows(1 << 20, 7, 8) == (7 << 17, 8 << 17)
