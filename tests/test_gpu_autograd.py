@@ -49,10 +49,11 @@ def test_input_and_parameter_gradients(kind, inverse):
     loss.backward()
     scale = gz_ref.abs().max().item()
     np.testing.assert_allclose(zc.grad.cpu().double().numpy(), gz_ref.numpy(), atol=2e-3 * scale, rtol=2e-3)
-    ours = []
+    ours = []      # oracle order: per conditioner, all weights then all biases
     for m in flow.modules():
-        if isinstance(m, torch.nn.Linear):
-            ours += [m.weight.grad, m.bias.grad]
+        if isinstance(m, bg.DenseNet):
+            lin = [l for l in m._layers if isinstance(l, torch.nn.Linear)]
+            ours += [l.weight.grad for l in lin] + [l.bias.grad for l in lin]
     assert len(ours) == len(gp_ref)
     for a, b in zip(ours, gp_ref):
         s = max(b.abs().max().item(), 1e-6)
