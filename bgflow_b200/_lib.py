@@ -91,6 +91,7 @@ SYMBOLS = {
                                   C.c_void_p]),
     "bgx_tc_selftest": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "bgx_set_status_buffer": (C.c_int, [C.c_void_p]),
     "bgx_debug_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "bgx_version": (C.c_char_p, []),
     "bgx_last_cuda_error": (C.c_char_p, []),

@@ -8,12 +8,25 @@ int spline_coupling_simt(const bgx_coupling_io*, const bgx_packed_mlp*, const bg
                          cudaStream_t);
 bool spline_tc_eligible(const bgx_packed_mlp*, const bgx_spline_cfg*, int);
 void tc_set_trace(unsigned long long*, int);
+bool affine_tc_eligible(const bgx_packed_mlp*, const bgx_packed_mlp*, int);
+int affine_coupling_tc(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, float, int, int*,
+                       cudaStream_t);
 int spline_coupling_tc(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int*,
                        cudaStream_t);
 }  // namespace bgx
 
+static int* g_status = nullptr;   // device flag raised by the tensor-core kernels on a pipeline timeout
+
+extern "C" int bgx_set_status_buffer(int32_t* device_int) {
+  g_status = device_int;
+  return BGX_OK;
+}
+
 extern "C" int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
                                    const bgx_packed_mlp* scale, float log_alpha, int flags, void* stream) {
+  if (!io) return BGX_ERR_INVALID;
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc_eligible(shift, scale, flags))
+    return bgx::affine_coupling_tc(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
   return bgx::affine_coupling_simt(io, shift, scale, log_alpha, flags, (cudaStream_t)stream);
 }
 
@@ -21,7 +34,8 @@ extern "C" int bgx_spline_coupling(const bgx_coupling_io* io, const bgx_packed_m
                                    const bgx_spline_cfg* cfg, int flags, void* stream) {
   if (!io || !params_net || !cfg) return BGX_ERR_INVALID;
   if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc_eligible(params_net, cfg, 0))
-    return bgx::spline_coupling_tc(io, params_net, cfg, flags, cfg->status, (cudaStream_t)stream);
+    return bgx::spline_coupling_tc(io, params_net, cfg, flags, cfg->status ? cfg->status : g_status,
+                                   (cudaStream_t)stream);
   return bgx::spline_coupling_simt(io, params_net, cfg, flags, (cudaStream_t)stream);
 }
 

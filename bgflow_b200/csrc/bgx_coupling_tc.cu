@@ -30,6 +30,7 @@
 
 #include "bgx_coupling.cuh"
 #include "bgx_tc.cuh"
+#include "bgx_tc_epi.cuh"
 
 namespace bgx {
 using namespace tc;
@@ -90,22 +91,6 @@ __device__ __forceinline__ void tc_trace(const TcArgs& a, int role, int ev, long
   }
 }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_drain() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-// shared -> global bulk copy (TMA engine); completion tracked with bulk async-groups
-__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
 struct alignas(16) TcSmem {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -123,31 +108,6 @@ struct alignas(16) TcSmem {
   float dl_part[4][TC_TM];
 };
 
-// exact split of two adjacent-k fp32 values into packed bf16x2 terms (element k in the low half)
-__device__ __forceinline__ void split_bf16(float x0, float x1, int nterms, uint32_t& t1, uint32_t& t2,
-                                           uint32_t& t3) {
-  t1 = pack_bf16x2(x0, x1);
-  const float r0 = x0 - bf16_lo_to_f32(t1), r1 = x1 - bf16_hi_to_f32(t1);
-  t2 = pack_bf16x2(r0, r1);
-  t3 = 0;
-  if (nterms == 3) t3 = pack_bf16x2(r0 - bf16_lo_to_f32(t2), r1 - bf16_hi_to_f32(t2));
-}
-
-// ---- fast special functions (MUFU): a few ulp, far inside the stated parity tolerance
-__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
-template <int ACT>
-__device__ __forceinline__ float act_fast(float x) {
-  if (ACT == BGX_ACT_RELU) return fmaxf(x, 0.f);
-  if (ACT == BGX_ACT_SILU) return x * rcp_fast(1.f + ex2_fast(-LOG2E * x));
-  if (ACT == BGX_ACT_TANH) return 1.f - 2.f * rcp_fast(1.f + ex2_fast(2.f * LOG2E * x));
-  return x;
-}
 
 __device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
   const float bs = c.beta * s;

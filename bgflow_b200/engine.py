@@ -46,6 +46,7 @@ def pipeline_status(device):
     key = torch.device(device)
     if key not in _status:
         _status[key] = torch.zeros(1, dtype=torch.int32, device=key)
+        _lib.load().bgx_set_status_buffer(C.c_void_p(_status[key].data_ptr()))   # one process per GPU
     return _status[key]
 
 
@@ -205,6 +206,7 @@ def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_v
     io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
     if io.batch == 0:
         return outs, dlogp
+    pipeline_status(tr[0].device)
     f = flags | _mode_flags() | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
         | (_lib.FLAG_CIRCULAR if is_circular else 0)
     rc = lib.bgx_affine_coupling(C.byref(io), C.byref(shift) if shift is not None else None,

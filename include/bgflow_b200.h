@@ -178,6 +178,10 @@ int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, floa
 int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                     int* status, void* stream);
 
+/* Device int the tensor-core kernels set to 1 if their internal barrier pipeline ever times out
+ * (results invalid; a bug, never an input property).  Used when a call carries no status pointer. */
+int bgx_set_status_buffer(int32_t* device_int);
+
 /* Debug: subsequent tensor-core launches record a timeline of CTA 0 into `device_buffer`
  * ([0] = event count, then (clock64, code) pairs; 1 + 2*capacity uint64).  NULL disables. */
 int bgx_debug_set_trace(uint64_t* device_buffer, int capacity);

@@ -19,8 +19,8 @@ DEV = "cuda:0"
 
 @pytest.fixture(params=["tc", "tc6", "simt"], autouse=True)
 def kernel_mode(request):
-    """Every parity test runs on the tensor-core kernel (where the shape is eligible) and on the
-    shape-general SIMT kernel."""
+    """Every parity test runs on the tensor-core kernels (spline and affine, where the shape is
+    eligible; both precisions) and on the shape-general SIMT kernel."""
     from bgflow_b200 import engine
     old = dict(engine.config)
     engine.config.update(force_simt=(request.param == "simt"),
