@@ -7,6 +7,8 @@ int affine_coupling_simt(const bgx_coupling_io*, const bgx_packed_mlp*, const bg
 int spline_coupling_simt(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int,
                          cudaStream_t);
 bool spline_tc_eligible(const bgx_packed_mlp*, const bgx_spline_cfg*, int);
+bool spline_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int);
+int spline_coupling_tc2(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int*, cudaStream_t);
 void tc_set_trace(unsigned long long*, int);
 bool affine_tc_eligible(const bgx_packed_mlp*, const bgx_packed_mlp*, int);
 int affine_coupling_tc(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, float, int, int*,
@@ -33,6 +35,9 @@ extern "C" int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_m
 extern "C" int bgx_spline_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* params_net,
                                    const bgx_spline_cfg* cfg, int flags, void* stream) {
   if (!io || !params_net || !cfg) return BGX_ERR_INVALID;
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc2_eligible(io, params_net, cfg, flags))
+    return bgx::spline_coupling_tc2(io, params_net, cfg, flags, cfg->status ? cfg->status : g_status,
+                                    (cudaStream_t)stream);
   if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc_eligible(params_net, cfg, 0))
     return bgx::spline_coupling_tc(io, params_net, cfg, flags, cfg->status ? cfg->status : g_status,
                                    (cudaStream_t)stream);

@@ -1,0 +1,96 @@
+// Register-resident rational-quadratic spline evaluation (8 bins) shared by the tensor-core
+// spline kernels.  Same algorithm as rqs_eval (bgx_common.cuh) / oracle.flows.rational_quadratic_spline.
+#pragma once
+#include "bgx_tc_epi.cuh"
+
+namespace bgx {
+
+constexpr int NB = 8;            // spline bins handled by the tensor-core kernels
+constexpr int PS = 3 * NB + 1;   // parameters per transformed dim
+
+// per-kernel constants of the spline (uniform across threads)
+struct SplineK {
+  float left, right, bottom, top;
+  float wscale, hscale;   // (right-left)*(1-min_w*K), (top-bottom)*(1-min_h*K)
+  float wstep, hstep;     // (right-left)*min_w, (top-bottom)*min_h
+  float min_d, beta_l2e, ln2_over_beta, beta;
+};
+
+__device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
+  const float bs = c.beta * s;
+  const float v = lg2_fast(1.f + ex2_fast(fminf(s * c.beta_l2e, 64.f))) * c.ln2_over_beta;
+  return bs > 20.f ? s : v;
+}
+
+// One (sample, dim) spline evaluation with the 25 parameters in registers (NB = 8 bins).
+// Same algorithm as rqs_eval (bgx_common.cuh); the knots are formed from prefix sums of the
+// softmax numerators instead of a running sum of the normalised bins.
+template <bool ROOT>
+__device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK& c, float x, float& y,
+                                             float& lad) {
+  const float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
+  const float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));
+  const float nmw = -mw * LOG2E, nmh = -mh * LOG2E;
+  float pw[NB], ph[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    pw[k] = ex2_fast(fmaf(p[k], LOG2E, nmw));
+    ph[k] = ex2_fast(fmaf(p[NB + k], LOG2E, nmh));
+  }
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    pw[k] += pw[k - 1];
+    ph[k] += ph[k - 1];
+  }
+  const float aw = c.wscale * rcp_fast(pw[NB - 1]);
+  const float ah = c.hscale * rcp_fast(ph[NB - 1]);
+  // knots 1..NB-1 (knot 0 = left/bottom, knot NB = right/top exactly)
+  float kw[NB + 1], kh[NB + 1];
+  kw[0] = c.left; kh[0] = c.bottom; kw[NB] = c.right; kh[NB] = c.top;
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    kw[k] = fmaf(aw, pw[k - 1], fmaf(c.wstep, (float)k, c.left));
+    kh[k] = fmaf(ah, ph[k - 1], fmaf(c.hstep, (float)k, c.bottom));
+  }
+  float w_lo = kw[0], w_hi = kw[1], h_lo = kh[0], h_hi = kh[1], s0 = p[2 * NB], s1 = p[2 * NB + 1];
+#pragma unroll
+  for (int k = 1; k < NB; ++k) {
+    const bool in = x >= (ROOT ? kh[k] : kw[k]);
+    w_lo = in ? kw[k] : w_lo;
+    w_hi = in ? kw[k + 1] : w_hi;
+    h_lo = in ? kh[k] : h_lo;
+    h_hi = in ? kh[k + 1] : h_hi;
+    s0 = in ? p[2 * NB + k] : s0;
+    s1 = in ? p[2 * NB + k + 1] : s1;
+  }
+  const float w = w_hi - w_lo, h = h_hi - h_lo;
+  const float rw = rcp_fast(w);
+  const float delta = h * rw;
+  const float d0 = c.min_d + softplus_fast(s0, c);
+  const float d1 = c.min_d + softplus_fast(s1, c);
+  const float s = d0 + d1 - 2.f * delta;
+  float th;
+  if (ROOT) {
+    const float q = x - h_lo;
+    const float qs = q * s;
+    const float a = fmaf(h, delta - d0, qs);
+    const float b = fmaf(h, d0, -qs);
+    const float cc = -delta * q;
+    const float disc = fmaxf(fmaf(b, b, -4.f * a * cc), 0.f);
+    th = 2.f * cc * rcp_fast(-b - sqrt_fast(disc));
+    y = fmaf(th, w, w_lo);
+  } else {
+    th = (x - w_lo) * rw;
+  }
+  const float omt = 1.f - th;
+  const float t1 = th * omt;
+  const float den = fmaf(s, t1, delta);
+  const float rden = rcp_fast(den);
+  if (!ROOT) y = fmaf(h * fmaf(delta * th, th, d0 * t1), rden, h_lo);
+  const float num = delta * delta * fmaf(d1 * th, th, fmaf(2.f * delta, t1, d0 * omt * omt));
+  const float l = logf(num * rden * rden);
+  lad = ROOT ? -l : l;
+}
+
+
+}  // namespace bgx
