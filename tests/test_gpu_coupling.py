@@ -219,3 +219,64 @@ def test_precision_modes_report(kernel_mode):
     print("max abs error vs reference fp64 (x, dlogp):", {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in errs.items()})
     for k, (ex, ed) in errs.items():
         assert ex < 1e-4 and ed < 1e-3, (k, ex, ed)
+
+
+@pytest.mark.parametrize("batch", [4, 132, 1000, 1001, 4099])
+def test_tensor_core_kernels_partial_tiles(batch, kernel_mode):
+    """hidden = 128 stacks on ragged batches: the 2-CTA kernel (batch % 4 == 0, partial last tile),
+    the single-CTA kernel (other batches / bf16x6) and the SIMT kernel must all agree with the oracle."""
+    blocks, split = of.make_stack("spline", 66, 3, hidden=(128, 128), seed=11)
+    flow = stack_from(blocks, split, DEV)
+    g = torch.Generator().manual_seed(batch)
+    z = torch.rand(batch, 66, generator=g)
+    blocks64, _ = of.make_stack("spline", 66, 3, hidden=(128, 128), seed=11, dtype=torch.float64)
+    x_ref, d_ref = of.coupling_stack(blocks64, z.double(), split)
+    with torch.no_grad():
+        x, d = flow(z.to(DEV))
+        zb, db = flow(x, inverse=True)
+    _cmp(x, x_ref, 3e-5, 1e-4)
+    _cmp(d, d_ref, 5e-4, 1e-4)
+    _cmp(zb, z.double(), 1e-4, 1e-4)
+
+
+def test_builder_style_stack_hidden128_on_tensor_cores(kernel_mode):
+    """Builder-exact Ala2 couplings (TORSIONS[17, circular] <-> FIXED[9],
+    BONDS[17] <-> ANGLES[17]; hidden (128,128) SiLU; WrapPeriodic conditioners on torsions): several
+    state tensors, periodic inputs, circular splines -> the tensor-core kernel's generic I/O path."""
+    g = torch.Generator().manual_seed(21)
+    nb = 8
+    T, F, Bd, A = 17, 9, 17, 17
+    def net(d_in, d_out, periodic=None):
+        m = of.make_mlp([d_in, 128, 128, d_out], "silu", g)
+        m.periodic = periodic
+        return m
+    blocks = [
+        {"kind": "spline", "transformed": (2,), "cond": (3,), "is_circular": True, "params_net": net(F, T * 3 * nb)},
+        {"kind": "spline", "transformed": (3,), "cond": (2,), "params_net": net(2 * T, F * (3 * nb + 1), (list(range(T)), 0.0, 1.0))},
+        {"kind": "spline", "transformed": (0,), "cond": (1,), "params_net": net(A, Bd * (3 * nb + 1))},
+        {"kind": "spline", "transformed": (1,), "cond": (0, 2), "params_net": net(Bd + 2 * T, A * (3 * nb + 1), (list(range(Bd, Bd + T)), 0.0, 1.0))},
+    ]
+    layers = [bg.CouplingFlow(transformer_from(b, DEV), transformed_indices=b["transformed"], cond_indices=b["cond"])
+              for b in blocks]
+    flow = bg.SequentialFlow(layers)
+    gd = torch.Generator().manual_seed(22)
+    xs = [torch.rand(300, w, generator=gd) for w in (Bd, A, T, F)]
+    ref = [x.double() for x in xs]
+    blocks64 = []
+    for b in blocks:
+        nb64 = dict(b)
+        m = b["params_net"]
+        nb64["params_net"] = of.MLP([w.double() for w in m.weights], [x.double() for x in m.biases], m.act, m.periodic)
+        blocks64.append(nb64)
+    dref = 0
+    for b in blocks64:
+        ref, d = of.coupling_block(b, ref)
+        dref = dref + d
+    with torch.no_grad():
+        *ys, dlogp = flow(*[x.to(DEV) for x in xs])
+        *zs, dinv = flow(*ys, inverse=True)
+    for got, want in zip(ys, ref):
+        _cmp(got, want, 3e-5, 1e-4)
+    _cmp(dlogp, dref, 5e-4, 1e-4)
+    for got, want in zip(zs, xs):
+        _cmp(got, want.double(), 1e-4, 1e-4)
