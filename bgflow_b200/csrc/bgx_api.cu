@@ -11,6 +11,9 @@ bool spline_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bg
 int spline_coupling_tc2(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int*, cudaStream_t);
 void tc_set_trace(unsigned long long*, int);
 bool affine_tc_eligible(const bgx_packed_mlp*, const bgx_packed_mlp*, int);
+bool affine_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, int);
+int affine_coupling_tc2(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, float, int, int*,
+                        cudaStream_t);
 int affine_coupling_tc(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, float, int, int*,
                        cudaStream_t);
 int spline_coupling_tc(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int*,
@@ -27,6 +30,8 @@ extern "C" int bgx_set_status_buffer(int32_t* device_int) {
 extern "C" int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
                                    const bgx_packed_mlp* scale, float log_alpha, int flags, void* stream) {
   if (!io) return BGX_ERR_INVALID;
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc2_eligible(io, shift, scale, flags))
+    return bgx::affine_coupling_tc2(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
   if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc_eligible(shift, scale, flags))
     return bgx::affine_coupling_tc(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
   return bgx::affine_coupling_simt(io, shift, scale, log_alpha, flags, (cudaStream_t)stream);

@@ -221,15 +221,17 @@ def test_precision_modes_report(kernel_mode):
         assert ex < 1e-4 and ed < 1e-3, (k, ex, ed)
 
 
-@pytest.mark.parametrize("batch", [4, 132, 1000, 1001, 4099])
-def test_tensor_core_kernels_partial_tiles(batch, kernel_mode):
-    """hidden = 128 stacks on ragged batches: the 2-CTA kernel (batch % 4 == 0, partial last tile),
-    the single-CTA kernel (other batches / bf16x6) and the SIMT kernel must all agree with the oracle."""
-    blocks, split = of.make_stack("spline", 66, 3, hidden=(128, 128), seed=11)
+@pytest.mark.parametrize("kind", ["spline", "affine"])
+@pytest.mark.parametrize("batch", [4, 132, 1000, 1001, 4099, 76036])
+def test_tensor_core_kernels_partial_tiles(kind, batch, kernel_mode):
+    """hidden = 128 stacks on ragged batches: the 2-CTA kernels (batch % 4 == 0, partial last tile;
+    76036 rows = more than two tiles per CTA), the single-CTA kernels (other batches / bf16x6) and the
+    SIMT kernel must all agree with the oracle."""
+    blocks, split = of.make_stack(kind, 66, 3, hidden=(128, 128), seed=11)
     flow = stack_from(blocks, split, DEV)
     g = torch.Generator().manual_seed(batch)
-    z = torch.rand(batch, 66, generator=g)
-    blocks64, _ = of.make_stack("spline", 66, 3, hidden=(128, 128), seed=11, dtype=torch.float64)
+    z = torch.rand(batch, 66, generator=g) if kind == "spline" else torch.randn(batch, 66, generator=g)
+    blocks64, _ = of.make_stack(kind, 66, 3, hidden=(128, 128), seed=11, dtype=torch.float64)
     x_ref, d_ref = of.coupling_stack(blocks64, z.double(), split)
     with torch.no_grad():
         x, d = flow(z.to(DEV))
@@ -237,6 +239,7 @@ def test_tensor_core_kernels_partial_tiles(batch, kernel_mode):
     _cmp(x, x_ref, 3e-5, 1e-4)
     _cmp(d, d_ref, 5e-4, 1e-4)
     _cmp(zb, z.double(), 1e-4, 1e-4)
+    _cmp(db, -d_ref, 5e-4, 1e-4)
 
 
 def test_builder_style_stack_hidden128_on_tensor_cores(kernel_mode):
