@@ -232,6 +232,33 @@ def bench_ic(args, dev):
     return out
 
 
+def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
+    """Secondary measurement (BASELINE config 5, "KL-train grad allreduce"): reverse-KL steps on a
+    Gaussian target — kernel forward, recompute backward, ONE flat gradient all-reduce (NCCL when
+    world > 1), Adam.  ``rows`` samples per rank per step."""
+    from bgflow_b200.distributed import allreduce_gradients
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-5)
+    n_elems = [0]
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        z = torch.rand(rows, dim, device=dev) if kind == "spline" else torch.randn(rows, dim, device=dev)
+        x, dlogp = flow(z)
+        loss = (0.5 * ((x - 0.5) / 0.25).square().sum(-1, keepdim=True) - dlogp).mean()
+        loss.backward()
+        n_elems[0] = allreduce_gradients(flow.parameters())
+        opt.step()
+
+    for _ in range(3):
+        train_step()
+    steps = max(3, args.steps // 2)
+    ms = run_timed(train_step, steps)
+    return {"samples_per_s": rows * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "rows_per_gpu": rows,
+            "allreduce_fp32_elems": n_elems[0], "n_gpus": world,
+            "what": "fused-kernel forward; backward = conditioner re-run + its GEMM backward (torch/cuBLAS fp32) + "
+                    "bgx_spline_backward kernel (affine: device-side torch); flat grad all-reduce; Adam"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,7 +271,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extras", action="store_true",
-                    help="also time the IC kernels and the restated single-GPU PyTorch path (adds to the JSON line)")
+                    help="also time the IC kernels, the restated single-GPU PyTorch path and a KL training step "
+                         "(adds to the JSON line)")
     args = ap.parse_args()
     if args.warmup < 3 and not DRYRUN:
         args.warmup = 3
@@ -433,6 +461,10 @@ def main():
                                  "sample": "65536 rows; oracle/flows.py op sequence on CUDA tensors (the reference's "
                                            "single-GPU PyTorch path, restated)"},
             "ic_ala2": bench_ic(args, dev)}
+    if args.extras:
+        tr = bench_train(args, flow, kind, dim, dev, run_timed, world)
+        if rank == 0:
+            out.setdefault("extras", {})["kl_train"] = tr
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

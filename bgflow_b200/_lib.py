@@ -83,6 +83,9 @@ SYMBOLS = {
                                       C.c_float, C.c_int, C.c_void_p]),
     "bgx_spline_coupling": (C.c_int, [P(bgx_coupling_io), P(bgx_packed_mlp), P(bgx_spline_cfg),
                                       C.c_int, C.c_void_p]),
+    "bgx_spline_backward": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, P(bgx_spline_cfg), C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "bgx_ic_to_xyz": (C.c_int, [P(bgx_zplan), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),

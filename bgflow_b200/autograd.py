@@ -1,17 +1,19 @@
-"""Autograd bridge for the fused coupling kernels (training support).
+"""Autograd bridge for the fused coupling and internal-coordinate kernels (training support,
+SURVEY.md §8b/§8e).
 
-Forward: always the fused CUDA kernel.  Backward: recompute-in-backward — the block is
-re-evaluated with the differentiable device-side PyTorch definition in ``_torch_math`` and
-differentiated by autograd (inputs AND conditioner parameters).  Nothing is saved besides the
-block's inputs, so training memory stays ``O(B * D)`` per block instead of the reference's
-``O(B * 825)`` parameter tensors; the backward itself is not fused yet.
+Forward: always the fused CUDA kernel.  Backward: recompute-in-backward — nothing is saved besides
+the block's inputs, so training memory stays ``O(B * D)`` per block instead of the reference's
+``O(B * 825)`` parameter tensors.  Spline blocks: the conditioner is re-run and differentiated by
+torch (dense GEMMs), the spline transform's chain rule is ONE hand-written kernel
+(``bgx_spline_backward``).  Affine blocks and the IC layer are re-evaluated with the differentiable
+device-side PyTorch definitions in ``_torch_math`` / ``_torch_math_ic``.
 """
 
 import torch
 
-from . import _torch_math
+from . import _torch_math, _torch_math_ic
 
-__all__ = ["fused_coupling_with_grad", "needs_grad"]
+__all__ = ["fused_coupling_with_grad", "needs_grad", "ic_to_xyz_with_grad", "ic_from_xyz_with_grad"]
 
 
 def needs_grad(tensors, module):
@@ -39,18 +41,45 @@ class _FusedCoupling(torch.autograd.Function):
         params = [p for p in t.parameters() if p.requires_grad]
         with torch.enable_grad():
             cond = [x.detach().requires_grad_(True) for x in saved[:ctx.n_cond]]
-            tr = [x.detach().requires_grad_(True) for x in saved[ctx.n_cond:]]
-            fn = _torch_math.spline if ctx.kind == "spline" else _torch_math.affine
-            out, dlogp = fn(t, torch.cat(cond, dim=-1), torch.cat(tr, dim=-1), ctx.inverse)
-            outs = torch.split(out, [x.shape[-1] for x in tr], dim=-1)
-            gin = torch.autograd.grad([*outs, dlogp], [*cond, *tr, *params],
-                                      grad_outputs=[g if g is not None else torch.zeros_like(o)
-                                                    for g, o in zip(grads, [*outs, dlogp])],
-                                      allow_unused=True)
-        g_inputs = gin[:ctx.n_cond + ctx.n_tr]
-        g_params = iter(gin[ctx.n_cond + ctx.n_tr:])
+            if ctx.kind == "spline":
+                gin, g_tr = _spline_backward(t, cond, saved[ctx.n_cond:], params, grads, ctx.inverse)
+            else:
+                tr = [x.detach().requires_grad_(True) for x in saved[ctx.n_cond:]]
+                out, dlogp = _torch_math.affine(t, torch.cat(cond, dim=-1), torch.cat(tr, dim=-1), ctx.inverse)
+                outs = torch.split(out, [x.shape[-1] for x in tr], dim=-1)
+                g_all = torch.autograd.grad([*outs, dlogp], [*cond, *tr, *params],
+                                            grad_outputs=[g if g is not None else torch.zeros_like(o)
+                                                          for g, o in zip(grads, [*outs, dlogp])],
+                                            allow_unused=True)
+                g_tr = g_all[ctx.n_cond:ctx.n_cond + ctx.n_tr]
+                gin = (*g_all[:ctx.n_cond], *g_all[ctx.n_cond + ctx.n_tr:])
+        g_cond = gin[:ctx.n_cond]
+        g_params = iter(gin[ctx.n_cond:])
         full = [next(g_params) if p.requires_grad else None for p in t.parameters()]
-        return (None, None, None, None, None, *g_inputs, *full)
+        return (None, None, None, None, None, *g_cond, *g_tr, *full)
+
+
+def _spline_backward(t, cond, tr, params, grads, inverse):
+    """Spline block backward: conditioner forward/backward with torch (dense GEMMs), the transform's
+    chain rule in ONE kernel (``bgx_spline_backward``).  Returns (grads of cond + params, grads of tr)."""
+    from . import engine
+    widths = [x.shape[-1] for x in tr]
+    y = torch.cat([x.detach() for x in tr], dim=-1) if len(tr) > 1 else tr[0].detach()
+    d_t = y.shape[-1]
+    p = t._params_net(torch.cat(cond, dim=-1) if len(cond) > 1 else cond[0])
+    lead = y.shape[:-1]
+    p2, y2 = p.reshape(-1, p.shape[-1]), y.reshape(-1, d_t)
+    k = p2.shape[-1] // (3 * d_t)
+    g_out = torch.cat([g if g is not None else torch.zeros_like(x) for g, x in zip(grads[:-1], tr)], dim=-1)
+    g_dl = grads[-1]
+    st = t._default_settings
+    d_p, d_y = engine.spline_backward(
+        p2.detach(), y2, g_out.reshape(-1, d_t), g_dl.reshape(-1) if g_dl is not None else None,
+        t._end_slope_cols(d_t, k, y.device), k, inverse=inverse, left=t._left, right=t._right, bottom=t._bottom,
+        top=t._top, min_bin_width=st["min_bin_width"], min_bin_height=st["min_bin_height"],
+        min_derivative=st["min_derivative"], identity_init=st["enable_identity_init"])
+    gin = torch.autograd.grad(p, [*cond, *params], grad_outputs=d_p.reshape(p.shape), allow_unused=True)
+    return gin, torch.split(d_y.reshape(*lead, d_t), widths, dim=-1)
 
 
 def fused_coupling_with_grad(transformer, kind, cond, tr, inverse):
@@ -58,3 +87,52 @@ def fused_coupling_with_grad(transformer, kind, cond, tr, inverse):
     params = list(transformer.parameters())
     res = _FusedCoupling.apply(transformer, kind, inverse, len(cond), len(tr), *cond, *tr, *params)
     return list(res[:-1]), res[-1]
+
+
+def _recompute_grads(fn, plan, saved, grads):
+    """Re-evaluate ``fn(plan, *inputs)`` with the device-side torch definition and pull ``grads`` back."""
+    with torch.enable_grad():
+        ins = [x.detach().requires_grad_(True) for x in saved]
+        outs = fn(plan, *ins)
+        pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
+        gin = torch.autograd.grad([o for o, _ in pairs], ins, grad_outputs=[g for _, g in pairs], allow_unused=True)
+    return gin
+
+
+class _ICToXYZ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, launch, bonds, angles, torsions, x0, R):
+        with torch.no_grad():
+            xyz, dlogp = launch(plan, bonds, angles, torsions, x0, R)
+        ctx.plan = plan
+        ctx.save_for_backward(bonds, angles, torsions, x0, R)
+        return xyz, dlogp
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_dlogp):
+        gin = _recompute_grads(_torch_math_ic.ic_to_xyz, ctx.plan, ctx.saved_tensors, (g_xyz, g_dlogp))
+        return (None, None, *gin)
+
+
+class _ICFromXYZ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, launch, xyz):
+        with torch.no_grad():
+            outs = launch(plan, xyz)
+        ctx.plan = plan
+        ctx.save_for_backward(xyz)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gin = _recompute_grads(_torch_math_ic.ic_from_xyz, ctx.plan, ctx.saved_tensors, grads)
+        return (None, None, *gin)
+
+
+def ic_to_xyz_with_grad(plan, launch, bonds, angles, torsions, x0, R):
+    """IC kernel forward, recompute backward.  ``launch`` is ``engine.ic_to_xyz``."""
+    return _ICToXYZ.apply(plan, launch, bonds, angles, torsions, x0, R)
+
+
+def ic_from_xyz_with_grad(plan, launch, xyz):
+    return _ICFromXYZ.apply(plan, launch, xyz)

@@ -235,6 +235,33 @@ def spline_coupling(cond, tr, net, n_bins, inverse=False, left=0.0, right=1.0, b
     return outs, dlogp
 
 
+def spline_backward(params, y, g_out, g_dlogp, end_slope_col, n_bins, inverse=False, left=0.0, right=1.0,
+                    bottom=0.0, top=1.0, min_bin_width=1e-3, min_bin_height=1e-3, min_derivative=1e-3,
+                    identity_init=True):
+    """dP, dy of the spline transform (``bgx_spline_backward``).  ``params`` ``[B, 3*K*D + n_nc]``
+    is the conditioner output, ``end_slope_col`` an int32 device tensor with D entries."""
+    lib = _lib.load()
+    require_cuda_fp32(params, y, g_out)
+    params, y, g_out = params.contiguous(), y.contiguous(), g_out.contiguous()
+    B, d_t = y.shape
+    d_params = torch.empty_like(params)
+    d_y = torch.empty_like(y)
+    if B == 0:
+        return d_params, d_y
+    gd = g_dlogp.reshape(-1).contiguous() if g_dlogp is not None else None
+    cfg = _lib.bgx_spline_cfg()
+    cfg.n_bins = n_bins
+    cfg.left, cfg.right, cfg.bottom, cfg.top = float(left), float(right), float(bottom), float(top)
+    cfg.min_bin_width, cfg.min_bin_height, cfg.min_derivative = min_bin_width, min_bin_height, min_derivative
+    cfg.identity_init = 1 if identity_init else 0
+    rc = lib.bgx_spline_backward(B, d_t, params.data_ptr(), params.stride(0), y.data_ptr(), g_out.data_ptr(),
+                                 gd.data_ptr() if gd is not None else None, end_slope_col.data_ptr(),
+                                 C.byref(cfg), _lib.FLAG_INVERSE if inverse else 0, d_params.data_ptr(),
+                                 d_y.data_ptr(), _stream())
+    _lib.check(rc, "bgx_spline_backward")
+    return d_params, d_y
+
+
 class ZPlan:
     """Host staging of a global z-matrix (what ic.py:25-97 does with numpy) + its device copy."""
 

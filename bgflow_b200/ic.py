@@ -5,12 +5,15 @@ same constructor, same read-only properties (consumed by the reference's
 ``ShapeDictionary.from_coordinate_transform``, factory/tensor_info.py:86-100), same direction
 convention: ``_forward`` maps Cartesian -> (bonds, angles, torsions, x0, R), ``_inverse`` maps
 back.  Host work (z-matrix staging, ic.py:25-97) happens once at construction in
-``engine.ZPlan``; every call is ONE kernel with closed-form log-determinants (no autograd).
+``engine.ZPlan``; every call is ONE kernel with closed-form log-determinants.  When gradients are
+requested the backward re-evaluates the transform with the device-side PyTorch definition in
+``_torch_math_ic`` (recompute-in-backward, like the coupling blocks).
 """
 
 import numpy as np
 import torch
 
+from . import autograd as _ag
 from . import engine
 from .flows import Flow
 
@@ -83,17 +86,16 @@ class GlobalInternalCoordinateTransformation(Flow):
     def _forward(self, x, *args, **kwargs):
         """xyz ``[B, 3N]`` -> bonds ``[B, N-1]``, angles ``[B, N-2]``, torsions ``[B, N-3]``,
         x0 ``[B, 1, 3]``, R ``[B, 3]``, dlogp ``[B, 1]`` (ic.py:633-676)."""
-        self._no_grad_yet(x)
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _ag.ic_from_xyz_with_grad(self._plan, engine.ic_from_xyz, x)
         return engine.ic_from_xyz(self._plan, x)
 
     def _inverse(self, bonds, angles, torsions, x0, R, *args, **kwargs):
         """(ic.py:678-716) -> xyz ``[B, 3N]``, dlogp ``[B, 1]``."""
-        self._no_grad_yet(bonds, angles, torsions, x0, R)
-        return engine.ic_to_xyz(self._plan, bonds, angles, torsions, x0, R)
-
-    @staticmethod
-    def _no_grad_yet(*tensors):
-        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-            raise NotImplementedError(
-                "the internal-coordinate kernels are inference-only in this version: call them under "
-                "torch.no_grad() / detach their inputs (backward kernels are listed as next in DESIGN.md)")
+        ins = (bonds, angles, torsions, x0, R)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in ins):
+            B = bonds.shape[0]
+            x0 = x0.reshape(-1, 1, 3).expand(B, 1, 3)
+            R = R.reshape(-1, 3).expand(B, 3)
+            return _ag.ic_to_xyz_with_grad(self._plan, engine.ic_to_xyz, bonds, angles, torsions, x0, R)
+        return engine.ic_to_xyz(self._plan, *ins)

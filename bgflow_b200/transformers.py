@@ -182,6 +182,22 @@ class ConditionalSplineTransformer(_FusedMixin, Transformer):
     def _n_noncircular(self, y_dim):
         return y_dim - sum(self._circular_mask(y_dim))
 
+    def _end_slope_cols(self, d_t, n_bins, device):
+        """int32 device tensor: for every transformed dim the column of the conditioner output that
+        holds its last slope (its own first slope if circular, else its S_last entry; spline.py:123-125)."""
+        key = (d_t, n_bins, str(device))
+        cache = self.__dict__.setdefault("_end_cols", {})
+        if key not in cache:
+            cols, nc = [], 0
+            for d, circ in enumerate(self._circular_mask(d_t)):
+                if circ:
+                    cols.append(2 * n_bins * d_t + d * n_bins)
+                else:
+                    cols.append(3 * n_bins * d_t + nc)
+                    nc += 1
+            cache[key] = torch.tensor(cols, dtype=torch.int32, device=device)
+        return cache[key]
+
     def _net_out_width(self):
         net = self._params_net.net if isinstance(self._params_net, WrapPeriodic) else self._params_net
         last = [m for m in net._layers if isinstance(m, torch.nn.Linear)][-1]

@@ -145,6 +145,23 @@ typedef struct bgx_spline_cfg {
 int bgx_spline_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* params_net,
                         const bgx_spline_cfg* cfg, int flags, void* stream);
 
+/* Backward of the spline TRANSFORM (training): the chain rule of spline.py:128-188 + nflows
+ * rational_quadratic_spline written out by hand, one thread per (sample, dim).
+ *   params        conditioner output [batch, >= 3*K*d_t + n_noncircular] in the reference's column
+ *                 layout (spline.py:113-125), row stride `params_stride` floats
+ *   y, g_out      [batch, d_t] dense: transformed input, gradient wrt the transformed output
+ *   g_dlogp       [batch] gradient wrt dlogp (or NULL = 0)
+ *   end_slope_col device, d_t entries: column of `params` that holds dim d's LAST slope — its own
+ *                 first slope column for circular dims, its S_last column otherwise (spline.py:123-125)
+ *   d_params      [batch, params_stride] gradient wrt `params` (every column the transform reads)
+ *   d_y           [batch, d_t] gradient wrt y (0 where y was clamped)
+ * flags: BGX_FLAG_INVERSE selects the direct branch (bgflow inverse).  The conditioner's own
+ * backward (dense GEMMs) stays with the caller (torch autograd in bgflow_b200/autograd.py). */
+int bgx_spline_backward(int64_t batch, int32_t d_t, const float* params, int64_t params_stride,
+                        const float* y, const float* g_out, const float* g_dlogp,
+                        const int32_t* end_slope_col, const bgx_spline_cfg* cfg, int flags,
+                        float* d_params, float* d_y, void* stream);
+
 /* ---- internal coordinates ------------------------------------------------------------- */
 
 /* Device-side plan of a global z-matrix (ic.py:25-97 staging done on the host). */

@@ -78,3 +78,117 @@ def test_kl_training_step_reduces_loss():
     opt = torch.optim.Adam(gen.parameters(), lr=5e-3)
     losses = [float(kl_train_step(gen, opt, 4096)) for _ in range(60)]
     assert np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.5, (losses[:5], losses[-5:])
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_internal_coordinate_gradients_match_oracle(normalize):
+    """IC kernels forward, recompute backward: vector-Jacobian products of both directions against
+    the oracle differentiated in fp64 (Energy.force / KLTrainer differentiate through the IC layer,
+    trainers.py:158-175)."""
+    from oracle import ic as oic
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z, normalize_angles=normalize)
+    oplan = oic.make_plan(oic.ALA2_GLOBAL_Z)
+    g = torch.Generator().manual_seed(8)
+    xyz = torch.as_tensor(oic.ALA2_XYZ, dtype=torch.float32).reshape(1, -1) + 0.01 * torch.randn(40, 66, generator=g)
+    x64 = xyz.double().requires_grad_(True)
+    ref = oic.xyz_to_ic(oplan, x64, normalize_angles=normalize)
+    ws = [torch.randn(t.shape, generator=g) for t in ref]
+    g_ref = torch.autograd.grad(sum((a * w.double()).sum() for a, w in zip(ref, ws)), x64)[0]
+    xc = xyz.to(DEV).requires_grad_(True)
+    outs = ic(xc)
+    assert all(o.requires_grad for o in outs)
+    sum((a * w.to(DEV)).sum() for a, w in zip(outs, ws)).backward()
+    s = g_ref.abs().max().item()
+    np.testing.assert_allclose(xc.grad.cpu().double().numpy(), g_ref.numpy(), atol=2e-3 * s, rtol=2e-3)
+
+    ins64 = [t.detach().clone().requires_grad_(True) for t in ref[:5]]
+    ref2 = oic.ic_to_xyz(oplan, *ins64, normalize_angles=normalize)
+    ws = [torch.randn(t.shape, generator=g) for t in ref2]
+    g_ref = torch.autograd.grad(sum((a * w.double()).sum() for a, w in zip(ref2, ws)), ins64)
+    ins = [t.detach().float().to(DEV).requires_grad_(True) for t in ref[:5]]
+    xyz_k, dlogp_k = ic(*ins, inverse=True)
+    np.testing.assert_allclose(xyz_k.detach().cpu().double().numpy(), ref2[0].detach().numpy(), atol=1e-4)
+    ((xyz_k * ws[0].to(DEV)).sum() + (dlogp_k * ws[1].to(DEV)).sum()).backward()
+    for got, want in zip(ins, g_ref):
+        s = max(want.abs().max().item(), 1e-6)
+        np.testing.assert_allclose(got.grad.cpu().double().numpy(), want.numpy(), atol=3e-3 * s, rtol=3e-3)
+
+
+def test_energy_gradient_reaches_flow_parameters_through_ic_layer():
+    """z -> spline couplings (kernel) -> IC layer (kernel) -> xyz -> energy; parameter gradients
+    against the same graph built from the oracle in fp64."""
+    from oracle import ic as oic
+    nb, na, nt = 21, 20, 19
+    blocks, split = of.make_stack("spline", nb + na + nt, 2, hidden=(128, 128), seed=13)
+    blocks64, _ = of.make_stack("spline", nb + na + nt, 2, hidden=(128, 128), seed=13, dtype=torch.float64)
+    flow = stack_from(blocks, split, DEV)
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    oplan = oic.make_plan(oic.ALA2_GLOBAL_Z)
+    g = torch.Generator().manual_seed(5)
+    z = 0.25 + 0.5 * torch.rand(64, nb + na + nt, generator=g)
+    x0 = torch.zeros(64, 1, 3)
+    R = torch.full((64, 3), 0.5)
+    w = torch.randn(64, 66, generator=g)
+
+    def to_ics(y):      # spline outputs live in (0,1): bonds scaled to a physical range
+        return 0.1 + 0.1 * y[:, :nb], 0.25 + 0.5 * y[:, nb:nb + na], y[:, nb + na:]
+
+    params64 = []
+    for b in blocks64:
+        for t in b["params_net"].weights + b["params_net"].biases:
+            t.requires_grad_(True)
+            params64.append(t)
+    y64, d64 = of.coupling_stack(blocks64, z.double(), split)
+    xyz64, dic64 = oic.ic_to_xyz(oplan, *to_ics(y64), x0.double(), R.double())
+    loss64 = (xyz64 * w.double()).sum() + (d64 + dic64).sum()
+    g_ref = torch.autograd.grad(loss64, params64)
+
+    y, d = flow(z.to(DEV))
+    xyz, dic = ic(*to_ics(y), x0.to(DEV), R.to(DEV), inverse=True)
+    loss = (xyz * w.to(DEV)).sum() + (d + dic).sum()
+    np.testing.assert_allclose(loss.item(), loss64.item(), rtol=1e-4)
+    loss.backward()
+    ours = []
+    for m in flow.modules():
+        if isinstance(m, bg.DenseNet):
+            lin = [l for l in m._layers if isinstance(l, torch.nn.Linear)]
+            ours += [l.weight.grad for l in lin] + [l.bias.grad for l in lin]
+    assert len(ours) == len(g_ref)
+    for a, b in zip(ours, g_ref):
+        s = max(b.abs().max().item(), 1e-6)
+        np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=5e-3 * s, rtol=5e-3)
+
+
+@pytest.mark.parametrize("d_t,n_bins,circular", [(7, 5, [True, False, True, False, False, True, False]),
+                                                 (4, 12, True), (3, 20, False), (33, 8, False)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_spline_backward_kernel_against_torch_definition(d_t, n_bins, circular, inverse):
+    """bgx_spline_backward (hand-written chain rule) against autograd of the device-side torch
+    definition, fp32 on both sides: circular / mixed masks, other bin counts, clamped inputs."""
+    from bgflow_b200 import _torch_math
+    torch.manual_seed(d_t * 100 + n_bins)
+    n_nc = d_t - (sum(circular) if isinstance(circular, list) else (d_t if circular else 0))
+    net = bg.DenseNet([6, 32, 3 * n_bins * d_t + n_nc], activation=torch.nn.SiLU()).to(DEV)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(3.0)
+    tr = bg.ConditionalSplineTransformer(net, is_circular=circular)
+    cond = torch.randn(257, 6, device=DEV, requires_grad=True)
+    y = torch.rand(257, d_t, device=DEV)
+    y[0, 0], y[1, -1] = -0.1, 1.2
+    y.requires_grad_(True)
+    wx, wd = torch.randn(257, d_t, device=DEV), torch.randn(257, 1, device=DEV)
+
+    out, dlogp = tr.forward(cond, y, inverse=inverse)
+    ((out * wx).sum() + (dlogp * wd).sum()).backward()
+    got = [cond.grad.clone(), y.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+    cond.grad = y.grad = None
+    net.zero_grad()
+    out_t, dlogp_t = _torch_math.spline(tr, cond, y, inverse)
+    torch.testing.assert_close(out, out_t, atol=2e-5, rtol=1e-4)
+    ((out_t * wx).sum() + (dlogp_t * wd).sum()).backward()
+    want = [cond.grad, y.grad] + [p.grad for p in net.parameters()]
+    for a, b in zip(got, want):
+        s = max(b.abs().max().item(), 1e-6)
+        torch.testing.assert_close(a, b, atol=2e-3 * s, rtol=2e-3)
+    assert y.grad[0, 0] == 0 and got[1][0, 0] == 0          # clamped input: no gradient
