@@ -35,7 +35,11 @@ def _stream():
 #: ~2^-16 relative per product, measured 6e-7 max abs error over the 8-block golden stack) or
 #: "bf16x6" (three terms, six products: fp32-equivalent, twice the tensor-core time);
 #: ``force_simt`` runs the shape-general fp32 SIMT kernel even where the tensor-core kernel applies.
-config = {"precision": "bf16x3", "force_simt": False}
+config = {"precision": "bf16x3", "force_simt": False,
+          # couplings over several / strided tensors: gather each side into one dense buffer first when
+          # the batch is large, so that the two-CTAs-per-SM kernels (dense single tensors only) apply;
+          # the copies cost ~5 % of a block, the one-CTA kernel ~25 %
+          "gather_segments": True, "gather_min_rows": 4096}
 
 _status = {}
 
@@ -169,6 +173,14 @@ def _fill_io(cond, tr, dlogp_in):
         if t.shape[0] != B:
             raise ValueError("all tensors of a coupling must share their batch shape")
     widths = [t.shape[1] for t in tr2]
+    if (config.get("gather_segments") and not config.get("force_simt") and config.get("precision") == "bf16x3"
+            and B >= config.get("gather_min_rows", 4096) and B % 4 == 0):
+        def dense(t):
+            return t.stride(0) == t.shape[1] and t.stride(1) == 1 and t.data_ptr() % 16 == 0
+        if len(cond2) > 1 or (cond2 and not dense(cond2[0])):
+            cond2 = [torch.cat(cond2, dim=1) if len(cond2) > 1 else cond2[0].contiguous()]
+        if len(tr2) > 1 or not dense(tr2[0]):
+            tr2 = [torch.cat(tr2, dim=1) if len(tr2) > 1 else tr2[0].contiguous()]
     out = torch.empty(B, sum(widths), dtype=torch.float32, device=tr2[0].device)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=tr2[0].device)
     io = _lib.bgx_coupling_io()
@@ -179,12 +191,17 @@ def _fill_io(cond, tr, dlogp_in):
     io.n_tr = len(tr2)
     col = 0
     outs = []
-    for i, t in enumerate(tr2):
-        io.tr_in[i].ptr, io.tr_in[i].width, io.tr_in[i].stride = t.data_ptr(), t.shape[1], t.stride(0) if B > 1 else t.shape[1]
-        o = out[:, col:col + widths[i]]
-        io.tr_out[i].ptr, io.tr_out[i].width, io.tr_out[i].stride = o.data_ptr(), widths[i], out.stride(0)
-        outs.append(o.reshape(*batch_shape, widths[i]) if len(batch_shape) != 1 else o)
-        col += widths[i]
+    for i, w in enumerate(widths):
+        o = out[:, col:col + w]
+        outs.append(o.reshape(*batch_shape, w) if len(batch_shape) != 1 else o)
+        if len(tr2) == len(widths):
+            t = tr2[i]
+            io.tr_in[i].ptr, io.tr_in[i].width, io.tr_in[i].stride = t.data_ptr(), w, t.stride(0) if B > 1 else w
+            io.tr_out[i].ptr, io.tr_out[i].width, io.tr_out[i].stride = o.data_ptr(), w, out.stride(0)
+        col += w
+    if len(tr2) != len(widths):          # gathered: one dense segment in, the whole output buffer out
+        io.tr_in[0].ptr, io.tr_in[0].width, io.tr_in[0].stride = tr2[0].data_ptr(), col, col
+        io.tr_out[0].ptr, io.tr_out[0].width, io.tr_out[0].stride = out.data_ptr(), col, col
     keep = [cond2, tr2]
     if dlogp_in is not None:
         require_cuda_fp32(dlogp_in)

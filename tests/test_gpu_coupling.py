@@ -242,10 +242,12 @@ def test_tensor_core_kernels_partial_tiles(kind, batch, kernel_mode):
     _cmp(db, -d_ref, 5e-4, 1e-4)
 
 
-def test_builder_style_stack_hidden128_on_tensor_cores(kernel_mode):
+@pytest.mark.parametrize("batch", [300, 4096])
+def test_builder_style_stack_hidden128_on_tensor_cores(batch, kernel_mode):
     """Builder-exact Ala2 couplings (TORSIONS[17, circular] <-> FIXED[9],
     BONDS[17] <-> ANGLES[17]; hidden (128,128) SiLU; WrapPeriodic conditioners on torsions): several
-    state tensors, periodic inputs, circular splines -> the tensor-core kernel's generic I/O path."""
+    state tensors, periodic inputs, circular splines -> the one-CTA kernel's generic I/O path (300 rows)
+    or the gather-then-two-CTA path (4096 rows)."""
     g = torch.Generator().manual_seed(21)
     nb = 8
     T, F, Bd, A = 17, 9, 17, 17
@@ -263,7 +265,7 @@ def test_builder_style_stack_hidden128_on_tensor_cores(kernel_mode):
               for b in blocks]
     flow = bg.SequentialFlow(layers)
     gd = torch.Generator().manual_seed(22)
-    xs = [torch.rand(300, w, generator=gd) for w in (Bd, A, T, F)]
+    xs = [torch.rand(batch, w, generator=gd) for w in (Bd, A, T, F)]
     ref = [x.double() for x in xs]
     blocks64 = []
     for b in blocks:
