@@ -12,7 +12,10 @@ from .flows import (Flow, SequentialFlow, InverseFlow, SplitFlow, MergeFlow, Swa
                     WrapFlow, SetConstantFlow)
 from .nets import DenseNet, MeanFreeDenseNet, WrapPeriodic
 from .transformers import Transformer, AffineTransformer, ConditionalSplineTransformer
-from .ic import GlobalInternalCoordinateTransformation
+from .ic import (GlobalInternalCoordinateTransformation, RelativeInternalCoordinateTransformation,
+                 MixedCoordinateTransformation, WhitenFlow)
+from .cdf import (CDFTransform, DistributionTransferFlow, ConstrainGaussianFlow, TruncatedNormalDistribution,
+                  SloppyUniform, MultiCDFFlow, MappedICTail, fuse_domain_maps)
 from .bg import (BoltzmannGenerator, NormalDistribution, UniformDistribution, unnormalized_kl_div,
                  unormalized_nll, log_weights, log_weights_given_latent, effective_sample_size,
                  sampling_efficiency)

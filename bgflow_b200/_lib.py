@@ -74,6 +74,20 @@ class bgx_zplan(C.Structure):
                 ("eps", C.c_float)]
 
 
+class bgx_cdf_col(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("p", C.c_float * 7)]
+
+
+class bgx_relplan(C.Structure):
+    _fields_ = [("n_atoms", C.c_int32), ("n_fixed", C.c_int32), ("n_rel", C.c_int32),
+                ("fixed", C.c_void_p), ("rel", C.c_void_p), ("order", C.c_void_p),
+                ("normalize_angles", C.c_int32), ("eps", C.c_float), ("keepdims", C.c_int32),
+                ("mean", C.c_void_p), ("blacken", C.c_void_p), ("whiten", C.c_void_p),
+                ("log_det_whiten", C.c_float)]
+
+
+DIST_NONE, DIST_NORMAL, DIST_TRUNCNORMAL, DIST_UNIFORM = 0, 1, 2, 3
+
 # every symbol include/bgflow_b200.h declares: (name, restype, argtypes)
 P = C.POINTER
 SYMBOLS = {
@@ -92,6 +106,19 @@ SYMBOLS = {
     "bgx_ic_from_xyz": (C.c_int, [P(bgx_zplan), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "bgx_cdf_col_init": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, P(bgx_cdf_col)]),
+    "bgx_cdf_map": (C.c_int, [C.c_int64, C.c_int32, P(bgx_seg), P(bgx_seg), C.c_void_p, C.c_float, C.c_float,
+                              C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgx_ic_to_xyz_mapped": (C.c_int, [P(bgx_zplan), C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgx_ic_from_xyz_mapped": (C.c_int, [P(bgx_zplan), C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgx_relic_to_xyz": (C.c_int, [P(bgx_relplan), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgx_relic_from_xyz": (C.c_int, [P(bgx_relplan), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_tc_selftest": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "bgx_set_status_buffer": (C.c_int, [C.c_void_p]),

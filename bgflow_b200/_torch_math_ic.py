@@ -15,7 +15,7 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["ic_to_xyz", "ic_from_xyz"]
+__all__ = ["ic_to_xyz", "ic_from_xyz", "relic_to_xyz", "relic_from_xyz"]
 
 _PI = math.pi
 _TWO_PI = 2.0 * math.pi
@@ -134,6 +134,81 @@ def ic_to_xyz(plan, bonds, angles, torsions, x0, R):
         d = rb.index_select(1, sel)[..., None]
         a = ra.index_select(1, sel)[..., None]
         t = rt.index_select(1, sel)[..., None]
+        q1 = torch.stack([pos[int(plan.rel[r, 1])] for r in rows], dim=1)
+        q2 = torch.stack([pos[int(plan.rel[r, 2])] for r in rows], dim=1)
+        q3 = torch.stack([pos[int(plan.rel[r, 3])] for r in rows], dim=1)
+        v1 = q1 - q2
+        normal = torch.linalg.cross(v1, q1 - q3, dim=-1)
+        inplane = _unit(torch.linalg.cross(v1, normal, dim=-1), eps)
+        normal = _unit(normal, eps)
+        direction = _unit(inplane * torch.cos(t) - normal * torch.sin(t), eps)
+        new = q1 + direction * (d * torch.sin(a)) - _unit(v1, eps) * (d * torch.cos(a))
+        for c, r in enumerate(rows):
+            pos[int(plan.rel[r, 0])] = new[:, c]
+    xyz = torch.stack([pos[i] for i in range(plan.n_atoms)], dim=1).reshape(B, -1)
+    return xyz, dlogp
+
+
+# ---- relative / mixed transforms (backward definitions of bgx_relic_*) -----------------------------
+
+def _whiten_tensors(plan, like):
+    w = plan.whitening
+    mk = lambda a: torch.as_tensor(np.asarray(a), dtype=like.dtype, device=like.device)
+    return mk(w["mean"]), mk(w["whiten"]), mk(w["blacken"])
+
+
+def relic_from_xyz(plan, xyz):
+    """xyz ``[B, 3N]`` -> (bonds, angles, torsions ``[B, n_rel]``, fixed block, dlogp)
+    (ic.py:386-433; with ``plan.whitening`` additionally pca.py:83-91)."""
+    eps = plan.eps
+    B = xyz.shape[0]
+    x = xyz.reshape(B, -1, 3)
+    idx = torch.as_tensor(np.ascontiguousarray(plan.rel.T), device=x.device)
+    pi, pj, pk, pl = (x.index_select(1, idx[c]) for c in range(4))
+    bond = torch.linalg.norm(pj - pi, dim=-1).clamp_min(eps)
+    cos_a, sin_a = _cos_sin_angle(pi, pj, pk, eps)
+    angle = torch.acos(cos_a)
+    axis = _unit(pk - pj, eps)
+    out0 = pi - pj
+    out1 = pl - pk
+    v = out0 - (out0 * axis).sum(-1, keepdim=True) * axis
+    w = out1 - (out1 * axis).sum(-1, keepdim=True) * axis
+    torsion = torch.atan2((torch.linalg.cross(axis, v, dim=-1) * w).sum(-1), (v * w).sum(-1))
+    dlogp = -(2.0 * torch.log(bond) + torch.log(sin_a)).sum(-1, keepdim=True)
+    if plan.normalize_angles:
+        angle = angle / _PI
+        torsion = (torsion + _PI) / _TWO_PI
+        dlogp = dlogp - angle.shape[-1] * math.log(_PI) - torsion.shape[-1] * math.log(_TWO_PI)
+    fixed = x.index_select(1, torch.as_tensor(plan.fixed, device=x.device)).reshape(B, -1)
+    if plan.whitening is not None:
+        mean, tw, _ = _whiten_tensors(plan, fixed)
+        fixed = torch.matmul(fixed - mean, tw)
+        dlogp = dlogp + float(plan.whitening["jacobian_xz"])
+    return bond, angle, torsion, fixed, dlogp
+
+
+def relic_to_xyz(plan, bonds, angles, torsions, fixed):
+    """(ic.py:435-513; with ``plan.whitening`` additionally pca.py:93-99) -> xyz ``[B, 3N]``, dlogp."""
+    eps = plan.eps
+    B = bonds.shape[0]
+    const = 0.0
+    if plan.normalize_angles:
+        angles = angles * _PI
+        torsions = torsions * _TWO_PI - _PI
+        const = angles.shape[-1] * math.log(_PI) + torsions.shape[-1] * math.log(_TWO_PI)
+    dlogp = (2.0 * torch.log(bonds)).sum(-1, keepdim=True) + torch.log(torch.sin(angles)).sum(-1, keepdim=True) + const
+    fixed = fixed.reshape(B, -1)
+    if plan.whitening is not None:
+        mean, _, tb = _whiten_tensors(plan, fixed)
+        fixed = torch.matmul(fixed, tb) + mean
+        dlogp = dlogp - float(plan.whitening["jacobian_xz"])
+    xf = fixed.reshape(B, -1, 3)
+    pos = {int(a): xf[:, c] for c, a in enumerate(plan.fixed)}
+    for rows in _stages(plan):
+        sel = torch.as_tensor(rows, device=bonds.device)
+        d = bonds.index_select(1, sel)[..., None]
+        a = angles.index_select(1, sel)[..., None]
+        t = torsions.index_select(1, sel)[..., None]
         q1 = torch.stack([pos[int(plan.rel[r, 1])] for r in rows], dim=1)
         q2 = torch.stack([pos[int(plan.rel[r, 2])] for r in rows], dim=1)
         q3 = torch.stack([pos[int(plan.rel[r, 3])] for r in rows], dim=1)

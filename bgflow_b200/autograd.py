@@ -13,7 +13,8 @@ import torch
 
 from . import _torch_math, _torch_math_ic
 
-__all__ = ["fused_coupling_with_grad", "needs_grad", "ic_to_xyz_with_grad", "ic_from_xyz_with_grad"]
+__all__ = ["fused_coupling_with_grad", "needs_grad", "ic_to_xyz_with_grad", "ic_from_xyz_with_grad",
+           "relic_to_xyz_with_grad", "relic_from_xyz_with_grad"]
 
 
 def needs_grad(tensors, module):
@@ -136,3 +137,42 @@ def ic_to_xyz_with_grad(plan, launch, bonds, angles, torsions, x0, R):
 
 def ic_from_xyz_with_grad(plan, launch, xyz):
     return _ICFromXYZ.apply(plan, launch, xyz)
+
+
+class _RelICToXYZ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, launch, bonds, angles, torsions, fixed):
+        with torch.no_grad():
+            xyz, dlogp = launch(plan, bonds, angles, torsions, fixed)
+        ctx.plan = plan
+        ctx.save_for_backward(bonds, angles, torsions, fixed)
+        return xyz, dlogp
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_dlogp):
+        gin = _recompute_grads(_torch_math_ic.relic_to_xyz, ctx.plan, ctx.saved_tensors, (g_xyz, g_dlogp))
+        return (None, None, *gin)
+
+
+class _RelICFromXYZ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, launch, xyz):
+        with torch.no_grad():
+            outs = launch(plan, xyz)
+        ctx.plan = plan
+        ctx.save_for_backward(xyz)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gin = _recompute_grads(_torch_math_ic.relic_from_xyz, ctx.plan, ctx.saved_tensors, grads)
+        return (None, None, *gin)
+
+
+def relic_to_xyz_with_grad(plan, launch, bonds, angles, torsions, fixed):
+    """Relative / mixed IC kernel forward, recompute backward.  ``launch`` is ``engine.relic_to_xyz``."""
+    return _RelICToXYZ.apply(plan, launch, bonds, angles, torsions, fixed)
+
+
+def relic_from_xyz_with_grad(plan, launch, xyz):
+    return _RelICFromXYZ.apply(plan, launch, xyz)

@@ -11,36 +11,39 @@
 // reference frame; both determinants have closed forms:
 //   placed atom: 2 ln b + ln sin a ;  frame: 2 ln d01 + 2 ln d12 + ln sin a012.
 //
+// The same two kernels also run the RELATIVE transform (RelativeInternalCoordinateTransformation,
+// ic.py:268-513: no reference frame, the fixed atoms' Cartesian coordinates are an input / output
+// block) and the MIXED transform (MixedCoordinateTransformation, ic.py:719-884: the fixed block is
+// whitened by a static PCA, pca.py:37-107), and can apply the IC-domain CDF maps of the builder
+// (cdf.py:29-46, bgx_cdf_math.cuh) to every internal coordinate on the fly.
+//
 // Layout: the [tile x 3N] coordinate block of a CTA is contiguous in global memory; it is
 // staged through shared memory as P[c][t] (leading dim BT+1: conflict-free both for the
 // per-thread phase (fixed c, consecutive t) and for the coalesced copy phase).
-#include "bgx_common.cuh"
+#include "bgx_ic.cuh"
+#include "bgx_cdf_math.cuh"
 
 namespace bgx {
 
-constexpr int BT = 128;       // samples (threads) per CTA
-constexpr int LDT = BT + 1;
-constexpr float PI_F = 3.14159265358979323846f;
-constexpr float TWO_PI_F = 6.28318530717958647692f;
-
-struct V3 {
-  float x, y, z;
-};
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) {
-  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
-}
-__device__ __forceinline__ float norm_c(V3 a, float eps) { return fmaxf(sqrtf(dot(a, a)), eps); }
-// 1 / max(|a|, eps) with one MUFU.RSQ (eps^2 = 1e-14 is representable)
-__device__ __forceinline__ float inv_norm_c(V3 a, float eps2) { return rsqrtf(fmaxf(dot(a, a), eps2)); }
+enum { IC_GLOBAL = 0, IC_RELATIVE = 1 };
 
 struct IcArgs {
   long long B;
+  int kind;               // IC_GLOBAL: 3 seed atoms + reference frame; IC_RELATIVE: fixed-atom block
   int n_atoms, n_rel;
+  int nb, na, nt;         // columns of bonds / angles / torsions (global: N-1, N-2, N-3; relative: n_rel each)
+  int off_b, off_a;       // column of z-matrix row 0 in bonds / angles (global: 2, 1; relative: 0, 0)
   int s0, s1, s2;
+  // relative / mixed transforms
+  int n_fixed, keep, fixed_w;          // fixed_w = keep ? keep : 3 * n_fixed (columns of the fixed tensor)
+  const int* fixed;                    // [n_fixed] atom ids
+  const float *mean, *blacken, *whiten;
+  float ld_whiten;
+  const float* fixed_in;
+  float* fixed_out;
+  // optional CDF maps of the IC columns (bonds | angles | torsions order)
+  const bgx_cdf_col* marg;
+  CdfClamp clamp;
   const int* rel;    // [n_rel][4]
   const int* order;  // [n_rel]
   const int* slot_of_col;  // [3N-6]: smem slot (3*atom + {0:bond,1:angle,2:torsion}) of every IC column,
@@ -56,35 +59,7 @@ struct IcArgs {
   float* dlogp_out;
 };
 
-template <bool SMEM>
-struct PosStore {
-  float* base;
-  long long stride_c;  // distance between consecutive coordinates
-  __device__ __forceinline__ V3 get(int atom) const {
-    const float* p = base + (long long)(3 * atom) * stride_c;
-    return {p[0], p[stride_c], p[2 * stride_c]};
-  }
-  __device__ __forceinline__ void set(int atom, V3 v) const {
-    float* p = base + (long long)(3 * atom) * stride_c;
-    p[0] = v.x;
-    p[stride_c] = v.y;
-    p[2 * stride_c] = v.z;
-  }
-};
-
 // ---------------------------------------------------------------- IC -> Cartesian
-// division-free walk of thread t over the elements e = t, t+BT, ... of a [rows x W] block
-template <typename F>
-__device__ __forceinline__ void walk_block(int t, int W, int rows, F&& body) {
-  int m = t / W, c = t - m * W;
-  const int dm = BT / W, dc = BT - dm * W;
-  while (m < rows) {
-    body(m, c);
-    m += dm; c += dc;
-    if (c >= W) { c -= W; ++m; }
-  }
-}
-
 template <bool SMEM>
 __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
   extern __shared__ float sm[];
@@ -92,8 +67,9 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
   const long long row0 = (long long)blockIdx.x * BT;
   const long long row = row0 + t;
   const bool live = row < a.B;
-  const int N = a.n_atoms, nb = N - 1, na = N - 2, nt = N - 3;
+  const int N = a.n_atoms, nb = a.nb, na = a.na, nt = a.nt;
   const int nrow = (int)min((long long)BT, a.B - row0);
+  const bool global = a.kind == IC_GLOBAL;
   PosStore<SMEM> pos;
   if (SMEM) {
     // Every placed atom owns exactly three internal coordinates and three Cartesian coordinates:
@@ -103,9 +79,25 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
     const float* gb = a.bonds + row0 * nb;
     const float* ga = a.angles + row0 * na;
     const float* gt = a.torsions + row0 * nt;
-    walk_block(t, nb, nrow, [&](int m, int c) { sm[a.slot_of_col[c] * LDT + m] = __ldg(gb + m * nb + c); });
-    walk_block(t, na, nrow, [&](int m, int c) { sm[a.slot_of_col[nb + c] * LDT + m] = __ldg(ga + m * na + c); });
-    walk_block(t, nt, nrow, [&](int m, int c) { sm[a.slot_of_col[nb + na + c] * LDT + m] = __ldg(gt + m * nt + c); });
+    if (global) {
+      walk_block(t, nb, nrow, [&](int m, int c) { sm[a.slot_of_col[c] * LDT + m] = __ldg(gb + m * nb + c); });
+      walk_block(t, na, nrow, [&](int m, int c) { sm[a.slot_of_col[nb + c] * LDT + m] = __ldg(ga + m * na + c); });
+      walk_block(t, nt, nrow, [&](int m, int c) { sm[a.slot_of_col[nb + na + c] * LDT + m] = __ldg(gt + m * nt + c); });
+    } else {
+      // column r of every IC tensor belongs to the atom of z-matrix row r
+      walk_block(t, nb, nrow, [&](int m, int c) { sm[(3 * a.rel[4 * c]) * LDT + m] = __ldg(gb + m * nb + c); });
+      walk_block(t, na, nrow, [&](int m, int c) { sm[(3 * a.rel[4 * c] + 1) * LDT + m] = __ldg(ga + m * na + c); });
+      walk_block(t, nt, nrow, [&](int m, int c) { sm[(3 * a.rel[4 * c] + 2) * LDT + m] = __ldg(gt + m * nt + c); });
+      const int wf = a.fixed_w;
+      const float* gf = a.fixed_in + row0 * wf;
+      if (a.keep == 0)     // Cartesian block of the fixed atoms goes straight to their position slots
+        walk_block(t, wf, nrow, [&](int m, int c) {
+          const int i = c / 3;
+          sm[(3 * a.fixed[i] + (c - 3 * i)) * LDT + m] = __ldg(gf + m * wf + c);
+        });
+      else                 // whitened block: parked behind the positions, un-whitened per thread below
+        walk_block(t, wf, nrow, [&](int m, int c) { sm[(3 * N + c) * LDT + m] = __ldg(gf + m * wf + c); });
+    }
     __syncthreads();
   } else {
     pos.base = a.xyz + row * (long long)(3 * N); pos.stride_c = 1;
@@ -115,6 +107,8 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
     const float* bo = a.bonds + row * nb;
     const float* an = a.angles + row * na;
     const float* to = a.torsions + row * nt;
+    float dl = 0.f;
+    if (global) {
     const float* x0p = a.x0 + row * a.x0_stride;
     const float* rp = a.R + row * a.r_stride;
     float d01, d12, a012;
@@ -124,12 +118,17 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
       d01 = bo[0]; d12 = bo[1]; a012 = an[0];
     }
     float alpha = rp[0], beta = rp[1], gamma = rp[2];
-    float dl = 0.f;
+    if (a.marg) {
+      float ld;
+      cdf_inverse(a.marg[0], a.clamp, d01, d01, ld); dl += ld;
+      cdf_inverse(a.marg[1], a.clamp, d12, d12, ld); dl += ld;
+      cdf_inverse(a.marg[nb], a.clamp, a012, a012, ld); dl += ld;
+    }
     if (a.normalize) {
       a012 *= PI_F;
       alpha = alpha * TWO_PI_F - PI_F;
       gamma = gamma * TWO_PI_F - PI_F;
-      dl = (float)((double)na * 1.1447298858494002 + (double)(nt + 2) * 1.8378770664093453);
+      dl += (float)((double)na * 1.1447298858494002 + (double)(nt + 2) * 1.8378770664093453);
     }
     float sa, ca, sb, cb, sg, cg, s012, c012;
     sincosf(alpha, &sa, &ca);
@@ -154,6 +153,30 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
     pos.set(a.s2, x2);
     // log-det terms are accumulated as a product where that cannot overflow: one log per 4 atoms
     dl += 2.f * __logf(d01 * d12) + __logf(s012);
+    } else {
+      if (a.normalize) dl = (float)((double)na * 1.1447298858494002 + (double)nt * 1.8378770664093453);
+      const int nf3 = 3 * a.n_fixed;
+      if (a.keep > 0) {
+        // x_fixed = z_fixed . Tblacken + mean   (pca.py:93-99), log-det -jacobian_xz
+        const float* zf = a.fixed_in + row * a.keep;
+        for (int i = 0; i < a.n_fixed; ++i) {
+          float acc[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c] = __ldg(a.mean + 3 * i + c);
+          for (int k = 0; k < a.keep; ++k) {
+            const float zk = SMEM ? pos.base[(3 * N + k) * LDT] : zf[k];
+            const float* tb = a.blacken + (long long)k * nf3 + 3 * i;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] = fmaf(zk, __ldg(tb + c), acc[c]);
+          }
+          pos.set(a.fixed[i], {acc[0], acc[1], acc[2]});
+        }
+        dl -= a.ld_whiten;
+      } else if (!SMEM) {
+        const float* xf = a.fixed_in + row * nf3;
+        for (int i = 0; i < a.n_fixed; ++i) pos.set(a.fixed[i], {xf[3 * i], xf[3 * i + 1], xf[3 * i + 2]});
+      }
+    }
     for (int q = 0; q < a.n_rel; ++q) {
       const int r = a.order[q];
       const int4 z = *reinterpret_cast<const int4*>(a.rel + 4 * r);
@@ -162,7 +185,14 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
         const float* ic = pos.base + (3 * z.x) * LDT;
         d = ic[0]; ang = ic[LDT]; tor = ic[2 * LDT];
       } else {
-        d = bo[2 + r]; ang = an[1 + r]; tor = to[r];
+        d = bo[a.off_b + r]; ang = an[a.off_a + r]; tor = to[r];
+      }
+      if (a.marg) {
+        float l0, l1, l2;
+        cdf_inverse(a.marg[a.off_b + r], a.clamp, d, d, l0);
+        cdf_inverse(a.marg[nb + a.off_a + r], a.clamp, ang, ang, l1);
+        cdf_inverse(a.marg[nb + na + r], a.clamp, tor, tor, l2);
+        dl += l0 + l1 + l2;
       }
       if (a.normalize) {
         ang *= PI_F;
@@ -200,23 +230,13 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
 constexpr int FS = 32;        // samples per CTA (from_xyz)
 constexpr int LDF = FS + 1;
 
-template <typename F>
-__device__ __forceinline__ void walk_block_f(int t, int W, int rows, F&& body) {
-  int m = t / W, c = t - m * W;
-  const int dm = BT / W, dc = BT - dm * W;
-  while (m < rows) {
-    body(m, c);
-    m += dm; c += dc;
-    if (c >= W) { c -= W; ++m; }
-  }
-}
-
 template <bool SMEM>
 __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
   extern __shared__ float sm[];
   const int t = threadIdx.x;
-  const int N = a.n_atoms, nb = N - 1, na = N - 2, nt = N - 3;
+  const int N = a.n_atoms, nb = a.nb, na = a.na, nt = a.nt;
   const int W = 3 * N;
+  const bool global = a.kind == IC_GLOBAL;
   const int spb = SMEM ? FS : BT;                    // samples per CTA
   const long long row0 = (long long)blockIdx.x * spb;
   const int s_loc = SMEM ? (t >> 2) : t, g = SMEM ? (t & 3) : 0, ng = SMEM ? 4 : 1;
@@ -260,14 +280,51 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
         ang *= (1.f / PI_F);
         tor = (tor + PI_F) * (1.f / TWO_PI_F);
       }
-      if (SMEM) {
-        Qs[(2 + r) * LDF] = n12; Qs[(nb + 1 + r) * LDF] = ang; Qs[(nb + na + r) * LDF] = tor;
-      } else {
-        bo[2 + r] = n12; an[1 + r] = ang; to[r] = tor;
-      }
       dl -= __logf(n12 * n12 * sqrtf(sin2));     // 2 ln b + ln sin a
+      float ob = n12;
+      if (a.marg) {
+        float l0, l1, l2;
+        cdf_forward(a.marg[a.off_b + r], a.clamp, ob, ob, l0);
+        cdf_forward(a.marg[nb + a.off_a + r], a.clamp, ang, ang, l1);
+        cdf_forward(a.marg[nb + na + r], a.clamp, tor, tor, l2);
+        dl += l0 + l1 + l2;
+      }
+      if (SMEM) {
+        Qs[(a.off_b + r) * LDF] = ob; Qs[(nb + a.off_a + r) * LDF] = ang; Qs[(nb + na + r) * LDF] = tor;
+      } else {
+        bo[a.off_b + r] = ob; an[a.off_a + r] = ang; to[r] = tor;
+      }
     }
-    if (g == ng - 1) {
+    if (g == ng - 1 && !global) {
+      // fixed block (ic.py:419) and, for the mixed transform, its whitening (pca.py:83-91)
+      const int nf3 = 3 * a.n_fixed;
+      float* fo = a.fixed_out + row * a.fixed_w;
+      float* Qf = Qs + (nb + na + nt) * LDF;
+      if (a.keep == 0) {
+        for (int i = 0; i < a.n_fixed; ++i) {
+          const V3 p = pos.get(a.fixed[i]);
+          if (SMEM) { Qf[(3 * i) * LDF] = p.x; Qf[(3 * i + 1) * LDF] = p.y; Qf[(3 * i + 2) * LDF] = p.z; }
+          else { fo[3 * i] = p.x; fo[3 * i + 1] = p.y; fo[3 * i + 2] = p.z; }
+        }
+      } else {
+        for (int k = 0; k < a.keep; ++k) {
+          float acc = 0.f;
+          for (int i = 0; i < a.n_fixed; ++i) {
+            const V3 p = pos.get(a.fixed[i]);
+            const float* tw = a.whiten + (long long)(3 * i) * a.keep + k;
+            acc = fmaf(p.x - __ldg(a.mean + 3 * i), __ldg(tw), acc);
+            acc = fmaf(p.y - __ldg(a.mean + 3 * i + 1), __ldg(tw + a.keep), acc);
+            acc = fmaf(p.z - __ldg(a.mean + 3 * i + 2), __ldg(tw + 2 * a.keep), acc);
+          }
+          if (SMEM) Qf[k * LDF] = acc;
+          else fo[k] = acc;
+        }
+        dl += a.ld_whiten;
+      }
+      (void)nf3;
+      if (a.normalize) dl -= (float)((double)na * 1.1447298858494002 + (double)nt * 1.8378770664093453);
+    }
+    if (g == ng - 1 && global) {
       const V3 p0 = pos.get(a.s0), p1 = pos.get(a.s1), p2 = pos.get(a.s2);
       const V3 e01 = p1 - p0, e12 = p2 - p1;
       const float d01 = norm_c(e01, a.eps), d12 = norm_c(e12, a.eps);
@@ -293,10 +350,18 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
         gamma = (gamma + PI_F) * (1.f / TWO_PI_F);
         dl -= (float)((double)na * 1.1447298858494002 + (double)(nt + 2) * 1.8378770664093453);
       }
+      float o01 = d01, o12 = d12;
+      if (a.marg) {
+        float l0, l1, l2;
+        cdf_forward(a.marg[0], a.clamp, o01, o01, l0);
+        cdf_forward(a.marg[1], a.clamp, o12, o12, l1);
+        cdf_forward(a.marg[nb], a.clamp, a012, a012, l2);
+        dl += l0 + l1 + l2;
+      }
       if (SMEM) {
-        Qs[0] = d01; Qs[LDF] = d12; Qs[nb * LDF] = a012;
+        Qs[0] = o01; Qs[LDF] = o12; Qs[nb * LDF] = a012;
       } else {
-        bo[0] = d01; bo[1] = d12; an[0] = a012;
+        bo[0] = o01; bo[1] = o12; an[0] = a012;
       }
       a.o_x0[row * 3 + 0] = p0.x;
       a.o_x0[row * 3 + 1] = p0.y;
@@ -320,6 +385,11 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
     walk_block_f(t, nb, nrow, [&](int m, int c) { gb[m * nb + c] = Qb[c * LDF + m]; });
     walk_block_f(t, na, nrow, [&](int m, int c) { ga[m * na + c] = Qb[(nb + c) * LDF + m]; });
     walk_block_f(t, nt, nrow, [&](int m, int c) { gt[m * nt + c] = Qb[(nb + na + c) * LDF + m]; });
+    if (!global) {
+      const int wf = a.fixed_w;
+      float* gf = a.fixed_out + row0 * wf;
+      walk_block_f(t, wf, nrow, [&](int m, int c) { gf[m * wf + c] = Qb[(nb + na + nt + c) * LDF + m]; });
+    }
   }
 }
 
@@ -327,8 +397,11 @@ static int fill_plan(const bgx_zplan* plan, long long batch, IcArgs& a) {
   if (!plan || plan->n_atoms < 4 || plan->n_rel != plan->n_atoms - 3 || !plan->rel || !plan->order || batch < 0)
     return BGX_ERR_INVALID;
   a.B = batch;
+  a.kind = IC_GLOBAL;
   a.n_atoms = plan->n_atoms;
   a.n_rel = plan->n_rel;
+  a.nb = plan->n_atoms - 1; a.na = plan->n_atoms - 2; a.nt = plan->n_atoms - 3;
+  a.off_b = 2; a.off_a = 1;
   a.s0 = plan->seeds[0]; a.s1 = plan->seeds[1]; a.s2 = plan->seeds[2];
   a.rel = plan->rel;
   a.order = plan->order;
@@ -341,13 +414,41 @@ static int fill_plan(const bgx_zplan* plan, long long batch, IcArgs& a) {
   return BGX_OK;
 }
 
+static int fill_relplan(const bgx_relplan* plan, long long batch, IcArgs& a) {
+  if (!plan || plan->n_fixed < 3 || plan->n_rel < 1 || plan->n_atoms != plan->n_fixed + plan->n_rel || !plan->fixed ||
+      !plan->rel || !plan->order || batch < 0 || plan->keepdims < 0 || plan->keepdims > 3 * plan->n_fixed)
+    return BGX_ERR_INVALID;
+  if (plan->keepdims > 0 && (!plan->mean || !plan->blacken || !plan->whiten)) return BGX_ERR_INVALID;
+  a.B = batch;
+  a.kind = IC_RELATIVE;
+  a.n_atoms = plan->n_atoms;
+  a.n_rel = plan->n_rel;
+  a.nb = a.na = a.nt = plan->n_rel;
+  a.off_b = a.off_a = 0;
+  a.n_fixed = plan->n_fixed;
+  a.keep = plan->keepdims;
+  a.fixed_w = plan->keepdims ? plan->keepdims : 3 * plan->n_fixed;
+  a.fixed = plan->fixed;
+  a.mean = plan->mean; a.blacken = plan->blacken; a.whiten = plan->whiten;
+  a.ld_whiten = plan->log_det_whiten;
+  a.rel = plan->rel;
+  a.order = plan->order;
+  a.normalize = plan->normalize_angles;
+  a.eps = plan->eps;
+  a.eps2 = plan->eps * plan->eps;
+  a.slot_of_col = nullptr;
+  a.cmin = (float)(-1.0 + (double)plan->eps);
+  a.cmax = (float)(1.0 - (double)plan->eps);
+  return BGX_OK;
+}
+
 template <typename KS, typename KG>
 static int launch_ic(KS ksm, KG kgl, const IcArgs& a, int extra_cols, int samples_per_cta, cudaStream_t st) {
   if (a.B == 0) return BGX_OK;
   long long grid = (a.B + BT - 1) / BT;
   if (grid > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
   size_t sb = sizeof(float) * (size_t)(3 * a.n_atoms + extra_cols) * (samples_per_cta + 1);
-  if (!a.slot_of_col) sb = (size_t)1 << 30;      // plans without a slot map use the global-memory path
+  if (a.kind == IC_GLOBAL && !a.slot_of_col) sb = (size_t)1 << 30;   // plans without a slot map: global-memory path
   if (sb <= 200 * 1024) {
     if (sb > 48 * 1024) {  // (both kernels share this instantiation: no static cache here)
       int rc = check(cudaFuncSetAttribute(ksm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
@@ -380,6 +481,35 @@ extern "C" int bgx_ic_to_xyz(const bgx_zplan* plan, int64_t batch, const float* 
   return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, 0, BT, (cudaStream_t)stream);
 }
 
+extern "C" int bgx_ic_to_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* marginals, float clamp_lo,
+                                    float clamp_hi, float logdet_min, int64_t batch, const float* bonds,
+                                    const float* angles, const float* torsions, const float* x0, int32_t x0_stride,
+                                    const float* R, int32_t r_stride, float* xyz, const float* dlogp_in,
+                                    float* dlogp_out, void* stream) {
+  IcArgs a{};
+  int rc = fill_plan(plan, batch, a);
+  if (rc) return rc;
+  if (!marginals || !bonds || !angles || !torsions || !x0 || !R || !xyz || !dlogp_out) return BGX_ERR_INVALID;
+  a.marg = marginals;
+  a.clamp = {clamp_lo, clamp_hi, logdet_min};
+  a.bonds = bonds; a.angles = angles; a.torsions = torsions;
+  a.x0 = x0; a.R = R; a.x0_stride = x0_stride; a.r_stride = r_stride;
+  a.xyz = xyz; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
+  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, 0, BT, (cudaStream_t)stream);
+}
+
+extern "C" int bgx_relic_to_xyz(const bgx_relplan* plan, int64_t batch, const float* bonds, const float* angles,
+                                const float* torsions, const float* fixed, float* xyz, const float* dlogp_in,
+                                float* dlogp_out, void* stream) {
+  IcArgs a{};
+  int rc = fill_relplan(plan, batch, a);
+  if (rc) return rc;
+  if (!bonds || !angles || !torsions || !fixed || !xyz || !dlogp_out) return BGX_ERR_INVALID;
+  a.bonds = bonds; a.angles = angles; a.torsions = torsions; a.fixed_in = fixed;
+  a.xyz = xyz; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
+  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, a.keep, BT, (cudaStream_t)stream);
+}
+
 extern "C" int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, float* bonds,
                                float* angles, float* torsions, float* x0, float* R, const float* dlogp_in,
                                float* dlogp_out, void* stream) {
@@ -390,4 +520,32 @@ extern "C" int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float
   a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions;
   a.o_x0 = x0; a.o_R = R; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
   return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_atoms - 6, FS, (cudaStream_t)stream);
+}
+
+extern "C" int bgx_ic_from_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* marginals, float clamp_lo,
+                                      float clamp_hi, float logdet_min, int64_t batch, const float* xyz, float* bonds,
+                                      float* angles, float* torsions, float* x0, float* R, const float* dlogp_in,
+                                      float* dlogp_out, void* stream) {
+  IcArgs a{};
+  int rc = fill_plan(plan, batch, a);
+  if (rc) return rc;
+  if (!marginals || !xyz || !bonds || !angles || !torsions || !x0 || !R || !dlogp_out) return BGX_ERR_INVALID;
+  a.marg = marginals;
+  a.clamp = {clamp_lo, clamp_hi, logdet_min};
+  a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions;
+  a.o_x0 = x0; a.o_R = R; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
+  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_atoms - 6, FS, (cudaStream_t)stream);
+}
+
+extern "C" int bgx_relic_from_xyz(const bgx_relplan* plan, int64_t batch, const float* xyz, float* bonds,
+                                  float* angles, float* torsions, float* fixed, const float* dlogp_in,
+                                  float* dlogp_out, void* stream) {
+  IcArgs a{};
+  int rc = fill_relplan(plan, batch, a);
+  if (rc) return rc;
+  if (!xyz || !bonds || !angles || !torsions || !fixed || !dlogp_out) return BGX_ERR_INVALID;
+  a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions; a.fixed_out = fixed;
+  a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
+  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_rel + a.fixed_w, FS,
+                   (cudaStream_t)stream);
 }

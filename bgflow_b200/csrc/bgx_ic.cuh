@@ -1,0 +1,61 @@
+// Geometry helpers shared by the internal-coordinate kernels (bgx_ic.cu: global z-matrix,
+// bgx_ic_rel.cu: relative / mixed transforms).
+#pragma once
+#include "bgx_common.cuh"
+
+namespace bgx {
+
+constexpr int BT = 128;       // samples (threads) per CTA
+constexpr int LDT = BT + 1;
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr float TWO_PI_F = 6.28318530717958647692f;
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float norm_c(V3 a, float eps) { return fmaxf(sqrtf(dot(a, a)), eps); }
+// 1 / max(|a|, eps) with one MUFU.RSQ (eps^2 = 1e-14 is representable)
+__device__ __forceinline__ float inv_norm_c(V3 a, float eps2) { return rsqrtf(fmaxf(dot(a, a), eps2)); }
+
+template <bool SMEM>
+struct PosStore {
+  float* base;
+  long long stride_c;  // distance between consecutive coordinates
+  __device__ __forceinline__ V3 get(int atom) const {
+    const float* p = base + (long long)(3 * atom) * stride_c;
+    return {p[0], p[stride_c], p[2 * stride_c]};
+  }
+  __device__ __forceinline__ void set(int atom, V3 v) const {
+    float* p = base + (long long)(3 * atom) * stride_c;
+    p[0] = v.x;
+    p[stride_c] = v.y;
+    p[2 * stride_c] = v.z;
+  }
+};
+
+// division-free walk of thread t over the elements e = t, t+BT, ... of a [rows x W] block
+template <typename F>
+__device__ __forceinline__ void walk_block(int t, int W, int rows, F&& body) {
+  int m = t / W, c = t - m * W;
+  const int dm = BT / W, dc = BT - dm * W;
+  while (m < rows) {
+    body(m, c);
+    m += dm; c += dc;
+    if (c >= W) { c -= W; ++m; }
+  }
+}
+
+// same walk for kernels whose CTA covers fewer samples than threads
+template <typename F>
+__device__ __forceinline__ void walk_block_f(int t, int W, int rows, F&& body) {
+  walk_block(t, W, rows, body);
+}
+
+}  // namespace bgx

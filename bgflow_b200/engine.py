@@ -13,7 +13,8 @@ import torch
 from . import _lib
 
 __all__ = ["PackedNet", "affine_coupling", "spline_coupling", "ic_to_xyz", "ic_from_xyz", "ZPlan",
-           "require_cuda_fp32", "config", "pipeline_status", "check_pipeline_status"]
+           "require_cuda_fp32", "config", "pipeline_status", "check_pipeline_status", "CdfTable", "cdf_map",
+           "ic_to_xyz_mapped", "ic_from_xyz_mapped", "RelPlan", "relic_to_xyz", "relic_from_xyz"]
 
 
 def require_cuda_fp32(*tensors):
@@ -396,3 +397,263 @@ def ic_from_xyz(plan, xyz, dlogp_in=None):
                              din.data_ptr() if din is not None else None, dlogp.data_ptr(), _stream())
     _lib.check(rc, "bgx_ic_from_xyz")
     return bonds, angles, torsions, x0, R, dlogp
+
+
+# ------------------------------------------------------------------------------------------------
+# IC-domain CDF maps (bgx_cdf_map) and the fused builder tail (bgx_ic_*_mapped)
+# ------------------------------------------------------------------------------------------------
+
+def _clamp_args(eps):
+    """CDFTransform's eps (cdf.py:22-27) as the three kernel scalars."""
+    if eps is None:
+        return 0.0, 1.0, float("-inf")
+    return float(np.float32(eps)), float(np.float32(1.0 - eps)), -1.0 / eps
+
+
+class CdfTable:
+    """Device table of ``bgx_cdf_col`` entries, one per tensor column.
+
+    ``columns``: sequence of ``(kind, a, b, lower, upper)`` with kind in
+    ``_lib.DIST_NONE / DIST_NORMAL / DIST_TRUNCNORMAL / DIST_UNIFORM`` (see ``bgx_cdf_col_init``)."""
+
+    def __init__(self, columns):
+        lib = _lib.load()
+        self.n = len(columns)
+        arr = (_lib.bgx_cdf_col * max(self.n, 1))()
+        for i, (kind, a, b, lower, upper) in enumerate(columns):
+            rc = lib.bgx_cdf_col_init(int(kind), float(a), float(b), float(lower), float(upper), C.byref(arr[i]))
+            if rc != 0:
+                raise ValueError(f"invalid marginal for column {i}: kind={kind}, a={a}, b={b}, "
+                                 f"lower={lower}, upper={upper}")
+        self._host = torch.from_numpy(np.frombuffer(arr, dtype=np.uint8).copy())
+        self._dev = {}
+
+    def device(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = self._host.to(device)
+        return self._dev[key]
+
+    @staticmethod
+    def concat(tables):
+        out = CdfTable([])
+        out.n = sum(t.n for t in tables)
+        out._host = torch.cat([t._host[:t.n * C.sizeof(_lib.bgx_cdf_col)] for t in tables])
+        return out
+
+
+def cdf_map(tensors, table, inverse=False, eps=1e-7, dlogp_in=None):
+    """Map a list of ``[B, w_i]`` tensors through their per-column CDFs (``inverse``: icdfs) in one
+    launch.  Returns (list of mapped tensors, dlogp ``[..., 1]``)."""
+    lib = _lib.load()
+    if not 1 <= len(tensors) <= _lib.BGX_MAX_SEGS:
+        raise NotImplementedError(f"1..{_lib.BGX_MAX_SEGS} tensors per CDF-map launch")
+    require_cuda_fp32(*tensors)
+    batch_shape = tensors[0].shape[:-1]
+    rows = [_as_rows(t) for t in tensors]
+    B = rows[0].shape[0]
+    if any(t.shape[0] != B for t in rows):
+        raise ValueError("all tensors of a CDF map must share their batch shape")
+    if sum(t.shape[1] for t in rows) != table.n:
+        raise ValueError(f"CDF table has {table.n} columns, tensors have {sum(t.shape[1] for t in rows)}")
+    outs = [torch.empty(B, t.shape[1], dtype=torch.float32, device=t.device) for t in rows]
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=rows[0].device)
+    segs_in = (_lib.bgx_seg * _lib.BGX_MAX_SEGS)()
+    segs_out = (_lib.bgx_seg * _lib.BGX_MAX_SEGS)()
+    for i, (t, o) in enumerate(zip(rows, outs)):
+        w = t.shape[1]
+        segs_in[i].ptr, segs_in[i].width, segs_in[i].stride = t.data_ptr(), w, t.stride(0) if B > 1 else w
+        segs_out[i].ptr, segs_out[i].width, segs_out[i].stride = o.data_ptr(), w, w
+    din = None
+    if dlogp_in is not None:
+        require_cuda_fp32(dlogp_in)
+        din = dlogp_in.reshape(-1).contiguous()
+        if din.shape[0] != B:
+            raise ValueError("dlogp accumulator has the wrong batch size")
+    if B > 0:
+        lo, hi, ldmin = _clamp_args(eps)
+        cols = table.device(rows[0].device)
+        rc = lib.bgx_cdf_map(B, len(rows), segs_in, segs_out, C.c_void_p(cols.data_ptr()), lo, hi, ldmin,
+                             _lib.FLAG_INVERSE if inverse else 0,
+                             din.data_ptr() if din is not None else None, dlogp.data_ptr(), _stream())
+        _lib.check(rc, "bgx_cdf_map")
+    outs = [o.reshape(*batch_shape, o.shape[1]) if len(batch_shape) != 1 else o for o in outs]
+    return outs, dlogp.reshape(*batch_shape, 1)
+
+
+def ic_to_xyz_mapped(plan, table, eps, bonds, angles, torsions, x0, R, dlogp_in=None):
+    """icdf maps of (bonds | angles | torsions) + IC -> Cartesian in one kernel."""
+    lib = _lib.load()
+    require_cuda_fp32(bonds, angles, torsions, x0, R)
+    n = plan.n_atoms
+    B = bonds.shape[0]
+    if bonds.shape != (B, n - 1) or angles.shape != (B, n - 2) or torsions.shape != (B, n - 3):
+        raise ValueError("bonds/angles/torsions must be [B, N-1], [B, N-2], [B, N-3]")
+    if table.n != 3 * n - 6:
+        raise ValueError(f"CDF table must have {3 * n - 6} columns (bonds | angles | torsions)")
+    bonds, angles, torsions = bonds.contiguous(), angles.contiguous(), torsions.contiguous()
+    x0f = x0.reshape(-1, 3).contiguous()
+    Rf = R.reshape(-1, 3).contiguous()
+    if x0f.shape[0] not in (1, B) or Rf.shape[0] not in (1, B):
+        raise ValueError("x0 must be [B,1,3] (or [1,3]) and R [B,3]")
+    xyz = torch.empty(B, 3 * n, dtype=torch.float32, device=bonds.device)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
+    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    if B == 0:
+        return xyz, dlogp
+    lo, hi, ldmin = _clamp_args(eps)
+    cols = table.device(bonds.device)
+    rc = lib.bgx_ic_to_xyz_mapped(C.byref(plan.device_plan(bonds.device)), C.c_void_p(cols.data_ptr()), lo, hi, ldmin,
+                                  B, bonds.data_ptr(), angles.data_ptr(), torsions.data_ptr(), x0f.data_ptr(),
+                                  3 if x0f.shape[0] == B else 0, Rf.data_ptr(), 3 if Rf.shape[0] == B else 0,
+                                  xyz.data_ptr(), din.data_ptr() if din is not None else None, dlogp.data_ptr(),
+                                  _stream())
+    _lib.check(rc, "bgx_ic_to_xyz_mapped")
+    return xyz, dlogp
+
+
+def ic_from_xyz_mapped(plan, table, eps, xyz, dlogp_in=None):
+    """Cartesian -> IC + cdf maps of every IC column in one kernel."""
+    lib = _lib.load()
+    require_cuda_fp32(xyz)
+    n = plan.n_atoms
+    B = xyz.shape[0]
+    x = xyz.reshape(B, -1).contiguous()
+    if x.shape[1] != 3 * n:
+        raise ValueError(f"xyz must have {3 * n} coordinates per sample")
+    if table.n != 3 * n - 6:
+        raise ValueError(f"CDF table must have {3 * n - 6} columns (bonds | angles | torsions)")
+    dev = x.device
+    bonds = torch.empty(B, n - 1, dtype=torch.float32, device=dev)
+    angles = torch.empty(B, n - 2, dtype=torch.float32, device=dev)
+    torsions = torch.empty(B, n - 3, dtype=torch.float32, device=dev)
+    x0 = torch.empty(B, 1, 3, dtype=torch.float32, device=dev)
+    R = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
+    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    if B == 0:
+        return bonds, angles, torsions, x0, R, dlogp
+    lo, hi, ldmin = _clamp_args(eps)
+    cols = table.device(dev)
+    rc = lib.bgx_ic_from_xyz_mapped(C.byref(plan.device_plan(dev)), C.c_void_p(cols.data_ptr()), lo, hi, ldmin, B,
+                                    x.data_ptr(), bonds.data_ptr(), angles.data_ptr(), torsions.data_ptr(),
+                                    x0.data_ptr(), R.data_ptr(), din.data_ptr() if din is not None else None,
+                                    dlogp.data_ptr(), _stream())
+    _lib.check(rc, "bgx_ic_from_xyz_mapped")
+    return bonds, angles, torsions, x0, R, dlogp
+
+
+# ------------------------------------------------------------------------------------------------
+# relative / mixed internal coordinates (bgx_relic_*)
+# ------------------------------------------------------------------------------------------------
+
+class RelPlan:
+    """Host staging of a relative z-matrix (ic.py:25-91 with fixed atoms) + optional static
+    whitening of the fixed block (pca.py:10-34), and their device copies."""
+
+    def __init__(self, z_matrix, fixed_atoms, normalize_angles=True, eps=1e-7, whitening=None):
+        z = np.asarray(z_matrix, dtype=np.int64)
+        fixed = np.asarray(fixed_atoms, dtype=np.int64).reshape(-1)
+        if z.ndim != 2 or z.shape[1] != 4:
+            raise ValueError("z_matrix must have shape (n_conditioned, 4)")
+        if (z < 0).any():
+            raise ValueError("a relative z-matrix has no undefined (-1) references")
+        n_atoms = len(z) + len(fixed)
+        if sorted(z[:, 0].tolist() + fixed.tolist()) != list(range(n_atoms)):
+            raise ValueError("z-matrix rows and fixed atoms must cover every atom exactly once")
+        placed = np.zeros(n_atoms, dtype=bool)
+        placed[fixed] = True
+        todo = list(range(len(z)))
+        order = []
+        while todo:
+            ready = [r for r in todo if placed[z[r, 1:]].all()]
+            if not ready:
+                raise ValueError(
+                    "Z-matrix decomposition failed. The following atoms were not reachable from "
+                    f"the fixed atoms: \n{z[todo, 0]}")
+            order.extend(ready)
+            placed[z[ready, 0]] = True
+            ready_set = set(ready)
+            todo = [r for r in todo if r not in ready_set]
+        self.rel, self.fixed, self.order, self.n_atoms = z, fixed, order, n_atoms
+        self.seeds = [int(a) for a in fixed]          # "already placed" atoms for the torch backward definition
+        self.normalize_angles = bool(normalize_angles)
+        self.eps = float(eps)
+        self.whitening = whitening                    # None or dict(mean, whiten, blacken, jacobian_xz, keepdims)
+        self._dev = {}
+
+    @property
+    def keepdims(self):
+        return 0 if self.whitening is None else int(self.whitening["keepdims"])
+
+    @property
+    def fixed_width(self):
+        return self.keepdims if self.whitening is not None else 3 * len(self.fixed)
+
+    def device_plan(self, device):
+        key = str(device)
+        if key not in self._dev:
+            as_i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+            rel, fixed, order = as_i32(self.rel), as_i32(self.fixed), as_i32(self.order)
+            plan = _lib.bgx_relplan()
+            plan.n_atoms, plan.n_fixed, plan.n_rel = self.n_atoms, len(self.fixed), len(self.rel)
+            plan.fixed, plan.rel, plan.order = fixed.data_ptr(), rel.data_ptr(), order.data_ptr()
+            plan.normalize_angles = 1 if self.normalize_angles else 0
+            plan.eps = self.eps
+            keep = [rel, fixed, order]
+            if self.whitening is not None:
+                w = self.whitening
+                as_f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+                mean, blacken, whiten = as_f32(w["mean"]), as_f32(w["blacken"]), as_f32(w["whiten"])
+                plan.keepdims = int(w["keepdims"])
+                plan.mean, plan.blacken, plan.whiten = mean.data_ptr(), blacken.data_ptr(), whiten.data_ptr()
+                plan.log_det_whiten = float(w["jacobian_xz"])
+                keep += [mean, blacken, whiten]
+            self._dev[key] = (plan, keep)
+        return self._dev[key][0]
+
+
+def relic_to_xyz(plan, bonds, angles, torsions, fixed, dlogp_in=None):
+    lib = _lib.load()
+    require_cuda_fp32(bonds, angles, torsions, fixed)
+    n_rel = len(plan.rel)
+    B = bonds.shape[0]
+    fixed2 = fixed.reshape(B, -1).contiguous()
+    if bonds.shape != (B, n_rel) or angles.shape != (B, n_rel) or torsions.shape != (B, n_rel):
+        raise ValueError("bonds/angles/torsions must be [B, n_conditioned]")
+    if fixed2.shape[1] != plan.fixed_width:
+        raise ValueError(f"the fixed block must have {plan.fixed_width} columns")
+    bonds, angles, torsions = bonds.contiguous(), angles.contiguous(), torsions.contiguous()
+    xyz = torch.empty(B, 3 * plan.n_atoms, dtype=torch.float32, device=bonds.device)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
+    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    if B == 0:
+        return xyz, dlogp
+    rc = lib.bgx_relic_to_xyz(C.byref(plan.device_plan(bonds.device)), B, bonds.data_ptr(), angles.data_ptr(),
+                              torsions.data_ptr(), fixed2.data_ptr(), xyz.data_ptr(),
+                              din.data_ptr() if din is not None else None, dlogp.data_ptr(), _stream())
+    _lib.check(rc, "bgx_relic_to_xyz")
+    return xyz, dlogp
+
+
+def relic_from_xyz(plan, xyz, dlogp_in=None):
+    lib = _lib.load()
+    require_cuda_fp32(xyz)
+    B = xyz.shape[0]
+    x = xyz.reshape(B, -1).contiguous()
+    if x.shape[1] != 3 * plan.n_atoms:
+        raise ValueError(f"xyz must have {3 * plan.n_atoms} coordinates per sample")
+    dev, n_rel = x.device, len(plan.rel)
+    bonds = torch.empty(B, n_rel, dtype=torch.float32, device=dev)
+    angles = torch.empty(B, n_rel, dtype=torch.float32, device=dev)
+    torsions = torch.empty(B, n_rel, dtype=torch.float32, device=dev)
+    fixed = torch.empty(B, plan.fixed_width, dtype=torch.float32, device=dev)
+    dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
+    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    if B == 0:
+        return bonds, angles, torsions, fixed, dlogp
+    rc = lib.bgx_relic_from_xyz(C.byref(plan.device_plan(dev)), B, x.data_ptr(), bonds.data_ptr(), angles.data_ptr(),
+                                torsions.data_ptr(), fixed.data_ptr(), din.data_ptr() if din is not None else None,
+                                dlogp.data_ptr(), _stream())
+    _lib.check(rc, "bgx_relic_from_xyz")
+    return bonds, angles, torsions, fixed, dlogp

@@ -279,6 +279,8 @@ class WrapFlow(Flow):
         self._flow = flow
         self._indices = indices
         self._out_indices = indices if out_indices is None else out_indices
+        # a wrapped kernel-backed flow still adds its log-det onto the running dlogp in-kernel
+        self._accumulates_dlogp = getattr(flow, "_accumulates_dlogp", False)
 
     @staticmethod
     def _route(xs, take, put, run):

@@ -17,7 +17,8 @@ from . import autograd as _ag
 from . import engine
 from .flows import Flow
 
-__all__ = ["GlobalInternalCoordinateTransformation"]
+__all__ = ["GlobalInternalCoordinateTransformation", "RelativeInternalCoordinateTransformation",
+           "MixedCoordinateTransformation", "WhitenFlow"]
 
 
 class GlobalInternalCoordinateTransformation(Flow):
@@ -99,3 +100,117 @@ class GlobalInternalCoordinateTransformation(Flow):
             R = R.reshape(-1, 3).expand(B, 3)
             return _ag.ic_to_xyz_with_grad(self._plan, engine.ic_to_xyz, bonds, angles, torsions, x0, R)
         return engine.ic_to_xyz(self._plan, *ins)
+
+
+class RelativeInternalCoordinateTransformation(Flow):
+    """Internal coordinates relative to a block of fixed atoms (ic.py:268-513): ``_forward`` maps
+    xyz ``[B, 3N]`` -> (bonds, angles, torsions ``[B, n]``, x_fixed ``[B, 3 n_fixed]``, dlogp),
+    ``_inverse`` maps back.  One kernel per call (``bgx_relic_from_xyz`` / ``bgx_relic_to_xyz``)."""
+
+    _accumulates_dlogp = False
+
+    def __init__(self, z_matrix, fixed_atoms, normalize_angles=True, eps: float = 1e-7,
+                 enforce_boundaries: bool = True, raise_warnings: bool = True, _whitening=None):
+        super().__init__()
+        if isinstance(z_matrix, torch.Tensor):
+            z_matrix = z_matrix.cpu().numpy()
+        if isinstance(fixed_atoms, torch.Tensor):
+            fixed_atoms = fixed_atoms.cpu().numpy()
+        if not enforce_boundaries:
+            raise NotImplementedError("the IC kernels always enforce the eps boundaries")
+        self._plan = engine.RelPlan(z_matrix, fixed_atoms, normalize_angles=normalize_angles, eps=eps,
+                                    whitening=_whitening)
+        self._raise_warnings = raise_warnings
+
+    z_matrix = property(lambda self: self._plan.rel)
+    fixed_atoms = property(lambda self: self._plan.fixed)
+    dim_bonds = property(lambda self: len(self._plan.rel))
+    dim_angles = property(lambda self: len(self._plan.rel))
+    dim_torsions = property(lambda self: len(self._plan.rel))
+    dim_fixed = property(lambda self: 3 * len(self._plan.fixed))
+    bond_indices = property(lambda self: self._plan.rel[:, :2])
+    angle_indices = property(lambda self: self._plan.rel[:, :3])
+    torsion_indices = property(lambda self: self._plan.rel[:, :4])
+    normalize_angles = property(lambda self: self._plan.normalize_angles)
+
+    def _forward(self, x, *args, **kwargs):
+        x = x.reshape(x.shape[0], -1)
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _ag.relic_from_xyz_with_grad(self._plan, engine.relic_from_xyz, x)
+        return engine.relic_from_xyz(self._plan, x)
+
+    def _inverse(self, bonds, angles, torsions, x_fixed, *args, **kwargs):
+        x_fixed = x_fixed.reshape(x_fixed.shape[0], -1)
+        ins = (bonds, angles, torsions, x_fixed)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in ins):
+            return _ag.relic_to_xyz_with_grad(self._plan, engine.relic_to_xyz, *ins)
+        return engine.relic_to_xyz(self._plan, *ins)
+
+
+def _pca(x0, keepdims):
+    """crd_transform/pca.py:10-34 (numpy, in the dtype of the data)."""
+    mean = x0.mean(axis=0)
+    xm = x0 - mean
+    cov = np.matmul(xm.T, xm) / (xm.shape[0] - 1.0)
+    eigval, eigvec = np.linalg.eigh(cov)
+    idx = np.argsort(eigval)[::-1][:keepdims]
+    std = np.sqrt(eigval[idx])
+    eigvec = eigvec[:, idx]
+    return mean, np.matmul(eigvec, np.diag(1.0 / std)), np.matmul(np.diag(std), eigvec.T), std
+
+
+class WhitenFlow(Flow):
+    """Static PCA whitening (crd_transform/pca.py:37-107).  A plain ``[B, d] x [d, k]`` library GEMM
+    when used on its own; inside ``MixedCoordinateTransformation`` it is part of the IC kernels."""
+
+    def __init__(self, X0, keepdims=None, whiten_inverse=True):
+        super().__init__()
+        if keepdims is None:
+            keepdims = X0.shape[1]
+        self.dim = X0.shape[1]
+        self.keepdims = keepdims
+        self.whiten_inverse = whiten_inverse
+        mean, tw, tb, std = _pca(X0.detach().cpu().numpy(), keepdims)
+        self.register_buffer("X0mean", torch.tensor(mean).to(X0))
+        self.register_buffer("Twhiten", torch.tensor(tw).to(X0))
+        self.register_buffer("Tblacken", torch.tensor(tb).to(X0))
+        self.register_buffer("std", torch.tensor(std).to(X0))
+        if torch.any(self.std <= 0):
+            raise ValueError("Cannot construct whiten layer because trying to keep nonpositive eigenvalues.")
+        self.jacobian_xz = -torch.sum(torch.log(self.std))
+
+    def _whiten(self, x):
+        return torch.matmul(x - self.X0mean, self.Twhiten), self.jacobian_xz * torch.ones((x.shape[0], 1)).to(x)
+
+    def _blacken(self, x):
+        return torch.matmul(x, self.Tblacken) + self.X0mean, -self.jacobian_xz * torch.ones((x.shape[0], 1)).to(x)
+
+    def _forward(self, x, *args, **kwargs):
+        return self._blacken(x) if self.whiten_inverse else self._whiten(x)
+
+    def _inverse(self, x, *args, **kwargs):
+        return self._whiten(x) if self.whiten_inverse else self._blacken(x)
+
+
+class MixedCoordinateTransformation(RelativeInternalCoordinateTransformation):
+    """Relative internal coordinates + PCA-whitened fixed block (ic.py:719-884): ``_forward`` maps
+    xyz -> (bonds, angles, torsions, z_fixed ``[B, keepdims]``, dlogp).  The whitening GEMV runs inside
+    the IC kernels; the PCA itself is host work done once here, in the dtype of ``data`` like the
+    reference (pca.py:61-62)."""
+
+    def __init__(self, data, z_matrix, fixed_atoms, keepdims=None, normalize_angles=True, eps: float = 1e-7,
+                 enforce_boundaries: bool = True, raise_warnings: bool = True):
+        if isinstance(fixed_atoms, torch.Tensor):
+            fixed_atoms = fixed_atoms.cpu().numpy()
+        fixed_atoms = np.asarray(fixed_atoms)
+        n_data = data.shape[0]
+        fixed = data.reshape(n_data, -1, 3)[:, fixed_atoms].reshape(n_data, -1)
+        self_whiten = WhitenFlow(fixed, keepdims=keepdims, whiten_inverse=False)
+        w = dict(mean=self_whiten.X0mean.cpu().numpy(), whiten=self_whiten.Twhiten.cpu().numpy(),
+                 blacken=self_whiten.Tblacken.cpu().numpy(), jacobian_xz=float(self_whiten.jacobian_xz),
+                 keepdims=int(self_whiten.keepdims))
+        super().__init__(z_matrix, fixed_atoms, normalize_angles=normalize_angles, eps=eps,
+                         enforce_boundaries=enforce_boundaries, raise_warnings=raise_warnings, _whitening=w)
+        self._whiten = self_whiten
+
+    dim_fixed = property(lambda self: self._whiten.keepdims)

@@ -17,6 +17,13 @@
  *                                    ic_helper.py:372-452, 480-575)
  *   bgx_ic_from_xyz       replaces  GlobalInternalCoordinateTransformation._forward
  *                                   (ic.py:633-676, 162-206, 386-433, ic_helper.py:148-293, 578-680)
+ *   bgx_cdf_map           replaces  CDFTransform._forward/_inverse (bgflow/nn/flow/cdf.py:29-46) over
+ *                                   TruncatedNormalDistribution / Normal / Uniform marginals
+ *   bgx_ic_to_xyz_mapped  replaces  the builder tail: icdf maps + InverseFlow(GlobalIC)
+ *   bgx_ic_from_xyz_mapped          (factory/generator_builder.py:408-459) in one kernel per direction
+ *   bgx_relic_to_xyz      replaces  RelativeInternalCoordinateTransformation._inverse (ic.py:435-513) and
+ *                                   MixedCoordinateTransformation._inverse (ic.py:862-884, pca.py:83-107)
+ *   bgx_relic_from_xyz    replaces  their _forward (ic.py:386-433, 836-860)
  *   bgx_pack_mlp          (no reference counterpart) re-lays nn.Linear weights for the kernels
  *
  * Conventions: plain pointers and sizes only, no torch types.  All device pointers are fp32,
@@ -186,6 +193,92 @@ int bgx_ic_to_xyz(const bgx_zplan* plan, int64_t batch, const float* bonds, cons
 int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, float* bonds,
                     float* angles, float* torsions, float* x0, float* R, const float* dlogp_in,
                     float* dlogp_out, void* stream);
+
+/* ---- IC-domain maps ------------------------------------------------------- */
+
+/* Column-wise CDF maps: CDFTransform._forward/_inverse (bgflow/nn/flow/cdf.py:29-46) over the
+ * marginals the builder installs with add_map_to_ic_domains (factory/generator_builder.py:443-459,
+ * factory/icmarginals.py:39-77): TruncatedNormalDistribution (bgflow/distribution/normal.py:95-227)
+ * for bonds / angles, (Sloppy)Uniform for torsions, torch.distributions.Normal for fixed /
+ * augmented fields.  One bgx_cdf_col per tensor column. */
+#define BGX_DIST_NONE 0          /* identity column, log-det 0 */
+#define BGX_DIST_NORMAL 1        /* Normal(loc, scale) */
+#define BGX_DIST_TRUNCNORMAL 2   /* Normal(mu, sigma) truncated to [lower, upper] */
+#define BGX_DIST_UNIFORM 3       /* Uniform(low, high) */
+
+typedef struct bgx_cdf_col {
+  int32_t kind;
+  float p[7];   /* filled by bgx_cdf_col_init: loc|low, scale|high-low, Phi(alpha), Z, log-normaliser,
+                   1/scale, high */
+} bgx_cdf_col;
+
+/* Host helper: derive the per-column constants in double precision.
+ *   NORMAL       a = loc, b = scale                     (lower / upper ignored)
+ *   TRUNCNORMAL  a = mu,  b = sigma, lower, upper       (+-INFINITY allowed)
+ *   UNIFORM      a = low, b = high
+ * Returns BGX_ERR_INVALID for scale <= 0, upper <= lower or an unknown kind. */
+int bgx_cdf_col_init(int32_t kind, double a, double b, double lower, double upper, bgx_cdf_col* out);
+
+/* Map `n_seg` tensors of one flow state in ONE launch.  Segment i has in[i].width columns whose
+ * bgx_cdf_col entries follow each other in `cols` (device array, sum of widths entries);
+ * out[i] has the same width (out[i].ptr is written; may alias in[i].ptr).
+ *   flags & BGX_FLAG_INVERSE : u -> x = icdf(clamp(u, clamp_lo, clamp_hi)), log-det = max(-log_prob(x), logdet_min)
+ *                              (CDFTransform._inverse = what InverseFlow(CDFTransform) runs when sampling)
+ *   otherwise                : x -> u = clamp(cdf(x), clamp_lo, clamp_hi), log-det = max(log_prob(x), logdet_min)
+ * The reference's eps = 1e-7 is clamp_lo = (float)eps, clamp_hi = (float)(1 - eps),
+ * logdet_min = -1/eps; eps = None is (0, 1, -INFINITY).
+ * dlogp_out[row] = (dlogp_in ? dlogp_in[row] : 0) + sum over all columns of the log-dets. */
+int bgx_cdf_map(int64_t batch, int32_t n_seg, const bgx_seg* in, const bgx_seg* out,
+                const bgx_cdf_col* cols, float clamp_lo, float clamp_hi, float logdet_min, int flags,
+                const float* dlogp_in, float* dlogp_out, void* stream);
+
+/* bgx_ic_to_xyz with the icdf maps of the IC fields applied on the fly (the tail of every builder
+ * stack: WrapFlow(InverseFlow(CDFTransform(marginal))) per field followed by
+ * InverseFlow(GlobalInternalCoordinateTransformation), generator_builder.py:408-459): bonds, angles
+ * and torsions arrive in [0,1], `marginals` (device, 3N-6 entries in bonds | angles | torsions column
+ * order) maps them to their IC domains, then the atoms are placed; dlogp gets both log-dets. */
+int bgx_ic_to_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* marginals, float clamp_lo,
+                         float clamp_hi, float logdet_min, int64_t batch, const float* bonds,
+                         const float* angles, const float* torsions, const float* x0,
+                         int32_t x0_stride, const float* R, int32_t r_stride, float* xyz,
+                         const float* dlogp_in, float* dlogp_out, void* stream);
+
+/* The reverse tail (energy / NLL direction): Cartesian -> ICs -> cdf of every IC column. */
+int bgx_ic_from_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* marginals, float clamp_lo,
+                           float clamp_hi, float logdet_min, int64_t batch, const float* xyz,
+                           float* bonds, float* angles, float* torsions, float* x0, float* R,
+                           const float* dlogp_in, float* dlogp_out, void* stream);
+
+/* ---- relative / mixed internal coordinates ------------------------------ */
+
+/* RelativeInternalCoordinateTransformation (bgflow/nn/flow/crd_transform/ic.py:268-513): the
+ * atoms in `fixed` keep their Cartesian coordinates, every other atom i has a z-matrix row
+ * (i, j, k, l).  With keepdims > 0 the plan is a MixedCoordinateTransformation (ic.py:719-884):
+ * the fixed block is additionally whitened by a static PCA (WhitenFlow, crd_transform/pca.py:37-107):
+ *   forward  z_fixed = (x_fixed - mean) . whiten      dlogp += log_det_whiten
+ *   inverse  x_fixed = z_fixed . blacken + mean       dlogp -= log_det_whiten */
+typedef struct bgx_relplan {
+  int32_t n_atoms, n_fixed, n_rel;   /* n_rel = n_atoms - n_fixed */
+  const int32_t* fixed;              /* device [n_fixed] atom ids, in the column order of x_fixed */
+  const int32_t* rel;                /* device [n_rel][4] rows (i,j,k,l) = column order of the IC tensors */
+  const int32_t* order;              /* device [n_rel] placement order (row ids): j,k,l before i */
+  int32_t normalize_angles;
+  float eps;
+  int32_t keepdims;                  /* 0 = relative transform; > 0 = mixed (whitened fixed block) */
+  const float* mean;                 /* device [3 n_fixed] */
+  const float* blacken;              /* device [keepdims][3 n_fixed] */
+  const float* whiten;               /* device [3 n_fixed][keepdims] */
+  float log_det_whiten;              /* WhitenFlow.jacobian_xz = -sum(log std) */
+} bgx_relplan;
+
+/* (bonds, angles, torsions [batch, n_rel]; fixed [batch, keepdims or 3 n_fixed]) -> xyz [batch, 3 n_atoms] */
+int bgx_relic_to_xyz(const bgx_relplan* plan, int64_t batch, const float* bonds, const float* angles,
+                     const float* torsions, const float* fixed, float* xyz, const float* dlogp_in,
+                     float* dlogp_out, void* stream);
+
+int bgx_relic_from_xyz(const bgx_relplan* plan, int64_t batch, const float* xyz, float* bonds,
+                       float* angles, float* torsions, float* fixed, const float* dlogp_in,
+                       float* dlogp_out, void* stream);
 
 /* ---- misc -------------------------------------------------------------------------------- */
 

@@ -22,4 +22,4 @@ Pinning status (see DESIGN.md "Oracle"):
     known-answer vector: that one constant (beta) is "parity unpinned".
 """
 
-from . import flows, ic  # noqa: F401
+from . import flows, ic, cdf  # noqa: F401

@@ -19,7 +19,9 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["ZPlan", "make_plan", "xyz_to_ic", "ic_to_xyz", "ALA2_GLOBAL_Z", "ALA2_XYZ", "chain_z_matrix"]
+__all__ = ["ZPlan", "make_plan", "xyz_to_ic", "ic_to_xyz", "ALA2_GLOBAL_Z", "ALA2_XYZ", "chain_z_matrix",
+           "RelPlan", "make_rel_plan", "rel_xyz_to_ic", "rel_ic_to_xyz", "Whitening", "mixed_xyz_to_ic",
+           "mixed_ic_to_xyz", "ALA2_RIGID_BLOCK", "ALA2_RELATIVE_Z"]
 
 
 # Fixture data of the reference's own test: tests/nn/flow/crd_transform/test_ic.py:64-89,91-116
@@ -229,3 +231,129 @@ def ic_to_xyz(plan, bonds, angles, torsions, x0, orientation, normalize_angles=T
         dlogp = dlogp + 2 * torch.log(d) + torch.log(torch.sin(a))
     xyz = torch.stack(pos, dim=1).reshape(b, -1)
     return xyz, dlogp
+
+
+# ------------------------------------------------------------------------------------------------
+# Relative and mixed transforms
+# ------------------------------------------------------------------------------------------------
+
+class RelPlan:
+    """Host-side description of a relative z-matrix (ic.py:268-384).
+
+    fixed   atoms that stay Cartesian, in the column order of the ``x_fixed`` tensor (ic.py:419)
+    rel     z-matrix rows ``(i, j, k, l)`` = column order of bonds / angles / torsions
+    order   placement order of the rows (any order compatible with the stages of
+            decompose_z_matrix, ic.py:25-91, gives identical results)
+    """
+
+    def __init__(self, fixed, rel, order, n_atoms):
+        self.fixed = fixed
+        self.rel = rel
+        self.order = order
+        self.n_atoms = n_atoms
+
+
+def make_rel_plan(z_matrix, fixed_atoms):
+    rel = np.asarray(z_matrix)
+    fixed = [int(a) for a in np.asarray(fixed_atoms)]
+    placed = set(fixed)
+    remaining = list(range(len(rel)))
+    order = []
+    while remaining:
+        stage = [r for r in remaining if all(int(a) in placed for a in rel[r, 1:])]
+        if not stage:
+            raise ValueError("z-matrix decomposition failed: atoms not reachable from the fixed atoms")
+        order.extend(stage)
+        placed.update(int(rel[r, 0]) for r in stage)
+        remaining = [r for r in remaining if r not in set(stage)]
+    return RelPlan(fixed, rel, order, len(rel) + len(fixed))
+
+
+def rel_xyz_to_ic(plan, xyz, normalize_angles=True, eps=1e-7):
+    """RelativeInternalCoordinateTransformation._forward (ic.py:386-433):
+    xyz ``[B, 3N]`` -> bonds, angles, torsions ``[B, n_rel]``, x_fixed ``[B, 3 n_fixed]``, dlogp."""
+    b = xyz.shape[0]
+    x = xyz.reshape(b, -1, 3)
+    rel = plan.rel
+    xi, xj, xk, xl = (x[:, rel[:, c]] for c in range(4))
+    bonds = _norm(xj - xi, eps)[..., 0]
+    angles, sin_a = _angle(xi, xj, xk, eps)
+    torsions = _torsion(xi, xj, xk, xl, eps)
+    dlogp = -(2 * torch.log(bonds) + torch.log(sin_a)).sum(-1, keepdim=True)
+    x_fixed = x[:, plan.fixed].reshape(b, -1)
+    if normalize_angles:
+        angles = angles / math.pi
+        torsions = (torsions + math.pi) / (2 * math.pi)
+        dlogp = dlogp - angles.shape[-1] * math.log(math.pi) - torsions.shape[-1] * math.log(2 * math.pi)
+    return bonds, angles, torsions, x_fixed, dlogp
+
+
+def rel_ic_to_xyz(plan, bonds, angles, torsions, x_fixed, normalize_angles=True, eps=1e-7):
+    """RelativeInternalCoordinateTransformation._inverse (ic.py:435-513)."""
+    b = x_fixed.shape[0]
+    const = 0.0
+    if normalize_angles:
+        angles = angles * math.pi
+        torsions = torsions * (2 * math.pi) - math.pi
+        const = angles.shape[-1] * math.log(math.pi) + torsions.shape[-1] * math.log(2 * math.pi)
+    xf = x_fixed.reshape(b, -1, 3)
+    pos = [None] * plan.n_atoms
+    for c, atom in enumerate(plan.fixed):
+        pos[atom] = xf[:, c]
+    dlogp = torch.zeros(b, 1, dtype=x_fixed.dtype) + const
+    for r in plan.order:
+        i, j, k, l = (int(v) for v in plan.rel[r])
+        d, a, t = bonds[:, r:r + 1], angles[:, r:r + 1], torsions[:, r:r + 1]
+        pos[i] = _place(pos[j], pos[k], pos[l], d, a, t, eps)
+        dlogp = dlogp + 2 * torch.log(d) + torch.log(torch.sin(a))
+    return torch.stack(pos, dim=1).reshape(b, -1), dlogp
+
+
+class Whitening:
+    """Static PCA whitening of the fixed block: WhitenFlow(X0, keepdims, whiten_inverse=False)
+    (crd_transform/pca.py:10-34,37-107), computed in numpy float64 exactly like ``_pca``."""
+
+    def __init__(self, x0, keepdims=None):
+        x0 = np.asarray(x0, dtype=np.float64) if not isinstance(x0, np.ndarray) else x0
+        if keepdims is None:
+            keepdims = x0.shape[1]
+        mean = x0.mean(axis=0)
+        xm = x0 - mean
+        cov = np.matmul(xm.T, xm) / (xm.shape[0] - 1.0)
+        eigval, eigvec = np.linalg.eigh(cov)
+        idx = np.argsort(eigval)[::-1][:keepdims]
+        std = np.sqrt(eigval[idx])
+        eigvec = eigvec[:, idx]
+        self.mean = mean
+        self.whiten = np.matmul(eigvec, np.diag(1.0 / std))      # [dim, keep]
+        self.blacken = np.matmul(np.diag(std), eigvec.T)         # [keep, dim]
+        self.std = std
+        self.keepdims = keepdims
+        self.jacobian_xz = -float(np.sum(np.log(std)))
+
+
+def mixed_xyz_to_ic(plan, white, xyz, normalize_angles=True, eps=1e-7):
+    """MixedCoordinateTransformation._forward (ic.py:836-860)."""
+    bonds, angles, torsions, x_fixed, dlogp = rel_xyz_to_ic(plan, xyz, normalize_angles, eps)
+    mean = torch.as_tensor(white.mean, dtype=xyz.dtype)
+    tw = torch.as_tensor(white.whiten, dtype=xyz.dtype)
+    z_fixed = torch.matmul(x_fixed - mean, tw)
+    return bonds, angles, torsions, z_fixed, dlogp + white.jacobian_xz
+
+
+def mixed_ic_to_xyz(plan, white, bonds, angles, torsions, z_fixed, normalize_angles=True, eps=1e-7):
+    """MixedCoordinateTransformation._inverse (ic.py:862-884)."""
+    mean = torch.as_tensor(white.mean, dtype=z_fixed.dtype)
+    tb = torch.as_tensor(white.blacken, dtype=z_fixed.dtype)
+    x_fixed = torch.matmul(z_fixed, tb) + mean
+    xyz, dlogp = rel_ic_to_xyz(plan, bonds, angles, torsions, x_fixed, normalize_angles, eps)
+    return xyz, dlogp - white.jacobian_xz
+
+
+# fixture of the reference's own test: tests/nn/flow/crd_transform/test_ic.py:37-62
+ALA2_RIGID_BLOCK = np.array([6, 8, 9, 10, 14])
+ALA2_RELATIVE_Z = np.array([
+    [0, 1, 4, 6], [1, 4, 6, 8], [2, 1, 4, 0], [3, 1, 4, 0], [4, 6, 8, 14], [5, 4, 6, 8], [7, 6, 8, 4],
+    [11, 10, 8, 6], [12, 10, 8, 11], [13, 10, 8, 11], [15, 14, 8, 16], [16, 14, 8, 6], [17, 16, 14, 15],
+    [18, 16, 14, 8], [19, 18, 16, 14], [20, 18, 16, 19], [21, 18, 16, 19],
+])

@@ -223,3 +223,141 @@ def test_ic_backward_definition_matches_oracle_values_and_gradients(mol, normali
         torch.testing.assert_close(b, a, atol=1e-11, rtol=0)
     for a, b in zip(g_ref, g_got):
         torch.testing.assert_close(b, a, atol=1e-9, rtol=1e-10)
+
+
+# ------------------------------------------------------------------ SURVEY 8f rows (host side, CPU)
+
+@pytest.mark.parametrize("keep", [None, 9, 15])
+def test_relative_ic_backward_definition_matches_oracle(keep):
+    """``_torch_math_ic.relic_*`` (what the relative / mixed IC backward re-evaluates) against the
+    oracle in fp64: values and vector-Jacobian products, both directions."""
+    from oracle import ic as oic
+    from bgflow_b200 import _torch_math_ic as tm
+    import bgflow_b200 as bg
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.as_tensor(oic.ALA2_XYZ).reshape(1, -1)
+    xyz = x0 + 0.01 * torch.randn(7, 66, generator=g, dtype=torch.float64)
+    oplan = oic.make_rel_plan(oic.ALA2_RELATIVE_Z, oic.ALA2_RIGID_BLOCK)
+    if keep is None:
+        layer = bg.RelativeInternalCoordinateTransformation(oic.ALA2_RELATIVE_Z, oic.ALA2_RIGID_BLOCK)
+        fwd = lambda x: oic.rel_xyz_to_ic(oplan, x)
+        inv = lambda *a: oic.rel_ic_to_xyz(oplan, *a)
+    else:
+        data = x0 + 0.02 * torch.randn(300, 66, generator=g, dtype=torch.float64)
+        layer = bg.MixedCoordinateTransformation(data, oic.ALA2_RELATIVE_Z, oic.ALA2_RIGID_BLOCK, keepdims=keep)
+        white = oic.Whitening(data.reshape(-1, 22, 3)[:, oic.ALA2_RIGID_BLOCK].reshape(-1, 15).numpy(), keepdims=keep)
+        assert layer.dim_fixed == keep and abs(white.jacobian_xz - layer._plan.whitening["jacobian_xz"]) < 1e-9
+        fwd = lambda x: oic.mixed_xyz_to_ic(oplan, white, x)
+        inv = lambda *a: oic.mixed_ic_to_xyz(oplan, white, *a)
+    plan = layer._plan
+    xyz.requires_grad_(True)
+    ref, got = fwd(xyz), tm.relic_from_xyz(plan, xyz)
+    ws = [torch.randn(t.shape, generator=g, dtype=torch.float64) for t in ref]
+    g_ref = torch.autograd.grad(sum((a * w).sum() for a, w in zip(ref, ws)), xyz)[0]
+    g_got = torch.autograd.grad(sum((a * w).sum() for a, w in zip(got, ws)), xyz)[0]
+    for a, b in zip(ref, got):
+        torch.testing.assert_close(b, a, atol=1e-10, rtol=0)
+    torch.testing.assert_close(g_got, g_ref, atol=1e-8, rtol=1e-9)
+    ins = [t.detach().clone().requires_grad_(True) for t in ref[:4]]
+    ref2, got2 = inv(*ins), tm.relic_to_xyz(plan, *ins)
+    ws = [torch.randn(t.shape, generator=g, dtype=torch.float64) for t in ref2]
+    g_ref = torch.autograd.grad(sum((a * w).sum() for a, w in zip(ref2, ws)), ins)
+    g_got = torch.autograd.grad(sum((a * w).sum() for a, w in zip(got2, ws)), ins)
+    for a, b in zip(ref2, got2):
+        torch.testing.assert_close(b, a, atol=1e-10, rtol=0)
+    for a, b in zip(g_ref, g_got):
+        torch.testing.assert_close(b, a, atol=1e-8, rtol=1e-9)
+    # reference properties (tests/nn/flow/crd_transform/test_ic.py:452-475)
+    assert layer.dim_bonds == layer.dim_angles == layer.dim_torsions == 17
+    assert (layer.bond_indices == oic.ALA2_RELATIVE_Z[:, :2]).all()
+    assert (layer.fixed_atoms == oic.ALA2_RIGID_BLOCK).all()
+
+
+def test_relplan_validation():
+    from bgflow_b200.engine import RelPlan
+    z = np.array([[3, 2, 1, 0], [4, 3, 2, 1]])
+    plan = RelPlan(z, np.array([0, 1, 2]))
+    assert plan.order == [0, 1] and plan.n_atoms == 5 and plan.fixed_width == 9
+    with pytest.raises(ValueError):
+        RelPlan(np.array([[3, 2, 1, 4], [4, 3, 2, 1]]), np.array([0, 1, 2]))     # cyclic: 3 needs 4 needs 3
+    with pytest.raises(ValueError):
+        RelPlan(np.array([[3, 2, 1, 0]]), np.array([0, 1, 2, 3]))                 # atom 3 twice
+
+
+def test_cdf_host_mirrors_match_oracle():
+    """TruncatedNormalDistribution / SloppyUniform mirrors and the torch CDFTransform definition
+    (generic path + backward) against the oracle in fp64 on the CPU."""
+    import bgflow_b200 as bg
+    from bgflow_b200 import cdf as bcdf
+    from oracle import cdf as ocdf
+    g = torch.Generator().manual_seed(2)
+    n = 6
+    mu = 1 + torch.rand(n, generator=g, dtype=torch.float64)
+    sigma = 0.2 + torch.rand(n, generator=g, dtype=torch.float64)
+    lower = torch.rand(n, generator=g, dtype=torch.float64)
+    upper = 4 * torch.ones(n, dtype=torch.float64)
+    mine = bg.TruncatedNormalDistribution(mu, sigma, lower, upper)
+    ref = ocdf.TruncatedNormal(mu, sigma, lower, upper)
+    u = torch.rand(50, n, generator=g, dtype=torch.float64)
+    for inverse in (True, False):
+        x = u if inverse else ref.icdf(u)
+        a = bcdf._torch_cdf_transform(mine, x, inverse, 1e-7)
+        b = ocdf.cdf_transform(ref, x, inverse=inverse)
+        torch.testing.assert_close(a[0], b[0], atol=1e-12, rtol=0)
+        torch.testing.assert_close(a[1], b[1], atol=1e-12, rtol=0)
+    s = mine.sample(1000)
+    assert s.shape == (1000, n) and (s >= lower).all() and (s <= upper).all()
+    assert torch.isfinite(mine.energy(s)).all()
+    with pytest.raises(ValueError):
+        mine.energy(torch.full((1, n), 5.0, dtype=torch.float64))
+    su = bg.SloppyUniform(torch.zeros(3, dtype=torch.float64), 2 * torch.ones(3, dtype=torch.float64))
+    ou = ocdf.Uniform(torch.zeros(3, dtype=torch.float64), 2 * torch.ones(3, dtype=torch.float64))
+    x = torch.tensor([[0.5, -0.1, 2.0]], dtype=torch.float64)
+    torch.testing.assert_close(su.cdf(x), ou.cdf(x))
+    assert torch.equal(su.log_prob(x), ou.log_prob(x))
+    # column specs for the kernel table
+    cols = bcdf.marginal_columns(mine, n)
+    assert len(cols) == n and cols[0][0] == _lib.DIST_TRUNCNORMAL and abs(cols[2][1] - float(mu[2])) < 1e-15
+    assert bcdf.marginal_columns(torch.distributions.Normal(torch.zeros(2), torch.ones(2)), 2)[1] == (1, 0.0, 1.0, 0.0, 0.0)
+    assert bcdf.marginal_columns(su, 3)[0][:3] == (3, 0.0, 2.0)
+    assert bcdf.marginal_columns(torch.distributions.Beta(torch.ones(2), torch.ones(2)), 2) is None
+    # kernel-backed marginals refuse CPU tensors like every other kernel-backed layer
+    with pytest.raises(RuntimeError):
+        bg.CDFTransform(mine)(torch.rand(4, n))
+    # the C helper that derives the per-column constants runs on the host
+    col = _lib.bgx_cdf_col()
+    assert _lib.load().bgx_cdf_col_init(_lib.DIST_TRUNCNORMAL, 1.0, 1.0, 1e-5, float("inf"), ctypes.byref(col)) == 0
+    assert abs(col.p[2] - 0.158657) < 1e-5 and abs(col.p[3] - 0.841343) < 1e-5
+    assert _lib.load().bgx_cdf_col_init(_lib.DIST_TRUNCNORMAL, 1.0, -1.0, 0.0, 1.0, ctypes.byref(col)) == -1
+
+
+def test_fuse_domain_maps_rewrites_builder_tail():
+    """Structure only (no compute): the builder's tail (generator_builder.py:408-459) becomes
+    [constants, one multi-tensor icdf launch for the non-IC fields, MappedICTail]."""
+    import bgflow_b200 as bg
+    from bgflow_b200 import cdf as bcdf
+    from oracle import ic as oic
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    tn = lambda n, lo, hi: bg.TruncatedNormalDistribution(torch.ones(n), torch.ones(n), torch.tensor(lo), torch.tensor(hi))
+    marg = [tn(21, 1e-5, float("inf")), tn(20, 1e-5, 1.0), bg.SloppyUniform(torch.zeros(19), torch.ones(19)),
+            torch.distributions.Normal(torch.zeros(10), torch.ones(10))]
+    head = bg.SwapFlow()
+    layers = [head] + [bg.WrapFlow(bg.InverseFlow(bg.CDFTransform(m)), (i,)) for i, m in enumerate(marg)]
+    layers += [bg.SetConstantFlow([4], [torch.zeros(1, 3)]), bg.SetConstantFlow([5], [torch.tensor([0.5, 0.5, 0.5])]),
+               bg.WrapFlow(bg.InverseFlow(ic), indices=[0, 1, 2, 4, 5], out_indices=(0,))]
+    fused = bg.fuse_domain_maps(bg.SequentialFlow(layers))
+    kinds = [type(b).__name__ for b in fused]
+    assert kinds == ["SwapFlow", "SetConstantFlow", "SetConstantFlow", "InverseFlow", "WrapFlow"]
+    multi = fused[3]._delegate
+    assert isinstance(multi, bcdf.MultiCDFFlow) and multi._indices == [3]
+    tail = fused[4]._flow
+    assert isinstance(tail, bcdf.MappedICTail) and tail._marginals[2] is marg[2]
+    assert fused[4]._accumulates_dlogp and fused[3]._accumulates_dlogp
+    # a generic (non kernel-backed) marginal on an IC field keeps the IC layer unfused
+    layers[2] = bg.WrapFlow(bg.InverseFlow(bg.CDFTransform(torch.distributions.Beta(torch.ones(20), torch.ones(20)))), (1,))
+    fused2 = bg.fuse_domain_maps(bg.SequentialFlow(layers))
+    assert [type(b).__name__ for b in fused2] == ["SwapFlow", "SetConstantFlow", "SetConstantFlow", "InverseFlow", "WrapFlow"]
+    assert isinstance(fused2[4]._flow, bg.InverseFlow) and fused2[3]._delegate._indices == [0, 1, 2, 3]
+    # nothing to fuse: unchanged block list
+    plain = bg.SequentialFlow([bg.SwapFlow(), bg.SwapFlow()])
+    assert len(bg.fuse_domain_maps(plain)) == 2

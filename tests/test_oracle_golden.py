@@ -133,3 +133,68 @@ def test_ala2_plan_matches_survey():
     plan = oic.make_plan(oic.ALA2_GLOBAL_Z)
     assert plan.seeds == [0, 1, 2]
     assert len(plan.rel) == 19 and sorted(plan.order) == list(range(19))
+
+
+# ------------------------------------------------------------------ SURVEY 8f rows
+from oracle import cdf as ocdf
+
+CDF_FIELDS = {"bonds": 21, "angles": 20, "torsions": 19, "fixed": 9, "augmented": 10}
+
+
+def _finite_close(a, b, tag, scale=1.0):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isfinite(a), np.isfinite(b))
+    m = np.isfinite(b)
+    _close(a[m], b[m], tag, scale)
+    assert np.array_equal(a[~m], b[~m])          # same +-inf
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_cdf_maps_match_reference(tag):
+    """CDFTransform over the builder's IC marginals, both directions, incl. the eps-clamped edges."""
+    g = load_golden("cdf_maps")
+    marg = ocdf.ic_marginals(CDF_FIELDS, DT[tag])
+    t = lambda k: torch.from_numpy(g[f"{k}_{tag}"])
+    custom = ocdf.TruncatedNormal(t("custom_mu"), t("custom_sigma"), t("custom_lower"), t("custom_upper"))
+    zero = torch.zeros(5, dtype=DT[tag])
+    halfopen = ocdf.TruncatedNormal(zero, torch.tensor(1.0), -torch.tensor(np.inf, dtype=DT[tag]),
+                                    torch.tensor(np.inf, dtype=DT[tag]))
+    cases = dict(marg, custom=custom, halfopen=halfopen)
+    for name, dist in cases.items():
+        x, d = ocdf.cdf_transform(dist, t(f"{name}_u"), inverse=True)
+        _finite_close(x, t(f"{name}_x"), tag)
+        _finite_close(d, t(f"{name}_dlogp"), tag, 4)
+        u, db = ocdf.cdf_transform(dist, t(f"{name}_x"), inverse=False)
+        _finite_close(u, t(f"{name}_ub"), tag)
+        _finite_close(db, t(f"{name}_dlogpb"), tag, 4)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["relic_ala2", "mixed_ala2_keep9", "mixed_ala2_keep15"])
+def test_relative_ic_matches_reference(name, tag):
+    g = load_golden(name)
+    plan = oic.make_rel_plan(g["z_matrix"], g["fixed"])
+    keep = int(g["keepdims"])
+    t = lambda k: torch.from_numpy(g[f"{k}_{tag}"])
+    if keep < 0:
+        fwd = lambda x: oic.rel_xyz_to_ic(plan, x)
+        inv = lambda *a: oic.rel_ic_to_xyz(plan, *a)
+    else:
+        data = torch.from_numpy(g["pca_data"]).to(DT[tag]).reshape(-1, 22, 3)[:, g["fixed"]].reshape(-1, 15)
+        white = oic.Whitening(data.numpy(), keepdims=keep)
+        fwd = lambda x: oic.mixed_xyz_to_ic(plan, white, x)
+        inv = lambda *a: oic.mixed_ic_to_xyz(plan, white, *a)
+    # fp32 PCA (numpy eigh in float32, pca.py:20-33) is only reproducible to ~1e-4 relative
+    fs = 1
+    bonds, angles, torsions, fixed, dlogp = fwd(t("xyz"))
+    _close(bonds, t("bonds"), tag, 4)
+    _close(angles, t("angles"), tag, 4)
+    _close(torsions, t("torsions"), tag, 4)
+    _close(fixed, t("fixed"), tag, 4 * fs)
+    _close(dlogp, t("dlogp"), tag, 40 * fs)
+    xyz, dinv = inv(t("bonds"), t("angles"), t("torsions"), t("fixed"))
+    _close(xyz, t("xyz_back"), tag, 10 * fs)
+    _close(dinv, t("dlogp_inv"), tag, 40 * fs)
+    xyz, dgen = inv(t("gen_bonds"), t("gen_angles"), t("gen_torsions"), t("gen_fixed"))
+    _close(xyz, t("gen_xyz"), tag, 10 * fs)
+    _close(dgen, t("gen_dlogp"), tag, 40 * fs)
