@@ -232,6 +232,73 @@ def bench_ic(args, dev):
     return out
 
 
+def bench_tail(args, dev):
+    """Secondary measurement: the builder tail on Ala2 — icdf maps of
+    bonds / angles / torsions / augmented + IC -> Cartesian — as the reference structures it (one
+    launch per field + the IC kernel) and fused (``fuse_domain_maps``: one multi-field launch + one
+    mapped-IC kernel); the stand-alone CDF-map kernel over all five fields (640 algorithmic
+    bytes/sample); the relative / mixed IC kernels."""
+    import math
+    import bgflow_b200 as bg
+    from oracle import ic as oic
+    B = args.batch_per_gpu
+    pk = peaks()
+    one = lambda n, v=1.0: torch.full((n,), v, device=dev)
+    inf = torch.tensor(math.inf, device=dev)
+    m = {"bonds": bg.TruncatedNormalDistribution(one(21), one(21), torch.tensor(1e-5, device=dev), inf),
+         "angles": bg.TruncatedNormalDistribution(one(20, 0.5), one(20), torch.tensor(1e-5, device=dev),
+                                                  torch.tensor(1.0, device=dev)),
+         "torsions": bg.SloppyUniform(torch.zeros(19, device=dev), one(19)),
+         "fixed": torch.distributions.Normal(torch.zeros(9, device=dev), 20 * one(9)),
+         "augmented": torch.distributions.Normal(torch.zeros(10, device=dev), one(10))}
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    layers = [bg.WrapFlow(bg.InverseFlow(bg.CDFTransform(m[n])), (i,))
+              for i, n in enumerate(("bonds", "angles", "torsions", "augmented"))]
+    layers += [bg.SetConstantFlow([4], [torch.zeros(1, 3, device=dev)]),
+               bg.SetConstantFlow([5], [torch.tensor([0.5, 0.5, 0.5], device=dev)]),
+               bg.WrapFlow(bg.InverseFlow(ic), indices=[0, 1, 2, 4, 5], out_indices=(0,))]
+    tail = bg.SequentialFlow(layers).to(dev)
+    fused = bg.fuse_domain_maps(tail)
+    g = torch.Generator().manual_seed(1)
+    us = [(torch.rand(B, w, generator=g) * 0.9 + 0.05).to(dev) for w in (21, 20, 19, 10)]
+    u5 = us[:3] + [torch.rand(B, 9, generator=g).to(dev) * 0.9 + 0.05, us[3]]
+    multi = bg.InverseFlow(bg.MultiCDFFlow([m[n] for n in ("bonds", "angles", "torsions", "fixed", "augmented")]))
+    rel = bg.RelativeInternalCoordinateTransformation(oic.ALA2_RELATIVE_Z, oic.ALA2_RIGID_BLOCK)
+    x0 = torch.as_tensor(oic.ALA2_XYZ, dtype=torch.float32).reshape(1, -1)
+    xyz = (x0 + 0.01 * torch.randn(B, 66, generator=g)).to(dev)
+    mixed = bg.MixedCoordinateTransformation(x0 + 0.02 * torch.randn(2000, 66, generator=g), oic.ALA2_RELATIVE_Z,
+                                             oic.ALA2_RIGID_BLOCK, keepdims=9)
+    out = {}
+
+    def timed(name, fn, alg_bytes):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        gbs = alg_bytes * B / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "samples_per_s": B / (ms * 1e-3), "hbm_GBps_algorithmic": gbs,
+                     "hbm_frac": gbs / pk["hbm_gbs"], "algorithmic_bytes_per_sample": alg_bytes}
+
+    with torch.no_grad():
+        timed("cdf_map_5_fields_79_cols", lambda: multi(*u5), 4 * (2 * 79 + 1))
+        # tail: reads 70 uniforms, writes 66 coordinates + 10 augmented + dlogp
+        timed("tail_per_field_launches", lambda: tail(*us), 4 * (70 + 76 + 1))
+        timed("tail_fused", lambda: fused(*us), 4 * (70 + 76 + 1))
+        rics = rel(xyz)[:-1]
+        timed("relative_xyz_to_ic", lambda: rel(xyz), 4 * (2 * 66 + 1))
+        timed("relative_ic_to_xyz", lambda: rel(*rics, inverse=True), 4 * (2 * 66 + 1))
+        mics = mixed(xyz)[:-1]
+        timed("mixed_xyz_to_ic", lambda: mixed(xyz), 4 * (66 + 60 + 1))
+        timed("mixed_ic_to_xyz", lambda: mixed(*mics, inverse=True), 4 * (66 + 60 + 1))
+    return out
+
+
 def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     """Secondary measurement (BASELINE config 5, "KL-train grad allreduce"): reverse-KL steps on a
     Gaussian target — kernel forward, recompute backward, ONE flat gradient all-reduce (NCCL when
@@ -460,7 +527,7 @@ def main():
             "gpu_pytorch_port": {"value": time_gpu_torch_port(blocks, kind, dim, 65536, dev), "unit": "samples/s",
                                  "sample": "65536 rows; oracle/flows.py op sequence on CUDA tensors (the reference's "
                                            "single-GPU PyTorch path, restated)"},
-            "ic_ala2": bench_ic(args, dev)}
+            "ic_ala2": bench_ic(args, dev), "ic_tail": bench_tail(args, dev)}
     if args.extras:
         tr = bench_train(args, flow, kind, dim, dev, run_timed, world)
         if rank == 0:

@@ -2,11 +2,11 @@
 // field of the flow state in ONE launch (the reference runs one WrapFlow(InverseFlow(CDFTransform))
 // per field, generator_builder.py:443-459: ~10 elementwise passes + a row sum each).
 //
-// HBM-bound: 8 B per element + 8 B per row of dlogp.  A CTA owns 128 consecutive rows; its threads
-// walk each segment's [rows x w] block element-wise (consecutive threads = consecutive floats of a
-// row piece: fully coalesced for dense tensors), write the mapped value straight back and park the
-// element's log-det in shared memory, column-major (leading dim 129: conflict-free for both
-// phases); then thread r sums row r in a fixed order, so dlogp is deterministic.
+// HBM-bound: 8 B per element + 8 B per row of dlogp.  A CTA owns 128 consecutive rows; for each
+// segment a thread owns one column and every k-th row (column constants in registers, accesses of a
+// pass contiguous for dense tensors), writes the mapped value straight back and parks the element's
+// log-det in shared memory, column-major (leading dim 129: conflict-free for both phases); then
+// thread r sums row r in a fixed order, so dlogp is deterministic.
 #include <cmath>
 
 #include "bgx_cdf_math.cuh"
@@ -16,7 +16,8 @@ namespace bgx {
 
 constexpr int CT = 128;          // rows (threads) per CTA
 constexpr int CLD = CT + 1;
-constexpr int CCHUNK = 88;       // columns staged per pass: 88 * 129 * 4 B = 45.4 KB (5 CTAs / SM)
+constexpr int CU = 8;            // loads in flight per thread
+constexpr int CCHUNK = 44;       // columns staged per pass: 44 * 129 * 4 B = 22.7 KB (10 CTAs / SM)
 
 struct CdfArgs {
   long long B;
@@ -50,22 +51,37 @@ __global__ void __launch_bounds__(CT) cdf_map_kernel(const CdfArgs a) {
     for (int c0 = 0; c0 < W; c0 += CCHUNK) {
       const int cw = min(CCHUNK, W - c0);
       if (used + cw > CCHUNK) flush();
-      const float* gin = a.in[s].ptr + row0 * (long long)a.in[s].stride + c0;
-      float* gout = const_cast<float*>(a.out[s].ptr) + row0 * (long long)a.out[s].stride + c0;
+      const int si = a.in[s].stride, so = a.out[s].stride;       // (128 rows x stride fits 32 bits: checked on the host)
+      const float* gin = a.in[s].ptr + row0 * (long long)si + c0;
+      float* gout = const_cast<float*>(a.out[s].ptr) + row0 * (long long)so + c0;
       const bgx_cdf_col* cols = a.cols + col_base + c0;
-      // division-free walk over e = t, t + CT, ... of the [nrow x cw] block
-      int m = t / cw, c = t - m * cw;
-      const int dm = CT / cw, dc = CT - dm * cw;
-      while (m < nrow) {
+      // thread t owns ONE column of the chunk (c = t mod cw) and every (CT / cw)-th row: its column's
+      // constants stay in registers, and the active threads of a pass still cover rows_per_pass * cw
+      // consecutive floats of a dense tensor (fully coalesced)
+      const int rpp = CT / cw;                       // rows per pass (cw <= CCHUNK < CT)
+      if (t < rpp * cw) {
+        int m = t / cw;
+        const int c = t - m * cw;
         const bgx_cdf_col cc = cols[c];
-        const float v = __ldg(gin + (long long)m * a.in[s].stride + c);
-        float y, ld;
-        if (INVERSE) cdf_inverse(cc, a.clamp, v, y, ld);
-        else cdf_forward(cc, a.clamp, v, y, ld);
-        gout[(long long)m * a.out[s].stride + c] = y;
-        ld_s[(used + c) * CLD + m] = ld;
-        m += dm; c += dc;
-        if (c >= cw) { c -= cw; ++m; }
+        // CU loads in flight per thread: one-at-a-time loads would leave the kernel bound by DRAM
+        // latency (40 warps x 128 B per SM in flight), not by bandwidth
+        for (; m < nrow; m += CU * rpp) {
+          float v[CU];
+#pragma unroll
+          for (int u = 0; u < CU; ++u)
+            if (m + u * rpp < nrow) v[u] = __ldg(gin + (m + u * rpp) * si + c);
+#pragma unroll
+          for (int u = 0; u < CU; ++u) {
+            const int mu = m + u * rpp;
+            if (mu < nrow) {
+              float y, ld;
+              if (INVERSE) cdf_inverse(cc, a.clamp, v[u], y, ld);
+              else cdf_forward(cc, a.clamp, v[u], y, ld);
+              gout[mu * so + c] = y;
+              ld_s[(used + c) * CLD + mu] = ld;
+            }
+          }
+        }
       }
       used += cw;
     }
@@ -94,6 +110,7 @@ extern "C" int bgx_cdf_map(int64_t batch, int32_t n_seg, const bgx_seg* in, cons
     if (!in[s].ptr || !out[s].ptr || in[s].width < 1 || out[s].width != in[s].width || in[s].stride < in[s].width ||
         out[s].stride < out[s].width)
       return BGX_ERR_INVALID;
+    if ((long long)CT * in[s].stride > 0x7fffffffLL || (long long)CT * out[s].stride > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
     a.in[s] = in[s];
     a.out[s] = out[s];
   }

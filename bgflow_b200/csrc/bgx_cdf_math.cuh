@@ -20,6 +20,18 @@
 #define BGX_HD inline
 #endif
 
+// Device code uses the MUFU approximations (lg2 / rcp / sqrt: a few ulp) for the logarithm, the
+// divisions and the square root of the inverse normal cdf; the host build (tests/native) uses libm.
+#if defined(__CUDA_ARCH__)
+#define BGX_CDF_LOG(x) __logf(x)
+#define BGX_CDF_DIV(a, b) __fdividef((a), (b))
+#define BGX_CDF_SQRT(x) __fsqrt_rn(x)
+#else
+#define BGX_CDF_LOG(x) logf(x)
+#define BGX_CDF_DIV(a, b) ((a) / (b))
+#define BGX_CDF_SQRT(x) sqrtf(x)
+#endif
+
 namespace bgx {
 
 // indices into bgx_cdf_col::p
@@ -40,19 +52,19 @@ BGX_HD float std_normal_icdf(float p) {
     const float r = 0.180625f - q * q;
     const float num = ((5.9109374720e+01f * r + 1.5929113202e+02f) * r + 5.0434271938e+01f) * r + 3.3871327179e+00f;
     const float den = ((6.7187563600e+01f * r + 7.8757757664e+01f) * r + 1.7895169469e+01f) * r + 1.0f;
-    return q * num / den;
+    return BGX_CDF_DIV(q * num, den);
   }
   float r = q < 0.f ? p : 1.0f - p;
-  r = sqrtf(-logf(r));
+  r = BGX_CDF_SQRT(-BGX_CDF_LOG(r));
   float z;
   if (r <= 5.0f) {
     r -= 1.6f;
-    z = (((1.7023821103e-01f * r + 1.3067284816e+00f) * r + 2.7568153900e+00f) * r + 1.4234372777e+00f) /
-        ((1.2021132975e-01f * r + 7.3700164250e-01f) * r + 1.0f);
+    z = BGX_CDF_DIV(((1.7023821103e-01f * r + 1.3067284816e+00f) * r + 2.7568153900e+00f) * r + 1.4234372777e+00f,
+                    (1.2021132975e-01f * r + 7.3700164250e-01f) * r + 1.0f);
   } else {
     r -= 5.0f;
-    z = (((1.7337203997e-02f * r + 4.2868294337e-01f) * r + 3.0812263860e+00f) * r + 6.6579051150e+00f) /
-        ((1.2258202635e-02f * r + 2.4197894225e-01f) * r + 1.0f);
+    z = BGX_CDF_DIV(((1.7337203997e-02f * r + 4.2868294337e-01f) * r + 3.0812263860e+00f) * r + 6.6579051150e+00f,
+                    (1.2258202635e-02f * r + 2.4197894225e-01f) * r + 1.0f);
   }
   return q < 0.f ? -z : z;
 }
@@ -76,7 +88,7 @@ BGX_HD void cdf_forward(const bgx_cdf_col& c, const CdfClamp& k, float x, float&
   } else {
     const float z = (x - c.p[CP_LOC]) * c.p[CP_INV_SCALE];
     u = std_normal_cdf(z);
-    if (c.kind == BGX_DIST_TRUNCNORMAL) u = (u - c.p[CP_CDF_LO]) / c.p[CP_Z];
+    if (c.kind == BGX_DIST_TRUNCNORMAL) u = BGX_CDF_DIV(u - c.p[CP_CDF_LO], c.p[CP_Z]);
     lp = -0.5f * z * z - c.p[CP_LOGNORM];
   }
   u = fminf(fmaxf(u, k.lo), k.hi);

@@ -115,7 +115,8 @@ __device__ __forceinline__ float do_dim(const TcArgs& a, const float (&p)[PS], f
 template <bool INVERSE, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = base;                                          // a.stages x 16 KB
   TcSmem* S = (TcSmem*)(base + (size_t)a.stages * a.nterms * TILE_BYTES);
   float* bias_s = (float*)(S + 1);                               // all layers' biases, concatenated

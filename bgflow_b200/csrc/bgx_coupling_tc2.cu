@@ -34,6 +34,8 @@ constexpr uint32_t T2_TILE_BYTES = 16384;
 constexpr uint32_t T2_SLOT_BYTES = 2 * T2_TILE_BYTES;      // two bf16 terms of one 64-wide k-tile
 constexpr int T2_ACC = 0, T2_A = 128, T2_A_STRIDE = 64;
 constexpr int T2_NB = 8, T2_PS = 3 * T2_NB + 1, T2_DPP = 5;
+constexpr int T2_BPAD = 28;           // last-layer bias: 25 parameters per dim padded to 7 float4
+constexpr int T2_FAST_DEFAULT = 1;   // BGX_T2_FAST=0/1: see the kernel comment
 
 
 struct T2Args {
@@ -67,10 +69,15 @@ struct alignas(16) T2Smem {
   float dl_part[2][T2_TM];
 };
 
-template <bool INVERSE, int ACT>
+// FAST: the last layer's bias in a 16-byte aligned [chunk][dim][28] layout (7 LDS.128 instead of 25
+// loads per dim) and MUFU lg2 for the log-det.  (Tried and measured slower on the B200: evaluating two
+// dims in one basic block for ILP; handing the accumulator back before evaluating — both cost more in
+// registers, extra tcgen05.ld and instruction-cache misses than the shorter wait gains.)
+template <bool INVERSE, int ACT, bool FAST>
 __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(const T2Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = base;
   T2Smem* S = (T2Smem*)(base + T2_SLOTS * T2_SLOT_BYTES);
   float* bias_s = (float*)(S + 1);
@@ -97,9 +104,15 @@ __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(cons
   {
     int off = 0;
     for (int l = 0; l < L; ++l) {
+      if (FAST && l == L - 1) break;
       for (int i = threadIdx.x; i < a.net.Np[l]; i += T2_THREADS) bias_s[off + i] = a.net.bias[l][i];
       off += a.net.Np[l];
     }
+    if (FAST)      // last layer: [chunk][dim][28], zero padded
+      for (int i = threadIdx.x; i < a.npass * T2_DPP * T2_BPAD; i += T2_THREADS) {
+        const int c = i / (T2_DPP * T2_BPAD), r = i - c * (T2_DPP * T2_BPAD), d = r / T2_BPAD, k = r - d * T2_BPAD;
+        bias_s[off + i] = (k < T2_PS) ? a.net.bias[L - 1][c * 128 + d * T2_PS + k] : 0.f;
+      }
   }
   if (warp == 9) tmem_alloc<256>(&S->tmem_base);
   tc_fence_before();
@@ -322,6 +335,7 @@ __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(cons
         const int i0 = (j + c) & 1;                           // (5c + i) % 2 == j  <=>  i % 2 == (j + c) % 2
         int n_mine = 0;
         for (int i = i0; i < T2_DPP; i += 2) n_mine += (5 * c + i < a.D_t) ? 1 : 0;
+        const float* bv = bias_s + last_off + c * (T2_DPP * T2_BPAD);
         bool released = false;
         for (int m = 0; m < n_mine; ++m) {
           const int i = i0 + 2 * m;
@@ -335,14 +349,27 @@ __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(cons
             released = true;
           }
           float p[T2_PS];
+          if (FAST) {
+            const float4* b4 = reinterpret_cast<const float4*>(bv + i * T2_BPAD);
 #pragma unroll
-          for (int k = 0; k < T2_PS; ++k) p[k] = __uint_as_float(v[k]) + bl[i * T2_PS + k];
+            for (int q = 0; q < 6; ++q) {
+              const float4 bb = b4[q];
+              p[4 * q] = __uint_as_float(v[4 * q]) + bb.x;
+              p[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+              p[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+              p[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+            }
+            p[24] = __uint_as_float(v[24]) + bv[i * T2_BPAD + 24];
+          } else {
+#pragma unroll
+            for (int k = 0; k < T2_PS; ++k) p[k] = __uint_as_float(v[k]) + bl[i * T2_PS + k];
+          }
           float* ys = yrow + 5 * c + i;
           float x = *ys;
           n_oob += (x < a.ck.left || x > a.ck.right) ? 1 : 0;
           x = fminf(fmaxf(x, a.ck.left), a.ck.right);
           float y, lad;
-          rqs_eval_reg<!INVERSE>(p, a.ck, x, y, lad);
+          rqs_eval_reg<!INVERSE, FAST>(p, a.ck, x, y, lad);
           *ys = y;
           ld += lad;
         }
@@ -393,7 +420,7 @@ bool spline_tc2_eligible(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   if (!dense(io->cond[0]) || !dense(io->tr_in[0]) || !dense(io->tr_out[0])) return false;
   if (io->cond[0].width != net->raw_width) return false;
   size_t bias = 0;
-  for (int l = 0; l < L; ++l) bias += net->Np[l];
+  for (int l = 0; l < L; ++l) bias += (l == L - 1) ? (size_t)(net->Np[l] / 128) * T2_DPP * T2_BPAD : net->Np[l];
   const size_t need = 1024 + T2_SLOTS * T2_SLOT_BYTES + sizeof(T2Smem) +
                       4 * (bias + (size_t)T2_TM * (io->tr_in[0].width + io->cond[0].width)) + 64;
   return need <= 112 * 1024;
@@ -415,7 +442,7 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
     a.wb[0][l] = (const uint16_t*)net->Wb[0][l];
     a.wb[1][l] = (const uint16_t*)net->Wb[1][l];
     a.ktiles[l] = ceil_div(net->K[l], 64);
-    bias_floats += net->Np[l];
+    bias_floats += (l == L - 1) ? (net->Np[l] / 128) * T2_DPP * T2_BPAD : net->Np[l];   // room for the padded layout
   }
   a.bias_floats = bias_floats;
   a.npass = net->N[L - 1] / 128;
@@ -447,20 +474,22 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
     if (rc) return rc;
   }
   using KernT = void (*)(const T2Args);
-  static const KernT kerns[2][4] = {
-      {spline_coupling_tc2_kernel<false, 0>, spline_coupling_tc2_kernel<false, 1>, spline_coupling_tc2_kernel<false, 2>,
-       spline_coupling_tc2_kernel<false, 3>},
-      {spline_coupling_tc2_kernel<true, 0>, spline_coupling_tc2_kernel<true, 1>, spline_coupling_tc2_kernel<true, 2>,
-       spline_coupling_tc2_kernel<true, 3>}};
+#define BGX_T2_ROW(INV, FAST) \
+  {spline_coupling_tc2_kernel<INV, 0, FAST>, spline_coupling_tc2_kernel<INV, 1, FAST>, \
+   spline_coupling_tc2_kernel<INV, 2, FAST>, spline_coupling_tc2_kernel<INV, 3, FAST>}
+  static const KernT kerns[2][2][4] = {{BGX_T2_ROW(false, false), BGX_T2_ROW(true, false)},
+                                       {BGX_T2_ROW(false, true), BGX_T2_ROW(true, true)}};
+#undef BGX_T2_ROW
   if (net->act < 0 || net->act > 3) return BGX_ERR_INVALID;
-  KernT kern = kerns[a.inverse][net->act];
-  static size_t configured[2][4] = {};
-  if (smem > configured[a.inverse][net->act]) {
+  static const int pair = [] { const char* e = getenv("BGX_T2_FAST"); return e ? (atoi(e) ? 1 : 0) : T2_FAST_DEFAULT; }();
+  KernT kern = kerns[pair][a.inverse][net->act];
+  static size_t configured[2][2][4] = {};
+  if (smem > configured[pair][a.inverse][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (rc) return rc;
-    configured[a.inverse][net->act] = smem;
+    configured[pair][a.inverse][net->act] = smem;
   }
   const unsigned grid = (unsigned)std::min<long long>(a.ntiles, 2LL * sm_count);
   kern<<<grid, T2_THREADS, smem, st>>>(a);

@@ -52,7 +52,8 @@ struct alignas(16) A2Smem {
 template <bool INVERSE, int ACT>
 __global__ void __launch_bounds__(A2_THREADS, 2) affine_coupling_tc2_kernel(const A2Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = base;
   A2Smem* S = (A2Smem*)(base + A2_SLOTS * A2_SLOT_BYTES);
   float* bias_s = (float*)(S + 1);                 // [2][bias_floats]

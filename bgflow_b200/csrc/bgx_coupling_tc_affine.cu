@@ -58,7 +58,8 @@ struct alignas(16) AfSmem {
 template <bool INVERSE, int ACT>
 __global__ void __launch_bounds__(AF_THREADS, 1) affine_coupling_tc_kernel(const AfArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST)
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NT = a.nterms, NST = a.stages, L = a.L;
   uint8_t* ring = base;
   AfSmem* S = (AfSmem*)(base + (size_t)NST * NT * AF_TILE_BYTES);

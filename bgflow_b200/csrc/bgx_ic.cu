@@ -80,23 +80,31 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
     const float* ga = a.angles + row0 * na;
     const float* gt = a.torsions + row0 * nt;
     if (global) {
-      walk_block(t, nb, nrow, [&](int m, int c) { sm[a.slot_of_col[c] * LDT + m] = __ldg(gb + m * nb + c); });
-      walk_block(t, na, nrow, [&](int m, int c) { sm[a.slot_of_col[nb + c] * LDT + m] = __ldg(ga + m * na + c); });
-      walk_block(t, nt, nrow, [&](int m, int c) { sm[a.slot_of_col[nb + na + c] * LDT + m] = __ldg(gt + m * nt + c); });
+      walk_block_ld(t, nb, nrow, [&](int m, int c) { return __ldg(gb + m * nb + c); },
+                    [&](int m, int c, float v) { sm[a.slot_of_col[c] * LDT + m] = v; });
+      walk_block_ld(t, na, nrow, [&](int m, int c) { return __ldg(ga + m * na + c); },
+                    [&](int m, int c, float v) { sm[a.slot_of_col[nb + c] * LDT + m] = v; });
+      walk_block_ld(t, nt, nrow, [&](int m, int c) { return __ldg(gt + m * nt + c); },
+                    [&](int m, int c, float v) { sm[a.slot_of_col[nb + na + c] * LDT + m] = v; });
     } else {
       // column r of every IC tensor belongs to the atom of z-matrix row r
-      walk_block(t, nb, nrow, [&](int m, int c) { sm[(3 * a.rel[4 * c]) * LDT + m] = __ldg(gb + m * nb + c); });
-      walk_block(t, na, nrow, [&](int m, int c) { sm[(3 * a.rel[4 * c] + 1) * LDT + m] = __ldg(ga + m * na + c); });
-      walk_block(t, nt, nrow, [&](int m, int c) { sm[(3 * a.rel[4 * c] + 2) * LDT + m] = __ldg(gt + m * nt + c); });
+      walk_block_ld(t, nb, nrow, [&](int m, int c) { return __ldg(gb + m * nb + c); },
+                    [&](int m, int c, float v) { sm[(3 * a.rel[4 * c]) * LDT + m] = v; });
+      walk_block_ld(t, na, nrow, [&](int m, int c) { return __ldg(ga + m * na + c); },
+                    [&](int m, int c, float v) { sm[(3 * a.rel[4 * c] + 1) * LDT + m] = v; });
+      walk_block_ld(t, nt, nrow, [&](int m, int c) { return __ldg(gt + m * nt + c); },
+                    [&](int m, int c, float v) { sm[(3 * a.rel[4 * c] + 2) * LDT + m] = v; });
       const int wf = a.fixed_w;
       const float* gf = a.fixed_in + row0 * wf;
       if (a.keep == 0)     // Cartesian block of the fixed atoms goes straight to their position slots
-        walk_block(t, wf, nrow, [&](int m, int c) {
-          const int i = c / 3;
-          sm[(3 * a.fixed[i] + (c - 3 * i)) * LDT + m] = __ldg(gf + m * wf + c);
-        });
+        walk_block_ld(t, wf, nrow, [&](int m, int c) { return __ldg(gf + m * wf + c); },
+                      [&](int m, int c, float v) {
+                        const int i = c / 3;
+                        sm[(3 * a.fixed[i] + (c - 3 * i)) * LDT + m] = v;
+                      });
       else                 // whitened block: parked behind the positions, un-whitened per thread below
-        walk_block(t, wf, nrow, [&](int m, int c) { sm[(3 * N + c) * LDT + m] = __ldg(gf + m * wf + c); });
+        walk_block_ld(t, wf, nrow, [&](int m, int c) { return __ldg(gf + m * wf + c); },
+                      [&](int m, int c, float v) { sm[(3 * N + c) * LDT + m] = v; });
     }
     __syncthreads();
   } else {
@@ -247,7 +255,8 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
   PosStore<SMEM> pos;
   if (SMEM) {
     const float* gx = a.xyz_in + row0 * W;
-    walk_block_f(t, W, nrow, [&](int m, int c) { sm[c * LDF + m] = __ldg(gx + m * W + c); });
+    walk_block_ld(t, W, nrow, [&](int m, int c) { return __ldg(gx + m * W + c); },
+                  [&](int m, int c, float v) { sm[c * LDF + m] = v; });
     __syncthreads();
     pos.base = sm + s_loc;
     pos.stride_c = LDF;

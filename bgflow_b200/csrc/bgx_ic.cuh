@@ -52,6 +52,31 @@ __device__ __forceinline__ void walk_block(int t, int W, int rows, F&& body) {
   }
 }
 
+// The same walk for global -> shared staging: UNROLL loads are issued before the first of their
+// values is consumed, so a thread keeps UNROLL requests in flight (one-at-a-time loads leave the
+// copy phase bound by DRAM latency, not bandwidth).
+template <int UNROLL = 8, typename L, typename S>
+__device__ __forceinline__ void walk_block_ld(int t, int W, int rows, L&& load, S&& store) {
+  int m = t / W, c = t - m * W;
+  const int dm = BT / W, dc = BT - dm * W;
+  while (m < rows) {
+    int ms[UNROLL], cs[UNROLL];
+    float v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      ms[u] = m; cs[u] = c;
+      m += dm; c += dc;
+      if (c >= W) { c -= W; ++m; }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (ms[u] < rows) v[u] = load(ms[u], cs[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (ms[u] < rows) store(ms[u], cs[u], v[u]);
+  }
+}
+
 // same walk for kernels whose CTA covers fewer samples than threads
 template <typename F>
 __device__ __forceinline__ void walk_block_f(int t, int W, int rows, F&& body) {

@@ -17,15 +17,18 @@ struct SplineK {
 };
 
 __device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
-  const float bs = c.beta * s;
+  // softplus(s) >= s, and lg2(1 + 2^t) -> t for large t: the max() only matters once the exponent
+  // clamp (t > 64, i.e. slopes above ~44) bites, where torch's thresholded softplus returns s too
   const float v = lg2_fast(1.f + ex2_fast(fminf(s * c.beta_l2e, 64.f))) * c.ln2_over_beta;
-  return bs > 20.f ? s : v;
+  return fmaxf(v, s);
 }
 
 // One (sample, dim) spline evaluation with the 25 parameters in registers (NB = 8 bins).
 // Same algorithm as rqs_eval (bgx_common.cuh); the knots are formed from prefix sums of the
 // softmax numerators instead of a running sum of the normalised bins.
-template <bool ROOT>
+// FASTLOG: log-det through MUFU lg2 (absolute error <= 2^-22 ln 2 per evaluation) instead of logf,
+// binary instead of linear bin search.
+template <bool ROOT, bool FASTLOG = false>
 __device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK& c, float x, float& y,
                                              float& lad) {
   const float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
@@ -52,7 +55,33 @@ __device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK
     kw[k] = fmaf(aw, pw[k - 1], fmaf(c.wstep, (float)k, c.left));
     kh[k] = fmaf(ah, ph[k - 1], fmaf(c.hstep, (float)k, c.bottom));
   }
-  float w_lo = kw[0], w_hi = kw[1], h_lo = kh[0], h_hi = kh[1], s0 = p[2 * NB], s1 = p[2 * NB + 1];
+  float w_lo, w_hi, h_lo, h_hi, s0, s1;
+  if (FASTLOG) {
+    // binary search over the 8 bins: 3 dependent compares, 30 selects (the linear walk below needs
+    // 7 compares and 42 selects in a 7-deep chain); same bin: the largest k with x >= knot[k]
+    const float* sl = p + 2 * NB;
+    const bool c4 = x >= (ROOT ? kh[4] : kw[4]);
+    float qw[5], qh[5], qs[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      qw[q] = c4 ? kw[4 + q] : kw[q];
+      qh[q] = c4 ? kh[4 + q] : kh[q];
+      qs[q] = c4 ? sl[4 + q] : sl[q];
+    }
+    const bool c2 = x >= (ROOT ? qh[2] : qw[2]);
+    float bw[3], bh[3], bs[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      bw[q] = c2 ? qw[2 + q] : qw[q];
+      bh[q] = c2 ? qh[2 + q] : qh[q];
+      bs[q] = c2 ? qs[2 + q] : qs[q];
+    }
+    const bool c1 = x >= (ROOT ? bh[1] : bw[1]);
+    w_lo = c1 ? bw[1] : bw[0]; w_hi = c1 ? bw[2] : bw[1];
+    h_lo = c1 ? bh[1] : bh[0]; h_hi = c1 ? bh[2] : bh[1];
+    s0 = c1 ? bs[1] : bs[0]; s1 = c1 ? bs[2] : bs[1];
+  } else {
+  w_lo = kw[0]; w_hi = kw[1]; h_lo = kh[0]; h_hi = kh[1]; s0 = p[2 * NB]; s1 = p[2 * NB + 1];
 #pragma unroll
   for (int k = 1; k < NB; ++k) {
     const bool in = x >= (ROOT ? kh[k] : kw[k]);
@@ -62,6 +91,7 @@ __device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK
     h_hi = in ? kh[k + 1] : h_hi;
     s0 = in ? p[2 * NB + k] : s0;
     s1 = in ? p[2 * NB + k + 1] : s1;
+  }
   }
   const float w = w_hi - w_lo, h = h_hi - h_lo;
   const float rw = rcp_fast(w);
@@ -88,7 +118,7 @@ __device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK
   const float rden = rcp_fast(den);
   if (!ROOT) y = fmaf(h * fmaf(delta * th, th, d0 * t1), rden, h_lo);
   const float num = delta * delta * fmaf(d1 * th, th, fmaf(2.f * delta, t1, d0 * omt * omt));
-  const float l = logf(num * rden * rden);
+  const float l = FASTLOG ? LN2 * lg2_fast(num * rden * rden) : logf(num * rden * rden);
   lad = ROOT ? -l : l;
 }
 

@@ -14,7 +14,8 @@ from . import _lib
 
 __all__ = ["PackedNet", "affine_coupling", "spline_coupling", "ic_to_xyz", "ic_from_xyz", "ZPlan",
            "require_cuda_fp32", "config", "pipeline_status", "check_pipeline_status", "CdfTable", "cdf_map",
-           "ic_to_xyz_mapped", "ic_from_xyz_mapped", "RelPlan", "relic_to_xyz", "relic_from_xyz"]
+           "ic_to_xyz_mapped", "ic_from_xyz_mapped", "RelPlan", "relic_to_xyz", "relic_from_xyz", "split_cols",
+           "merge_cols"]
 
 
 def require_cuda_fp32(*tensors):
@@ -657,3 +658,49 @@ def relic_from_xyz(plan, xyz, dlogp_in=None):
                                 dlogp.data_ptr(), _stream())
     _lib.check(rc, "bgx_relic_from_xyz")
     return bonds, angles, torsions, fixed, dlogp
+
+
+# ------------------------------------------------------------------------------------------------
+# SplitFlow / MergeFlow by sizes along the last dim (bgx_split_merge)
+# ------------------------------------------------------------------------------------------------
+
+def _seg(t, B):
+    s = _lib.bgx_seg()
+    s.ptr, s.width, s.stride = t.data_ptr(), t.shape[1], t.stride(0) if B > 1 else t.shape[1]
+    return s
+
+
+def split_cols(x, sizes):
+    """``x [.., W]`` -> dense tensors of the given last-dim sizes, one launch."""
+    lib = _lib.load()
+    require_cuda_fp32(x)
+    if not 1 <= len(sizes) <= _lib.BGX_MAX_SEGS:
+        raise NotImplementedError(f"1..{_lib.BGX_MAX_SEGS} parts per split")
+    lead = x.shape[:-1]
+    x2 = _as_rows(x)
+    B = x2.shape[0]
+    parts = [torch.empty(B, int(w), dtype=torch.float32, device=x.device) for w in sizes]
+    if B > 0:
+        segs = (_lib.bgx_seg * _lib.BGX_MAX_SEGS)(*[_seg(p, B) for p in parts])
+        whole = _seg(x2, B)
+        _lib.check(lib.bgx_split_merge(B, C.byref(whole), len(parts), segs, 0, _stream()), "bgx_split_merge")
+    return [p.reshape(*lead, p.shape[1]) if len(lead) != 1 else p for p in parts]
+
+
+def merge_cols(parts):
+    """Concatenate tensors along the last dim, one launch."""
+    lib = _lib.load()
+    require_cuda_fp32(*parts)
+    if not 1 <= len(parts) <= _lib.BGX_MAX_SEGS:
+        raise NotImplementedError(f"1..{_lib.BGX_MAX_SEGS} parts per merge")
+    lead = parts[0].shape[:-1]
+    rows = [_as_rows(p) for p in parts]
+    B = rows[0].shape[0]
+    if any(r.shape[0] != B for r in rows):
+        raise ValueError("all tensors of a merge must share their batch shape")
+    out = torch.empty(B, sum(r.shape[1] for r in rows), dtype=torch.float32, device=rows[0].device)
+    if B > 0:
+        segs = (_lib.bgx_seg * _lib.BGX_MAX_SEGS)(*[_seg(r, B) for r in rows])
+        whole = _seg(out, B)
+        _lib.check(lib.bgx_split_merge(B, C.byref(whole), len(rows), segs, 1, _stream()), "bgx_split_merge")
+    return out.reshape(*lead, out.shape[1]) if len(lead) != 1 else out

@@ -138,13 +138,28 @@ class SplitFlow(Flow):
     def _apply_tuple(self, xs, inverse):
         if not inverse:
             (x,) = xs
+            if self._kernel_ok(x):
+                # dense halves let the coupling kernels move whole [128 x D] tiles with one bulk TMA
+                # copy each (strided views would fall back to element-wise staging): one launch
+                from . import engine
+                n = x.shape[-1]
+                rest = n - sum(self._sizes)
+                if rest < 0:
+                    raise ValueError(f"can't split x [{x.shape}] into sizes {self._sizes} along {self._split_dim}")
+                return tuple(engine.split_cols(x, list(self._sizes) + ([rest] if rest > 0 else [])))
             parts = tuple(self._split(x))
             if x.is_cuda:
-                # dense halves let the coupling kernels move whole [128 x D] tiles with one bulk TMA
-                # copy each (strided views would fall back to element-wise staging); costs one pass
                 parts = tuple(p.contiguous() for p in parts)
             return parts
+        if all(self._kernel_ok(x) for x in xs):
+            from . import engine
+            return (engine.merge_cols(list(xs)),)
         return (self._merge(*xs),)
+
+    def _kernel_ok(self, x):
+        return (self._indices is None and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 1
+                and self._split_dim in (-1, x.dim() - 1) and len(self._sizes) < 8
+                and not (torch.is_grad_enabled() and x.requires_grad))
 
     def _split(self, x):
         n = x.shape[self._split_dim]

@@ -24,6 +24,7 @@
  *   bgx_relic_to_xyz      replaces  RelativeInternalCoordinateTransformation._inverse (ic.py:435-513) and
  *                                   MixedCoordinateTransformation._inverse (ic.py:862-884, pca.py:83-107)
  *   bgx_relic_from_xyz    replaces  their _forward (ic.py:386-433, 836-860)
+ *   bgx_split_merge       replaces  SplitFlow._forward / MergeFlow by sizes (coupling.py:46-62, 107-110)
  *   bgx_pack_mlp          (no reference counterpart) re-lays nn.Linear weights for the kernels
  *
  * Conventions: plain pointers and sizes only, no torch types.  All device pointers are fp32,
@@ -279,6 +280,12 @@ int bgx_relic_to_xyz(const bgx_relplan* plan, int64_t batch, const float* bonds,
 int bgx_relic_from_xyz(const bgx_relplan* plan, int64_t batch, const float* xyz, float* bonds,
                        float* angles, float* torsions, float* fixed, const float* dlogp_in,
                        float* dlogp_out, void* stream);
+
+/* SplitFlow._forward / MergeFlow (bgflow/nn/flow/coupling.py:46-62, 107-110) by sizes along the last
+ * dim as one launch: column blocks of `whole` ([batch, width], row stride whole->stride) <-> `parts`
+ * (widths must add up to whole->width).  merge == 0 writes the parts, merge != 0 writes `whole`. */
+int bgx_split_merge(int64_t batch, const bgx_seg* whole, int32_t n_parts, const bgx_seg* parts, int merge,
+                    void* stream);
 
 /* ---- misc -------------------------------------------------------------------------------- */
 

@@ -285,3 +285,30 @@ def test_builder_style_stack_hidden128_on_tensor_cores(batch, kernel_mode):
     _cmp(dlogp, dref, 5e-4, 1e-4)
     for got, want in zip(zs, xs):
         _cmp(got, want.double(), 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("batch", [1, 63, 64, 65, 1000, 70001])
+def test_split_merge_kernel_matches_torch(batch):
+    """SplitFlow / MergeFlow by sizes run as one launch each (bgx_split_merge): bit-exact copies."""
+    from bgflow_b200 import _lib, engine
+    g = torch.Generator().manual_seed(batch)
+    x = torch.randn(batch, 66, generator=g).to(DEV)
+    n0 = _lib.launch_count()
+    a, b = bg.SplitFlow(33)._apply_tuple((x,), False)
+    assert _lib.launch_count() == n0 + 1
+    assert a.is_contiguous() and b.is_contiguous()
+    assert torch.equal(a, x[:, :33]) and torch.equal(b, x[:, 33:])
+    (back,) = bg.SplitFlow(33)._apply_tuple((b, a), True)
+    assert torch.equal(back, torch.cat([b, a], dim=-1))
+    # several parts, a strided source (column window of a wider tensor), leading batch dims
+    wide = torch.randn(batch, 100, generator=g).to(DEV)
+    src = wide[:, 7:7 + 40]
+    parts = engine.split_cols(src, [1, 17, 22])
+    for p, ref in zip(parts, torch.split(src, [1, 17, 22], dim=-1)):
+        assert torch.equal(p, ref)
+    assert torch.equal(engine.merge_cols(parts), src)
+    x3 = x.reshape(1, batch, 66)
+    *ys, d = bg.SplitFlow(10, 20)(x3)
+    assert [tuple(y.shape) for y in ys] == [(1, batch, 10), (1, batch, 20), (1, batch, 36)] and d.shape == (1, batch, 1)
+    p3 = bg.SplitFlow(10, 20)._apply_tuple((x3,), False)
+    assert all(torch.equal(p, r) for p, r in zip(p3, torch.split(x3, [10, 20, 36], dim=-1)))
