@@ -139,10 +139,11 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
       dl += (float)((double)na * 1.1447298858494002 + (double)(nt + 2) * 1.8378770664093453);
     }
     float sa, ca, sb, cb, sg, cg, s012, c012;
-    sincosf(alpha, &sa, &ca);
-    sincosf(acosf(beta), &sb, &cb);
-    sincosf(gamma, &sg, &cg);
-    sincosf(a012, &s012, &c012);
+    __sincosf(alpha, &sa, &ca);                 // arguments in [-pi, pi]: MUFU error ~4e-7
+    cb = beta;                                  // theta = acos(beta): cos = beta, sin = sqrt(1 - beta^2)
+    sb = sqrt_approx(fmaxf(1.f - beta * beta, 0.f));
+    __sincosf(gamma, &sg, &cg);
+    __sincosf(a012, &s012, &c012);
     // R = Rz(alpha) Rx(theta) Rz(gamma)   (ic_helper.py:344-368)
     const float m00 = ca, m01 = -sa * cb, m02 = sa * sb;
     const float m10 = sa, m11 = ca * cb, m12 = -ca * sb;
@@ -277,19 +278,20 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
       const float n12 = fmaxf(dot(r12, r12) * i12, a.eps);        // |r12| clamped like the reference
       float c = dot(r12, r32) * (i12 * i32);
       c = fminf(fmaxf(c, a.cmin), a.cmax);
-      float ang = acosf(c);
       const float sin2 = 1.f - c * c;
+      const float sin1 = sqrt_approx(sin2);
+      float ang = atan2_fast(sin1, c);                 // acos(c), c in [-1 + eps, 1 - eps]
       // torsion (ic_helper.py:220-278): b0 = xi - xj, b1 = xk - xj, b2 = xl - xk
       const V3 b2 = xl - xk;
       const V3 u = r32 * i32;
       const V3 v = r12 - u * dot(r12, u);
       const V3 w = b2 - u * dot(b2, u);
-      float tor = atan2f(dot(cross(u, v), w), dot(v, w));
+      float tor = atan2_fast(dot(cross(u, v), w), dot(v, w));
       if (a.normalize) {
         ang *= (1.f / PI_F);
         tor = (tor + PI_F) * (1.f / TWO_PI_F);
       }
-      dl -= __logf(n12 * n12 * sqrtf(sin2));     // 2 ln b + ln sin a
+      dl -= __logf(n12 * n12 * sin1);     // 2 ln b + ln sin a
       float ob = n12;
       if (a.marg) {
         float l0, l1, l2;
@@ -304,19 +306,19 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
         bo[a.off_b + r] = ob; an[a.off_a + r] = ang; to[r] = tor;
       }
     }
-    if (g == ng - 1 && !global) {
-      // fixed block (ic.py:419) and, for the mixed transform, its whitening (pca.py:83-91)
-      const int nf3 = 3 * a.n_fixed;
+    if (!global) {
+      // fixed block (ic.py:419) and, for the mixed transform, its whitening (pca.py:83-91): the
+      // threads of a sample share the atoms / the whitened components
       float* fo = a.fixed_out + row * a.fixed_w;
       float* Qf = Qs + (nb + na + nt) * LDF;
       if (a.keep == 0) {
-        for (int i = 0; i < a.n_fixed; ++i) {
+        for (int i = g; i < a.n_fixed; i += ng) {
           const V3 p = pos.get(a.fixed[i]);
           if (SMEM) { Qf[(3 * i) * LDF] = p.x; Qf[(3 * i + 1) * LDF] = p.y; Qf[(3 * i + 2) * LDF] = p.z; }
           else { fo[3 * i] = p.x; fo[3 * i + 1] = p.y; fo[3 * i + 2] = p.z; }
         }
       } else {
-        for (int k = 0; k < a.keep; ++k) {
+        for (int k = g; k < a.keep; k += ng) {
           float acc = 0.f;
           for (int i = 0; i < a.n_fixed; ++i) {
             const V3 p = pos.get(a.fixed[i]);
@@ -328,10 +330,9 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
           if (SMEM) Qf[k * LDF] = acc;
           else fo[k] = acc;
         }
-        dl += a.ld_whiten;
+        if (g == ng - 1) dl += a.ld_whiten;
       }
-      (void)nf3;
-      if (a.normalize) dl -= (float)((double)na * 1.1447298858494002 + (double)nt * 1.8378770664093453);
+      if (g == ng - 1 && a.normalize) dl -= (float)((double)na * 1.1447298858494002 + (double)nt * 1.8378770664093453);
     }
     if (g == ng - 1 && global) {
       const V3 p0 = pos.get(a.s0), p1 = pos.get(a.s1), p2 = pos.get(a.s2);
@@ -341,18 +342,18 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
       const V3 ra = p0 - p1;
       float c = dot(ra * (1.f / norm_c(ra, a.eps)), e12 * (1.f / d12));
       c = fminf(fmaxf(c, a.cmin), a.cmax);
-      float a012 = acosf(c);
-      const float sin012 = sqrtf(1.f - c * c);
+      const float sin012 = sqrt_approx(1.f - c * c);
+      float a012 = atan2_fast(sin012, c);
       // tripod (ic_helper.py:114-138): e1 = (p1-p0)/|.|, e2 = ((p2-p0) x e1)/|.|, e3 = e2 x e1
       const V3 e1 = e01 * (1.f / d01);
       V3 e2 = cross(p2 - p0, e1);
       e2 = e2 * (1.f / norm_c(e2, a.eps));
       const V3 e3 = cross(e2, e1);
       // basis (X, Y, Z) = (-e3, -e2, e1); euler (ic_helper.py:330-341)
-      float alpha = atan2f(e1.x, -e1.y);
+      float alpha = atan2_fast(e1.x, -e1.y);
       const float beta = e1.z;
-      float gamma = atan2f(-e3.z, -e2.z);
-      dl -= 2.f * logf(d01) + 2.f * logf(d12) + logf(sin012);
+      float gamma = atan2_fast(-e3.z, -e2.z);
+      dl -= __logf(d01 * d01 * d12 * d12 * sin012);
       if (a.normalize) {
         a012 *= (1.f / PI_F);
         alpha = (alpha + PI_F) * (1.f / TWO_PI_F);
