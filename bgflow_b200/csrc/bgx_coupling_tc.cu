@@ -107,7 +107,7 @@ __device__ __forceinline__ float do_dim(const TcArgs& a, const float (&p)[PS], f
   n_oob += (x < a.ck.left || x > a.ck.right) ? 1 : 0;
   x = fminf(fmaxf(x, a.ck.left), a.ck.right);
   float y, lad;
-  rqs_eval_reg<!INVERSE>(p, a.ck, x, y, lad);   // bgflow forward == root branch
+  rqs_eval_reg<!INVERSE, true>(p, a.ck, x, y, lad);   // bgflow forward == root branch; binary bin search, MUFU log-det
   *yslot = y;
   return lad;
 }

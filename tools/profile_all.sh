@@ -10,6 +10,8 @@ timeout 300 $NCU --set full --import-source on -k regex:spline_coupling_tc2 -s 1
 timeout 300 $NCU --set full --import-source on -k regex:affine_coupling_tc -s 10 -c 1 -o gpurun_out/r1_affine_tc \
   python bench.py --workload ala2_affine_d66_8blk --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --batch-per-gpu $B > gpurun_out/r1_affine_tc.log 2>&1
 timeout 300 $NCU --set full --import-source on -k regex:ic_ -s 2 -c 2 -o gpurun_out/r1_ic python tools/run_ic.py > gpurun_out/r1_ic.log 2>&1
+# SURVEY 8f kernels: cdf map (both directions), mapped IC tail (both), relative + mixed IC (both each), split, merge
+timeout 300 $NCU --set full --import-source on -k regex:"cdf_map|ic_|split_merge" -s 20 -c 10 -o gpurun_out/r1_tail python tools/run_tail.py > gpurun_out/r1_tail.log 2>&1
 BGX_TC_SINGLE_CTA=1 timeout 300 $NCU --set full --import-source on -k regex:spline_coupling_tc_kernel -s 10 -c 1 -o gpurun_out/r1_spline_tc1 \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --batch-per-gpu $B > gpurun_out/r1_spline_tc1.log 2>&1
 # launch lists of the bench command (shares of the step)
