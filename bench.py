@@ -299,6 +299,69 @@ def bench_tail(args, dev):
     return out
 
 
+def bench_config4(args, dev, rows=262144):
+    """Secondary measurement: BASELINE config 4 end to end at batch 262144 — the builder-exact augmented
+    Ala2 stack (tests/factory/test_generator_builder.py:45-66): uniform prior on (BONDS[21], ANGLES[20],
+    TORSIONS[19, circular], AUGMENTED[10]) -> 14 multi-tensor spline couplings (WrapPeriodic conditioners on
+    torsions) -> icdf maps of every field -> InverseFlow(GlobalIC) with constant origin / rotation."""
+    import math
+    import bgflow_b200 as bg
+    from oracle import ic as oic
+    torch.manual_seed(0)
+    width = {0: 21, 1: 20, 2: 19, 3: 10}
+
+    def coupling(what, on):
+        raw = sum(width[f] for f in on)
+        periodic, col = [], 0
+        for f in on:
+            if f == 2:
+                periodic += list(range(col, col + width[f]))
+            col += width[f]
+        circular = what == 2
+        net = bg.DenseNet([raw + len(periodic), 128, 128, 24 * width[what] + (0 if circular else width[what])],
+                          activation=torch.nn.SiLU())
+        if periodic:
+            net = bg.WrapPeriodic(net, left=0.0, right=1.0, indices=periodic)
+        return bg.CouplingFlow(bg.ConditionalSplineTransformer(net, is_circular=circular),
+                               transformed_indices=(what,), cond_indices=tuple(on))
+    layers = []
+    for _ in range(4):
+        layers += [coupling(2, (3,)), coupling(3, (2,))]
+    for _ in range(2):
+        layers += [coupling(0, (1,)), coupling(1, (0,))]
+    layers += [coupling(1, (2, 3)), coupling(0, (1, 2, 3))]
+    one = lambda n, v=1.0: torch.full((n,), v, device=dev)
+    marg = [bg.TruncatedNormalDistribution(one(21), one(21), torch.tensor(1e-5, device=dev), torch.tensor(math.inf, device=dev)),
+            bg.TruncatedNormalDistribution(one(20, 0.5), one(20), torch.tensor(1e-5, device=dev), torch.tensor(1.0, device=dev)),
+            bg.SloppyUniform(torch.zeros(19, device=dev), one(19)),
+            torch.distributions.Normal(torch.zeros(10, device=dev), one(10))]
+    layers += [bg.WrapFlow(bg.InverseFlow(bg.CDFTransform(m)), (i,)) for i, m in enumerate(marg)]
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    layers += [bg.SetConstantFlow([4], [torch.zeros(1, 3, device=dev)]),
+               bg.SetConstantFlow([5], [torch.tensor([0.5, 0.5, 0.5], device=dev)]),
+               bg.WrapFlow(bg.InverseFlow(ic), indices=[0, 1, 2, 4, 5], out_indices=(0,))]
+    flow = bg.fuse_domain_maps(bg.SequentialFlow(layers).to(dev))
+    g = torch.Generator().manual_seed(1)
+    us = [torch.rand(rows, w, generator=g).to(dev) for w in (21, 20, 19, 10)]
+    from bgflow_b200 import _lib
+    with torch.no_grad():
+        for _ in range(3):
+            flow(*us)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            flow(*us)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    return {"samples_per_s": rows / (ms * 1e-3), "ms_per_pass": ms, "rows": rows,
+            "kernel_launches_per_pass": (_lib.launch_count() - n0) // args.steps,
+            "what": "uniform prior -> 14 multi-tensor spline couplings -> icdf maps -> global IC -> (xyz[66], aug[10]), "
+                    "forward + log|det J|"}
+
+
 def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     """Secondary measurement (BASELINE config 5, "KL-train grad allreduce"): reverse-KL steps on a
     Gaussian target — kernel forward, recompute backward, ONE flat gradient all-reduce (NCCL when
@@ -527,7 +590,8 @@ def main():
             "gpu_pytorch_port": {"value": time_gpu_torch_port(blocks, kind, dim, 65536, dev), "unit": "samples/s",
                                  "sample": "65536 rows; oracle/flows.py op sequence on CUDA tensors (the reference's "
                                            "single-GPU PyTorch path, restated)"},
-            "ic_ala2": bench_ic(args, dev), "ic_tail": bench_tail(args, dev)}
+            "ic_ala2": bench_ic(args, dev), "ic_tail": bench_tail(args, dev),
+            "config4_pipeline": bench_config4(args, dev)}
     if args.extras:
         tr = bench_train(args, flow, kind, dim, dev, run_timed, world)
         if rank == 0:

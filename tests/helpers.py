@@ -45,3 +45,39 @@ def stack_from(blocks, split, device):
         layers.append(bg.SwapFlow())
     layers.append(bg.MergeFlow(split))
     return bg.SequentialFlow(layers).to(device)
+
+
+def config4_blocks(dtype=torch.float32, seed=11, hidden=(128, 128), n_bins=8):
+    """BASELINE config 4, the builder-exact augmented Ala2 stack of
+    tests/factory/test_generator_builder.py:45-66: state (BONDS[21], ANGLES[20], TORSIONS[19,
+    circular], AUGMENTED[10]); 4 x (T <- Aug, Aug <- T), 2 x (B <- A, A <- B), A <- (T, Aug),
+    B <- (A, T, Aug); conditioners DenseNet(in, 128, 128, out) SiLU, torsions enter conditioners
+    through WrapPeriodic (cos / sin), 8-bin splines.  Returns oracle block dicts."""
+    from oracle import flows as of
+    g = torch.Generator().manual_seed(seed)
+    B_, A_, T_, X_ = 0, 1, 2, 3
+    width = {B_: 21, A_: 20, T_: 19, X_: 10}
+
+    def block(what, on):
+        d_t = width[what]
+        raw = sum(width[f] for f in on)
+        periodic, col = [], 0
+        for f in on:
+            if f == T_:
+                periodic += list(range(col, col + width[f]))
+            col += width[f]
+        circular = what == T_
+        n_out = 3 * n_bins * d_t + (0 if circular else d_t)
+        net = of.make_mlp([raw + len(periodic), *hidden, n_out], "silu", g, dtype)
+        if periodic:
+            net.periodic = (periodic, 0.0, 1.0)
+        return {"kind": "spline", "transformed": (what,), "cond": tuple(on), "params_net": net,
+                "is_circular": True if circular else None}
+
+    blocks = []
+    for _ in range(4):
+        blocks += [block(T_, (X_,)), block(X_, (T_,))]
+    for _ in range(2):
+        blocks += [block(B_, (A_,)), block(A_, (B_,))]
+    blocks += [block(A_, (T_, X_)), block(B_, (A_, T_, X_))]
+    return blocks

@@ -1,0 +1,98 @@
+"""BASELINE config 4 end to end: builder-exact augmented Ala2 stack — 14 multi-tensor
+spline couplings (circular torsions, WrapPeriodic conditioners) -> icdf maps of every field ->
+InverseFlow(GlobalInternalCoordinateTransformation) with origin 0 / rotation (0.5, 0.5, 0.5) —
+through the fused kernels, against the oracle composed in fp64 on the CPU.
+
+Tolerances: the 14 couplings stay inside the coupling bar (1e-4 on [0,1]-valued fields, 1e-3 on
+dlogp); the icdf maps then amplify an input error by 1/pdf (up to ~30x for |z| < 2.5) and the
+chain of 19 placements by the bond lengths (~1..3 here), so Cartesian coordinates are checked at
+the median (2e-5) and at the 99th percentile (1e-3) rather than at the maximum."""
+
+import numpy as np
+import pytest
+import torch
+
+import bgflow_b200 as bg
+from bgflow_b200 import _lib
+from oracle import cdf as ocdf, flows as of, ic as oic
+from helpers import config4_blocks, transformer_from
+from test_gpu_cdf import marginals
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+WIDTHS = (21, 20, 19, 10)
+NAMES = ("bonds", "angles", "torsions", "augmented")
+
+
+def build(blocks, fuse):
+    ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    m = marginals()
+    layers = [bg.CouplingFlow(transformer_from(b, DEV), transformed_indices=b["transformed"], cond_indices=b["cond"])
+              for b in blocks]
+    layers += [bg.WrapFlow(bg.InverseFlow(bg.CDFTransform(m[n])), (i,)) for i, n in enumerate(NAMES)]
+    layers += [bg.SetConstantFlow([4], [torch.zeros(1, 3, device=DEV)]),
+               bg.SetConstantFlow([5], [torch.tensor([0.5, 0.5, 0.5], device=DEV)]),
+               bg.WrapFlow(bg.InverseFlow(ic), indices=[0, 1, 2, 4, 5], out_indices=(0,))]
+    flow = bg.SequentialFlow(layers).to(DEV)
+    return bg.fuse_domain_maps(flow) if fuse else flow
+
+
+def oracle_pipeline(blocks64, us):
+    xs, dlogp = list(us), 0
+    for b in blocks64:
+        xs, d = of.coupling_block(b, xs)
+        dlogp = dlogp + d
+    fields = list(xs)
+    om = ocdf.ic_marginals(dict(zip(NAMES, WIDTHS)), torch.float64)
+    for i, n in enumerate(NAMES):
+        xs[i], d = ocdf.cdf_transform(om[n], xs[i], inverse=True)
+        dlogp = dlogp + d
+    B = xs[0].shape[0]
+    xyz, d = oic.ic_to_xyz(oic.make_plan(oic.ALA2_GLOBAL_Z), xs[0], xs[1], xs[2],
+                           torch.zeros(B, 1, 3, dtype=torch.float64), torch.full((B, 3), 0.5, dtype=torch.float64))
+    return fields, xyz, xs[3], dlogp + d
+
+
+@pytest.mark.parametrize("batch,fuse", [(257, False), (257, True), (4608, True)])
+def test_config4_pipeline_matches_oracle(batch, fuse):
+    blocks = config4_blocks(torch.float32)
+    blocks64 = config4_blocks(torch.float64)
+    flow = build(blocks, fuse)
+    g = torch.Generator().manual_seed(batch)
+    us = [torch.rand(batch, w, generator=g) for w in WIDTHS]               # the builder's uniform prior
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        xyz, aug, dlogp = flow(*(u.to(DEV) for u in us))
+    n_launch = _lib.launch_count() - n0
+    assert xyz.shape == (batch, 66) and aug.shape == (batch, 10) and dlogp.shape == (batch, 1)
+    fields, xyz_ref, aug_ref, dlogp_ref = oracle_pipeline(blocks64, [u.double() for u in us])
+    # well-conditioned samples: every field value away from the eps-clamped ends of the icdf maps
+    ok = torch.stack([((f > 2e-3) & (f < 1 - 2e-3)).all(-1) for f in fields]).all(0).numpy()
+    assert ok.mean() > 0.6
+    err = (xyz.cpu().double() - xyz_ref).abs().numpy()[ok]
+    assert np.median(err) < 2e-5 and np.quantile(err, 0.99) < 1e-3, (np.median(err), np.quantile(err, 0.99), err.max())
+    np.testing.assert_allclose(aug.cpu().double().numpy()[ok], aug_ref.numpy()[ok], atol=2e-3, rtol=1e-3)
+    derr = (dlogp.cpu().double() - dlogp_ref).abs().numpy()[ok]
+    assert np.median(derr) < 2e-4 and np.quantile(derr, 0.99) < 1e-2, (np.median(derr), derr.max())
+    if fuse:
+        # 14 couplings (+ segment gathers are torch copies) + one cdf launch (augmented) + one mapped-IC launch
+        assert n_launch == 16, n_launch
+
+
+def test_config4_energy_direction_round_trip():
+    """generator.energy(x): xyz -> ICs -> cdf maps -> inverse couplings; composed with the sampling
+    direction it must return the prior sample and the negated log-det."""
+    blocks = config4_blocks(torch.float32)
+    flow = build(blocks, fuse=True)
+    g = torch.Generator().manual_seed(3)
+    us = [(torch.rand(2000, w, generator=g) * 0.9 + 0.05).to(DEV) for w in WIDTHS]
+    with torch.no_grad():
+        xyz, aug, dlogp = flow(*us)
+        *back, dinv = flow(xyz, aug, inverse=True)
+    for u, b, tol in zip(us, back, (2e-3, 2e-3, 2e-3, 2e-3)):
+        e = (u - b).abs()
+        if u.shape[1] == 19:
+            e = torch.minimum(e, 1 - e)                      # torsions are circular
+        assert float(e.median()) < 1e-5 and float(e.quantile(0.99)) < tol, (u.shape, float(e.max()))
+    s = (dlogp + dinv).abs()
+    assert float(s.median()) < 1e-3 and float(s.quantile(0.99)) < 5e-2
