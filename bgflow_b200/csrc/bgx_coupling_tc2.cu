@@ -35,6 +35,7 @@ constexpr uint32_t T2_SLOT_BYTES = 2 * T2_TILE_BYTES;      // two bf16 terms of 
 constexpr int T2_ACC = 0, T2_A = 128, T2_A_STRIDE = 64;
 constexpr int T2_NB = 8, T2_PS = 3 * T2_NB + 1, T2_DPP = 5;
 constexpr int T2_BPAD = 28;           // last-layer bias: 25 parameters per dim padded to 7 float4
+constexpr int T2_WIDE_MMA_DEFAULT = 1;   // BGX_T2_WIDE_MMA=0: lane-0-only issue loop (first version, A/B switch)
 constexpr int T2_FAST_DEFAULT = 1;   // BGX_T2_FAST=0/1: see the kernel comment
 
 
@@ -55,6 +56,7 @@ struct T2Args {
   int* status;
   long long ntiles;
   int bias_floats;
+  int wide_mma;      // all lanes of the MMA warp run the issue loop, one elected lane issues
 };
 
 struct alignas(16) T2Smem {
@@ -193,6 +195,57 @@ __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(cons
         if (a.status && (spin & 0xfff) == 0xfff && *(volatile int*)a.status) break;
       }
       if (y_store_next < n_my && a.status) atomicExch(a.status, 1);
+    }
+    __syncwarp();
+  } else if (warp == 9 && a.wide_mma) {
+    // ------------------------------------------------------------------ MMA issuer, warp-wide (see bgx_tc.cuh)
+    {
+      const uint32_t idesc = idesc_bf16(128, 128);
+      int slot = 0;
+      uint32_t ph_full[2] = {0, 0};
+      uint32_t ph_x = 0, ph_a = 0, ph_e = 0;
+      bool first = true;
+      for (long long it = 0; it < n_my; ++it) {
+        for (int l = 0; l < L; ++l) {
+          if (l == 0) { mbar_wait(&S->x_ready, ph_x, a.status); ph_x ^= 1; }
+          else { mbar_wait(&S->a_ready, ph_a, a.status); ph_a ^= 1; }
+          const bool last = (l == L - 1);
+          const int nch = last ? a.npass : 1;
+          const int kt = a.ktiles[l];
+          const int ksteps_total = (a.net.K[l] + 15) / 16;
+          for (int c = 0; c < nch; ++c) {
+            // the single accumulator must have been drained: chunk c-1 (or the previous tile's last chunk)
+            const bool need = last ? (c >= 1) : (l == 0 && !first);
+            if (need) { mbar_wait(&S->acc_empty, ph_e, a.status); ph_e ^= 1; }
+            tc_fence_after();
+            uint32_t acc = 0;
+            for (int t = 0; t < kt; ++t) {
+              mbar_wait(&S->full[slot], ph_full[slot], a.status);
+              ph_full[slot] ^= 1;
+              const uint32_t b1 = smem_u32(ring + (size_t)slot * T2_SLOT_BYTES), b2 = b1 + T2_TILE_BYTES;
+              slot ^= 1;
+              tc_fence_after();
+              const int nk = min(4, ksteps_total - t * 4);
+              // descriptors of the k-steps differ only in the 16-byte-unit start address (+2 per step)
+              const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);
+              const uint32_t a1 = tmem + T2_A + (uint32_t)(t * 32), a2 = a1 + T2_A_STRIDE;
+              if (nk == 4) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma3_bf16x3_elect(tmem + T2_ACC, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc,
+                                    ks == 0 ? acc : 1u);
+              } else {
+                for (int ks = 0; ks < nk; ++ks)
+                  mma3_bf16x3_elect(tmem + T2_ACC, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc,
+                                    ks == 0 ? acc : 1u);
+              }
+              acc = 1;
+            }
+            mma_commit_elect(&S->acc_full);
+          }
+        }
+        first = false;
+      }
     }
     __syncwarp();
   } else if (warp == 9) {
@@ -445,6 +498,10 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
     bias_floats += (l == L - 1) ? (net->Np[l] / 128) * T2_DPP * T2_BPAD : net->Np[l];   // room for the padded layout
   }
   a.bias_floats = bias_floats;
+  {
+    static const int wide = [] { const char* e = getenv("BGX_T2_WIDE_MMA"); return e ? atoi(e) : T2_WIDE_MMA_DEFAULT; }();
+    a.wide_mma = wide;
+  }
   a.npass = net->N[L - 1] / 128;
   a.inverse = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
   SplineParams sp;

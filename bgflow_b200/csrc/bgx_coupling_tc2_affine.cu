@@ -7,6 +7,7 @@
 //   net 0: x -> hidden (ACC) -> mu (ACC, N = round16(D_t)) -> +bias -> shared memory
 //   net 1: x -> hidden (ACC) -> s  (ACC)                    -> y' = y * exp(tanh(s) alpha) + mu
 #include <cstdlib>
+#include <type_traits>
 
 #include "bgx_coupling.cuh"
 #include "bgx_tc.cuh"
@@ -38,6 +39,7 @@ struct A2Args {
   float* dlogp_out;
   int* status;
   long long ntiles;
+  int wide_mma;      // all lanes of the MMA warp run the issue loop, one elected lane issues
   int bias_floats;     // per net
 };
 
@@ -156,8 +158,21 @@ __global__ void __launch_bounds__(A2_THREADS, 2) affine_coupling_tc2_kernel(cons
     }
     __syncwarp();
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer.  WIDE: every lane runs the
+    // (warp-uniform) loop and one elected lane issues (bgx_tc.cuh: mma3_bf16x3_elect); otherwise lane 0 alone.
+    auto issue = [&](auto wide_tag) {
+      constexpr bool WIDE = decltype(wide_tag)::value;
+      if (!WIDE && lane != 0) return;
+      auto mma3 = [&](uint32_t x1, uint32_t x2, uint64_t e1, uint64_t e2, uint32_t idesc, uint32_t acc) {
+        if (WIDE) {
+          mma3_bf16x3_elect(tmem + A2_ACC, x1, x2, e1, e2, idesc, acc);
+        } else {
+          mma_bf16_ts(tmem + A2_ACC, x1, e2, idesc, acc);
+          mma_bf16_ts(tmem + A2_ACC, x2, e1, idesc, 1);
+          mma_bf16_ts(tmem + A2_ACC, x1, e1, idesc, 1);
+        }
+      };
+    {
       const uint32_t idesc_h = idesc_bf16(128, 128), idesc_f = idesc_bf16(128, a.nfin);
       int slot = 0;
       uint32_t ph_full[2] = {0, 0};
@@ -181,21 +196,27 @@ __global__ void __launch_bounds__(A2_THREADS, 2) affine_coupling_tc2_kernel(cons
               slot ^= 1;
               tc_fence_after();
               const int nk = min(4, ksteps_total - t * 4);
-              for (int ks = 0; ks < nk; ++ks) {
-                const uint32_t kcol = (uint32_t)(t * 32 + ks * 8);
-                const uint32_t a1 = tmem + A2_A + kcol, a2 = a1 + A2_A_STRIDE;
-                const uint64_t d1 = smem_desc_sw128(b1 + ks * 32), d2 = smem_desc_sw128(b2 + ks * 32);
-                mma_bf16_ts(tmem + A2_ACC, a1, d2, idesc, acc);
-                mma_bf16_ts(tmem + A2_ACC, a2, d1, idesc, 1);
-                mma_bf16_ts(tmem + A2_ACC, a1, d1, idesc, 1);
-                acc = 1;
+              const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);   // +2 per k-step (16-byte units)
+              const uint32_t a1 = tmem + A2_A + (uint32_t)(t * 32), a2 = a1 + A2_A_STRIDE;
+              if (nk == 4) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma3(a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
+              } else {
+                for (int ks = 0; ks < nk; ++ks)
+                  mma3(a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
               }
+              acc = 1;
             }
-            mma_commit(&S->acc_full);
+            if (WIDE) mma_commit_elect(&S->acc_full);
+            else mma_commit(&S->acc_full);
           }
         first = false;
       }
     }
+    };
+    if (a.wide_mma) issue(std::true_type{});
+    else issue(std::false_type{});
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps (0..7)
@@ -413,6 +434,10 @@ int affine_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* shift, 
   a.dlogp_out = io->dlogp_out;
   a.status = status;
   a.ntiles = (a.B + A2_TM - 1) / A2_TM;
+  {
+    static const int wide = [] { const char* e = getenv("BGX_T2_WIDE_MMA"); return e ? atoi(e) : 1; }();
+    a.wide_mma = wide;
+  }
   const size_t smem = 1024 + A2_SLOTS * A2_SLOT_BYTES + sizeof(A2Smem) +
                       sizeof(float) * (2 * (size_t)bias_floats + (size_t)A2_TM * (a.D_t + a.K0raw)) + 64;
   static int sm_count = 0;

@@ -158,6 +158,35 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-wide variants: EVERY lane of the issuing warp executes the surrounding (warp-uniform) control
+// flow and operand arithmetic; one elected lane issues.  Keeps operands out of the divergent
+// lane-0-only path, where the compiler wraps each tcgen05 instruction in an elect / broadcast loop.
+__device__ __forceinline__ void mma_bf16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The three products of one k-step of the bf16x3 scheme (a1.b2, a2.b1, a1.b1) under ONE election:
+// seven operands cross into the uniform datapath once instead of twelve.
+__device__ __forceinline__ void mma3_bf16x3_elect(uint32_t d_tmem, uint32_t a1, uint32_t a2, uint64_t d1, uint64_t d2,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %6, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %4, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, 1;\n\t}" ::"r"(d_tmem),
+      "r"(a1), "r"(a2), "l"(d1), "l"(d2), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // two floats -> packed bf16x2 (lo = element k, hi = element k+1), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t d;
