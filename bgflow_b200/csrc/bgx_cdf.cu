@@ -64,23 +64,33 @@ __global__ void __launch_bounds__(CT) cdf_map_kernel(const CdfArgs a) {
         const int c = t - m * cw;
         const bgx_cdf_col cc = cols[c];
         // CU loads in flight per thread: one-at-a-time loads would leave the kernel bound by DRAM
-        // latency (40 warps x 128 B per SM in flight), not by bandwidth
-        for (; m < nrow; m += CU * rpp) {
+        // latency (40 warps x 128 B per SM in flight), not by bandwidth.  Pointer stepping, no
+        // per-element index arithmetic; the (< CU rows) remainder goes one row at a time.
+        const float* pin = gin + m * si + c;
+        float* pout = gout + m * so + c;
+        float* pld = ld_s + (used + c) * CLD + m;
+        const int istep = rpp * si, ostep = rpp * so;
+        for (; m + (CU - 1) * rpp < nrow; m += CU * rpp) {
           float v[CU];
 #pragma unroll
-          for (int u = 0; u < CU; ++u)
-            if (m + u * rpp < nrow) v[u] = __ldg(gin + (m + u * rpp) * si + c);
+          for (int u = 0; u < CU; ++u) v[u] = __ldg(pin + u * istep);
 #pragma unroll
           for (int u = 0; u < CU; ++u) {
-            const int mu = m + u * rpp;
-            if (mu < nrow) {
-              float y, ld;
-              if (INVERSE) cdf_inverse(cc, a.clamp, v[u], y, ld);
-              else cdf_forward(cc, a.clamp, v[u], y, ld);
-              gout[mu * so + c] = y;
-              ld_s[(used + c) * CLD + mu] = ld;
-            }
+            float y, ld;
+            if (INVERSE) cdf_inverse(cc, a.clamp, v[u], y, ld);
+            else cdf_forward(cc, a.clamp, v[u], y, ld);
+            pout[u * ostep] = y;
+            pld[u * rpp] = ld;
           }
+          pin += CU * istep; pout += CU * ostep; pld += CU * rpp;
+        }
+        for (; m < nrow; m += rpp) {
+          float y, ld;
+          if (INVERSE) cdf_inverse(cc, a.clamp, __ldg(pin), y, ld);
+          else cdf_forward(cc, a.clamp, __ldg(pin), y, ld);
+          *pout = y;
+          *pld = ld;
+          pin += istep; pout += ostep; pld += rpp;
         }
       }
       used += cw;

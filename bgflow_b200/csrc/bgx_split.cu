@@ -30,29 +30,26 @@ __global__ void __launch_bounds__(ST) split_merge_kernel(const SplitArgs a) {
     const int ws = a.whole.stride, ps = a.parts[p].stride;
     const float* whole = a.whole.ptr + row0 * ws + col0;
     const float* part = a.parts[p].ptr + row0 * ps;
-    for (int c0 = 0; c0 < w; c0 += ST) {           // (parts wider than the CTA: column windows)
-      const int cw = min(ST, w - c0);
-      // thread t owns one column of the window and every rpp-th row: no per-element index
-      // arithmetic, and a pass still touches rpp * cw consecutive floats of a dense part
-      const int rpp = ST / cw;
-      if (t < rpp * cw) {
-        int m = t / cw;
-        const int c = c0 + t - m * cw;
-        const float* src = MERGE ? part + m * ps + c : whole + m * ws + c;
-        float* dst = const_cast<float*>(MERGE ? whole + m * ws + c : part + m * ps + c);
-        const int sstep = rpp * (MERGE ? ps : ws), dstep = rpp * (MERGE ? ws : ps);
-        for (; m < nrow; m += SU * rpp) {
-          float v[SU];
+    int m = t / w, c = t - m * w;
+    const int dm = ST / w, dc = ST - dm * w;
+    while (m < nrow) {          // SU loads in flight per thread before the first store
+      int ms[SU], cs[SU];
+      float v[SU];
 #pragma unroll
-          for (int u = 0; u < SU; ++u)
-            if (m + u * rpp < nrow) v[u] = __ldg(src + u * sstep);
-#pragma unroll
-          for (int u = 0; u < SU; ++u)
-            if (m + u * rpp < nrow) dst[u * dstep] = v[u];
-          src += SU * sstep;
-          dst += SU * dstep;
-        }
+      for (int u = 0; u < SU; ++u) {
+        ms[u] = m; cs[u] = c;
+        m += dm; c += dc;
+        if (c >= w) { c -= w; ++m; }
       }
+#pragma unroll
+      for (int u = 0; u < SU; ++u)
+        if (ms[u] < nrow) v[u] = MERGE ? __ldg(part + ms[u] * ps + cs[u]) : __ldg(whole + ms[u] * ws + cs[u]);
+#pragma unroll
+      for (int u = 0; u < SU; ++u)
+        if (ms[u] < nrow) {
+          if (MERGE) const_cast<float*>(whole)[ms[u] * ws + cs[u]] = v[u];
+          else const_cast<float*>(part)[ms[u] * ps + cs[u]] = v[u];
+        }
     }
     col0 += w;
   }
