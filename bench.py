@@ -205,7 +205,7 @@ def time_gpu_torch_port(blocks, kind, dim, rows, dev):
 def bench_ic(args, dev):
     """Secondary measurement: the Z-matrix <-> Cartesian kernels on Ala2 (532 algorithmic bytes/sample)."""
     import bgflow_b200 as bg
-    from oracle import ic as oic
+    from bgflow_b200 import fixtures as oic
     B = args.batch_per_gpu
     ic = bg.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
     g = torch.Generator().manual_seed(1)
@@ -240,7 +240,7 @@ def bench_tail(args, dev):
     bytes/sample); the relative / mixed IC kernels."""
     import math
     import bgflow_b200 as bg
-    from oracle import ic as oic
+    from bgflow_b200 import fixtures as oic
     B = args.batch_per_gpu
     pk = peaks()
     one = lambda n, v=1.0: torch.full((n,), v, device=dev)
@@ -306,7 +306,7 @@ def bench_config4(args, dev, rows=262144):
     torsions) -> icdf maps of every field -> InverseFlow(GlobalIC) with constant origin / rotation."""
     import math
     import bgflow_b200 as bg
-    from oracle import ic as oic
+    from bgflow_b200 import fixtures as oic
     torch.manual_seed(0)
     width = {0: 21, 1: 20, 2: 19, 3: 10}
 

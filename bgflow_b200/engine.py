@@ -435,13 +435,6 @@ class CdfTable:
             self._dev[key] = self._host.to(device)
         return self._dev[key]
 
-    @staticmethod
-    def concat(tables):
-        out = CdfTable([])
-        out.n = sum(t.n for t in tables)
-        out._host = torch.cat([t._host[:t.n * C.sizeof(_lib.bgx_cdf_col)] for t in tables])
-        return out
-
 
 def cdf_map(tensors, table, inverse=False, eps=1e-7, dlogp_in=None):
     """Map a list of ``[B, w_i]`` tensors through their per-column CDFs (``inverse``: icdfs) in one
