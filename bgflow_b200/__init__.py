@@ -19,6 +19,7 @@ from .cdf import (CDFTransform, DistributionTransferFlow, ConstrainGaussianFlow,
 from .bg import (BoltzmannGenerator, NormalDistribution, UniformDistribution, unnormalized_kl_div,
                  unormalized_nll, log_weights, log_weights_given_latent, effective_sample_size,
                  sampling_efficiency)
+from .convert import from_reference
 from . import engine, _lib, distributed
 
 __version__ = "0.1.0"

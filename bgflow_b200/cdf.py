@@ -162,7 +162,8 @@ def marginal_columns(distribution, width):
     """Column specs ``(kind, a, b, lower, upper)`` for ``engine.CdfTable`` or None if the
     distribution has no kernel (duck-typed, so the reference's own distribution objects work)."""
     d = distribution
-    if all(hasattr(d, a) for a in ("_mu", "_logsigma", "_lower_bound", "_upper_bound")):
+    # (isinstance, not hasattr: the reference's SloppyUniform.__getattr__ answers None for any name)
+    if all(isinstance(getattr(d, a, None), torch.Tensor) for a in ("_mu", "_logsigma", "_lower_bound", "_upper_bound")):
         mu, sg = _per_column(d._mu, width), _per_column(torch.exp(d._logsigma), width)
         lo, hi = _per_column(d._lower_bound, width), _per_column(d._upper_bound, width)
         return [(_lib.DIST_TRUNCNORMAL, m, s, l, h) for m, s, l, h in zip(mu, sg, lo, hi)]
