@@ -125,3 +125,47 @@ def test_relative_mixed_generator_and_fallthrough(ref):
     prior = ref.NormalDistribution(2)
     gen = bg.from_reference(ref.BoltzmannGenerator(prior, rflow, None))
     assert isinstance(gen, bg.BoltzmannGenerator) and gen.prior is prior and isinstance(gen.flow, bg.SequentialFlow)
+
+
+def test_real_builder_generator_converts(ref):
+    """BASELINE config 4 built by the REFERENCE's own BoltzmannGeneratorBuilder
+    (tests/factory/test_generator_builder.py:45-66, OpenMM-free z-matrix, no target): every coupling
+    becomes a kernel-backed one with the conditioner shapes SURVEY.md 8d lists, and the builder tail
+    (icdf maps + constants + map to Cartesian) collapses to [constants, one multi-field icdf, MappedICTail]."""
+    import bgflow_b200 as bg
+    from bgflow_b200 import cdf as bcdf
+    from bgflow import BoltzmannGeneratorBuilder, ShapeDictionary, BONDS, ANGLES, TORSIONS, AUGMENTED
+    from oracle import ic as oic
+    crd = ref.GlobalInternalCoordinateTransformation(oic.ALA2_GLOBAL_Z)
+    shape_info = ShapeDictionary.from_coordinate_transform(crd, dim_augmented=10)
+    b = BoltzmannGeneratorBuilder(shape_info, target=None, device=torch.device("cpu"), dtype=torch.float32)
+    for _ in range(4):
+        b.add_condition(TORSIONS, on=AUGMENTED)
+        b.add_condition(AUGMENTED, on=TORSIONS)
+    for _ in range(2):
+        b.add_condition(BONDS, on=ANGLES)
+        b.add_condition(ANGLES, on=BONDS)
+    b.add_condition(ANGLES, on=(TORSIONS, AUGMENTED))
+    b.add_condition(BONDS, on=(ANGLES, TORSIONS, AUGMENTED))
+    b.add_map_to_ic_domains()
+    b.add_map_to_cartesian(crd)
+    gen = b.build_generator()
+    fast = bg.from_reference(gen)
+    blocks = list(fast.flow)
+    couplings = [blk for blk in blocks if isinstance(blk, bg.CouplingFlow)]
+    assert len(couplings) == 14 and all(isinstance(c.transformer, bg.ConditionalSplineTransformer) for c in couplings)
+    shapes = []
+    for c in couplings:
+        net = c.transformer._params_net
+        inner = net.net if isinstance(net, bg.WrapPeriodic) else net
+        assert isinstance(inner, bg.DenseNet)
+        lin = [m for m in inner._layers if isinstance(m, torch.nn.Linear)]
+        assert [l.out_features for l in lin[:-1]] == [128, 128]
+        shapes.append((lin[0].in_features, lin[-1].out_features, isinstance(net, bg.WrapPeriodic)))
+    assert shapes == ([(10, 456, False), (38, 250, True)] * 4 + [(20, 525, False), (21, 500, False)] * 2
+                      + [(48, 500, True), (68, 525, True)])
+    assert [type(x).__name__ for x in blocks[14:]] == ["SetConstantFlow", "SetConstantFlow", "InverseFlow", "WrapFlow"]
+    assert isinstance(blocks[16]._delegate, bcdf.MultiCDFFlow) and blocks[16]._delegate._indices == [3]
+    assert isinstance(blocks[17]._flow, bcdf.MappedICTail)
+    assert all(a is b_ for a, b_ in zip(fast.flow.parameters(), gen.flow.parameters()))
+    assert fast.prior is gen.prior
