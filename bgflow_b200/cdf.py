@@ -371,13 +371,18 @@ class MappedICTail(Flow):
         self._table = None
 
     def _get_table(self):
-        if self._table is None:
+        # rebuilt when a marginal's tensors change (learnable marginals after an optimiser step, .to())
+        key = tuple((t.data_ptr(), t._version) for d in self._marginals for t in _dist_tensors(d))
+        if self._table is None or self._table[0] != key:
             ic = self._ic
             cols = []
             for d, w in zip(self._marginals, (ic.dim_bonds, ic.dim_angles, ic.dim_torsions)):
                 cols.extend(marginal_columns(d, w))
-            self._table = engine.CdfTable(cols)
-        return self._table
+            self._table = (key, engine.CdfTable(cols))
+        return self._table[1]
+
+    def _learnable(self):
+        return any(t.requires_grad for d in self._marginals for t in _dist_tensors(d))
 
     def _unfused(self):
         return SequentialFlow([InverseFlow(MultiCDFFlow(self._marginals, indices=(0, 1, 2), eps=self._eps)),
@@ -385,13 +390,13 @@ class MappedICTail(Flow):
 
     def _forward(self, bonds, angles, torsions, x0, R, _dlogp_acc=None, **kwargs):
         ins = (bonds, angles, torsions, x0, R)
-        if torch.is_grad_enabled() and any(t.requires_grad for t in ins):
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in ins) or self._learnable()):
             *out, dlogp = self._unfused()(*ins)
             return (*out, dlogp if _dlogp_acc is None else _dlogp_acc + dlogp)
         return engine.ic_to_xyz_mapped(self._ic._plan, self._get_table(), self._eps, *ins, dlogp_in=_dlogp_acc)
 
     def _inverse(self, xyz, _dlogp_acc=None, **kwargs):
-        if torch.is_grad_enabled() and xyz.requires_grad:
+        if torch.is_grad_enabled() and (xyz.requires_grad or self._learnable()):
             *out, dlogp = self._unfused()(xyz, inverse=True)
             return (*out, dlogp if _dlogp_acc is None else _dlogp_acc + dlogp)
         return engine.ic_from_xyz_mapped(self._ic._plan, self._get_table(), self._eps, xyz, dlogp_in=_dlogp_acc)

@@ -131,17 +131,10 @@ def _convert_flow(f, strict):
                                                             eps=f._eps, enforce_boundaries=f._enforce_boundaries,
                                                             raise_warnings=f._raise_warnings)
     if n == "MixedCoordinateTransformation" and hasattr(f, "_whiten") and hasattr(f, "_rel_ic"):
-        rel, w = f._rel_ic, f._whiten
-        whitening = dict(mean=w.X0mean.detach().cpu().numpy(), whiten=w.Twhiten.detach().cpu().numpy(),
-                         blacken=w.Tblacken.detach().cpu().numpy(), jacobian_xz=float(w.jacobian_xz),
-                         keepdims=int(w.keepdims))
-        out = _ic.RelativeInternalCoordinateTransformation(rel._z_matrix, rel._fixed_atoms,
-                                                           normalize_angles=rel._normalize_angles, eps=rel._eps,
-                                                           enforce_boundaries=rel._enforce_boundaries,
-                                                           raise_warnings=rel._raise_warnings, _whitening=whitening)
-        out.__class__ = _ic.MixedCoordinateTransformation       # same kernels; the PCA is taken over, not redone
-        out._whiten = w
-        return out
+        rel = f._rel_ic
+        return _ic.MixedCoordinateTransformation.from_whitening(          # the PCA is taken over, not redone
+            f._whiten, rel._z_matrix, rel._fixed_atoms, normalize_angles=rel._normalize_angles, eps=rel._eps,
+            enforce_boundaries=rel._enforce_boundaries, raise_warnings=rel._raise_warnings)
     if strict:
         raise NotImplementedError(f"flow {n} has no mirror in bgflow_b200")
     return f

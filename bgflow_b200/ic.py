@@ -213,4 +213,16 @@ class MixedCoordinateTransformation(RelativeInternalCoordinateTransformation):
                          enforce_boundaries=enforce_boundaries, raise_warnings=raise_warnings, _whitening=w)
         self._whiten = self_whiten
 
+    @classmethod
+    def from_whitening(cls, whiten, z_matrix, fixed_atoms, **kwargs):
+        """Build the layer around an existing ``WhitenFlow`` (this package's or the reference's: anything
+        with ``X0mean / Twhiten / Tblacken / jacobian_xz / keepdims``) instead of redoing the PCA."""
+        w = dict(mean=whiten.X0mean.detach().cpu().numpy(), whiten=whiten.Twhiten.detach().cpu().numpy(),
+                 blacken=whiten.Tblacken.detach().cpu().numpy(), jacobian_xz=float(whiten.jacobian_xz),
+                 keepdims=int(whiten.keepdims))
+        self = cls.__new__(cls)
+        RelativeInternalCoordinateTransformation.__init__(self, z_matrix, fixed_atoms, _whitening=w, **kwargs)
+        self._whiten = whiten
+        return self
+
     dim_fixed = property(lambda self: self._whiten.keepdims)
