@@ -169,3 +169,57 @@ def test_real_builder_generator_converts(ref):
     assert isinstance(blocks[17]._flow, bcdf.MappedICTail)
     assert all(a is b_ for a, b_ in zip(fast.flow.parameters(), gen.flow.parameters()))
     assert fast.prior is gen.prior
+
+
+def test_plumbing_matches_reference_on_random_layouts(ref):
+    """The mirror's tuple plumbing (WrapFlow routing, SplitFlow by sizes / indices, MergeFlow,
+    SetConstantFlow, SwapFlow inside SequentialFlow, both directions) against the reference's own
+    classes on random layouts — CPU tensors, generic inner flows, bit-for-bit."""
+    import bgflow_b200 as bg
+    rng = np.random.default_rng(0)
+
+    class Scale(ref.Flow):                        # generic inner flow: multiplies tensor i by (i + 2)
+        def _forward(self, *xs, **kw):
+            return (*[x * (i + 2) for i, x in enumerate(xs)], torch.full((xs[0].shape[0], 1), float(len(xs))))
+
+        def _inverse(self, *xs, **kw):
+            return (*[x / (i + 2) for i, x in enumerate(xs)], torch.full((xs[0].shape[0], 1), -float(len(xs))))
+
+    def same(a, b):
+        assert len(a) == len(b)
+        for u, v in zip(a, b):
+            assert torch.equal(u, v), (u, v)
+
+    for trial in range(40):
+        n = int(rng.integers(2, 6))
+        xs = [torch.randn(5, int(rng.integers(1, 4))) for _ in range(n)]
+        k = int(rng.integers(1, n + 1))
+        idx = [int(i) for i in rng.permutation(n)[:k]]
+        out_idx = None if trial % 2 else [int(i) for i in rng.permutation(n)[:k]]
+        r = ref.WrapFlow(Scale(), idx, out_idx)
+        m = bg.WrapFlow(Scale(), idx, out_idx)
+        same(r(*xs), m(*xs))
+        ys = r(*xs)[:-1]
+        same(r(*ys, inverse=True), m(*ys, inverse=True))
+        # SequentialFlow of wrap + swap + set-constant, forward then inverse
+        const = torch.randn(1, 2)
+        pos = int(rng.integers(0, n + 1))
+        rseq = ref.SequentialFlow([r, ref.SwapFlow(), ref.SetConstantFlow([pos], [const])])
+        mseq = bg.SequentialFlow([m, bg.SwapFlow(), bg.SetConstantFlow([pos], [const])])
+        fr, fm = rseq(*xs), mseq(*xs)
+        same(fr, fm)
+        same(rseq(*fr[:-1], inverse=True), mseq(*fm[:-1], inverse=True))
+    for trial in range(20):
+        d = int(rng.integers(4, 12))
+        x = torch.randn(3, d)
+        cuts = sorted(int(c) for c in rng.choice(np.arange(1, d), size=int(rng.integers(1, 3)), replace=False))
+        sizes = [b - a for a, b in zip([0] + cuts, cuts + [d])]
+        use = sizes if trial % 2 else sizes[:-1]               # the last size may be omitted
+        same(ref.SplitFlow(*use)(x), bg.SplitFlow(*use)(x))
+        parts = ref.SplitFlow(*use)(x)[:-1]
+        same(ref.MergeFlow(*use)(*parts), bg.MergeFlow(*use)(*parts))
+        perm = rng.permutation(d)
+        groups = [[int(i) for i in perm[:cuts[0]]], [int(i) for i in perm[cuts[0]:]]]
+        same(ref.SplitFlow(*groups)(x), bg.SplitFlow(*groups)(x))
+        gparts = ref.SplitFlow(*groups)(x)[:-1]
+        same(ref.SplitFlow(*groups)(*gparts, inverse=True), bg.SplitFlow(*groups)(*gparts, inverse=True))
