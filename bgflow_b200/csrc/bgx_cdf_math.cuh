@@ -14,10 +14,12 @@
 
 #include "bgflow_b200.h"
 
+#ifndef BGX_HD
 #if defined(__CUDACC__)
 #define BGX_HD __host__ __device__ __forceinline__
 #else
 #define BGX_HD inline
+#endif
 #endif
 
 // Device code uses the MUFU approximations (lg2 / rcp / sqrt: a few ulp) for the logarithm, the

@@ -1,7 +1,8 @@
 // Register-resident rational-quadratic spline evaluation (8 bins) shared by the tensor-core
-// spline kernels.  Same algorithm as rqs_eval (bgx_common.cuh) / oracle.flows.rational_quadratic_spline.
+// spline kernels; __host__ __device__, so tests/native/ checks this very arithmetic against the
+// oracle on the CPU (tests/test_native_math.py).  Same algorithm as rqs_eval (bgx_common.cuh) / oracle.flows.rational_quadratic_spline.
 #pragma once
-#include "bgx_tc_epi.cuh"
+#include "bgx_fastmath.cuh"
 
 namespace bgx {
 
@@ -16,7 +17,7 @@ struct SplineK {
   float min_d, beta_l2e, ln2_over_beta, beta;
 };
 
-__device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
+BGX_HD float softplus_fast(float s, const SplineK& c) {
   // softplus(s) >= s, and lg2(1 + 2^t) -> t for large t: the max() only matters once the exponent
   // clamp (t > 64, i.e. slopes above ~44) bites, where torch's thresholded softplus returns s too
   const float v = lg2_fast(1.f + ex2_fast(fminf(s * c.beta_l2e, 64.f))) * c.ln2_over_beta;
@@ -29,7 +30,7 @@ __device__ __forceinline__ float softplus_fast(float s, const SplineK& c) {
 // FASTLOG: log-det through MUFU lg2 (absolute error <= 2^-22 ln 2 per evaluation) instead of logf,
 // binary instead of linear bin search.
 template <bool ROOT, bool FASTLOG = false>
-__device__ __forceinline__ void rqs_eval_reg(const float (&p)[PS], const SplineK& c, float x, float& y,
+BGX_HD void rqs_eval_reg(const float (&p)[PS], const SplineK& c, float x, float& y,
                                              float& lad) {
   const float mw = fmaxf(fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3])), fmaxf(fmaxf(p[4], p[5]), fmaxf(p[6], p[7])));
   const float mh = fmaxf(fmaxf(fmaxf(p[8], p[9]), fmaxf(p[10], p[11])), fmaxf(fmaxf(p[12], p[13]), fmaxf(p[14], p[15])));

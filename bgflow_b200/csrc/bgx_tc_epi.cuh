@@ -2,19 +2,13 @@
 // operand splits, asynchronous tile copies.
 #pragma once
 #include "bgx_common.cuh"
+#include "bgx_fastmath.cuh"
 #include "bgx_tc.cuh"
 
 namespace bgx {
 using namespace tc;
 
-// ---- fast special functions (MUFU): a few ulp, far inside the stated parity tolerance
-__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
+// (MUFU special functions: bgx_fastmath.cuh)
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
   if (ACT == BGX_ACT_RELU) return fmaxf(x, 0.f);

@@ -18,3 +18,32 @@ extern "C" int hm_cdf_apply(int kind, double a, double b, double lower, double u
   }
   return 0;
 }
+
+// ---- register spline evaluation of the tensor-core kernels (bgx_spline_reg.cuh), host build
+#include "bgx_spline_reg.cuh"
+
+// params: n x 25 floats per evaluation ([W(8) H(8) S(9)], the kernels' dim-major layout); x, y, lad: n
+extern "C" int hm_rqs_eval(int root, int fast, float left, float right, float bottom, float top, float min_w,
+                           float min_h, float min_d, int identity_init, int n, const float* params,
+                           const float* x, float* y, float* lad) {
+  bgx::SplineK c;
+  const float wx = right - left, hy = top - bottom;
+  const float beta = identity_init ? (float)(0.6931471805599453 / (1.0 - (double)min_d)) : 1.f;
+  c.left = left; c.right = right; c.bottom = bottom; c.top = top;
+  c.wscale = wx * (1.f - min_w * bgx::NB); c.hscale = hy * (1.f - min_h * bgx::NB);
+  c.wstep = wx * min_w; c.hstep = hy * min_h;
+  c.min_d = min_d; c.beta = beta; c.beta_l2e = beta * bgx::LOG2E; c.ln2_over_beta = bgx::LN2 / beta;
+  for (int i = 0; i < n; ++i) {
+    float p[bgx::PS];
+    for (int k = 0; k < bgx::PS; ++k) p[k] = params[i * bgx::PS + k];
+    const float xi = fminf(fmaxf(x[i], left), right);
+    if (root) {
+      if (fast) bgx::rqs_eval_reg<true, true>(p, c, xi, y[i], lad[i]);
+      else bgx::rqs_eval_reg<true, false>(p, c, xi, y[i], lad[i]);
+    } else {
+      if (fast) bgx::rqs_eval_reg<false, true>(p, c, xi, y[i], lad[i]);
+      else bgx::rqs_eval_reg<false, false>(p, c, xi, y[i], lad[i]);
+    }
+  }
+  return 0;
+}

@@ -130,3 +130,68 @@ def test_cdf_edge_semantics(hm):
     # icdf clamps its argument to [eps, 1 - eps]: finite everywhere
     x, ld = apply(hm, "trunc", 1.0, 1.0, 1e-5, np.inf, np.array([0.0, 1.0], np.float32), inverse=True)
     assert np.all(np.isfinite(x)) and np.all(np.isfinite(ld)) and x[0] >= 1e-5
+
+
+# ------------------------------------------------------------------ register spline evaluation
+
+def _rqs(hm_lib, root, fast, params, x, dom=(0.0, 1.0, 0.0, 1.0), identity_init=True):
+    hm_lib.hm_rqs_eval.restype = C.c_int
+    hm_lib.hm_rqs_eval.argtypes = [C.c_int, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_int] + [C.c_void_p] * 4
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y, lad = np.empty_like(x), np.empty_like(x)
+    rc = hm_lib.hm_rqs_eval(int(root), int(fast), *dom, 1e-3, 1e-3, 1e-3, int(identity_init), x.size,
+                            params.ctypes.data, x.ctypes.data, y.ctypes.data, lad.ctypes.data)
+    assert rc == 0
+    return y, lad
+
+
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("root", [True, False])
+@pytest.mark.parametrize("dom", [(0.0, 1.0, 0.0, 1.0), (-2.0, 3.0, -1.0, 0.5)])
+def test_register_spline_evaluation_matches_oracle(hm, root, fast, dom):
+    """``rqs_eval_reg`` (the tensor-core kernels' per-dim spline arithmetic: softmax knots from prefix
+    sums, binary / linear bin search, root / direct branch, log-det) compiled for the host, against the
+    fp64 oracle restatement of nflows' rational_quadratic_spline on the same fp32 parameters."""
+    from oracle import flows as of
+    rng = np.random.default_rng(7)
+    n = 20000
+    params = (rng.standard_normal((n, 25)) * rng.choice([0.3, 1.0, 3.0], size=(n, 1))).astype(np.float32)
+    left, right, bottom, top = dom
+    lo, hi = (bottom, top) if root else (left, right)
+    x = (lo + (hi - lo) * rng.random(n)).astype(np.float32)
+    x[:4] = [lo, hi, lo + 1e-7 * (hi - lo), hi - 1e-6 * (hi - lo)]
+    y, lad = _rqs(hm, root, fast, params, x, dom)
+    p64 = torch.from_numpy(params).double()
+    yr, lr = of.rational_quadratic_spline(torch.from_numpy(x).double().clamp(lo, hi), p64[:, :8], p64[:, 8:16], p64[:, 16:],
+                                          inverse=root, left=left, right=right, bottom=bottom, top=top)
+    yr, lr = yr.numpy(), lr.numpy()
+    span = (right - left) if root else (top - bottom)
+    # a knot that moves by an fp32 rounding can flip the bin of an input sitting on it: y stays
+    # continuous across the flip, the log-det does not -> compare the log-det where the bins agree
+    # (parameters with std up to 3 give splines with slopes of 1e-3 .. 1e3: the few worst-conditioned
+    # evaluations lose fp32 digits in the quadratic root; bound the tail and the bulk separately)
+    err = np.abs(y - yr) / max(1.0, span)
+    assert err.max() < 1e-4 and np.quantile(err, 0.999) < 5e-6, (err.max(), np.quantile(err, 0.999))
+    close = np.abs(lad - lr) < 2e-4
+    assert close.mean() > 0.995, close.mean()
+    assert np.median(np.abs(lad - lr)) < 2e-6
+    # outputs stay inside the image interval (tests/nn/flow/transformer/test_spline.py:30-33)
+    olo, ohi = (left, right) if root else (bottom, top)
+    assert (y >= olo - 1e-6).all() and (y <= ohi + 1e-6).all()
+
+
+def test_register_spline_fast_and_reference_paths_agree(hm):
+    """Binary bin search + MUFU-style log-det vs linear walk + logf: same bins, same values."""
+    rng = np.random.default_rng(8)
+    params = rng.standard_normal((5000, 25)).astype(np.float32) * 2
+    x = rng.random(5000).astype(np.float32)
+    for root in (True, False):
+        y1, l1 = _rqs(hm, root, True, params, x)
+        y0, l0 = _rqs(hm, root, False, params, x)
+        np.testing.assert_array_equal(y1, y0)
+        np.testing.assert_allclose(l1, l0, atol=2e-6, rtol=0)
+    # zero parameters = identity (tests/factory/test_generator_builder.py:131-136, identity init)
+    y, lad = _rqs(hm, True, True, np.zeros((100, 25), np.float32), np.linspace(0.01, 0.99, 100))
+    np.testing.assert_allclose(y, np.linspace(0.01, 0.99, 100), atol=2e-6)
+    np.testing.assert_allclose(lad, 0.0, atol=2e-6)
