@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bgflow_b200 as bg
 from bgflow_b200 import engine
-from oracle import ic as oic
+from bgflow_b200 import fixtures as oic
 
 B = 1 << 20
 dev = "cuda"
