@@ -16,7 +16,6 @@ the reference's op sequence on the device with torch.
 
 import math
 
-import numpy as np
 import torch
 
 from . import _lib, engine

@@ -81,3 +81,20 @@ def config4_blocks(dtype=torch.float32, seed=11, hidden=(128, 128), n_bins=8):
         blocks += [block(B_, (A_,)), block(A_, (B_,))]
     blocks += [block(A_, (T_, X_)), block(B_, (A_, T_, X_))]
     return blocks
+
+
+import math
+
+
+def marginals(dev="cuda:0"):
+    """InternalCoordinateMarginals defaults (factory/icmarginals.py:14-77) with this package's classes."""
+    one = lambda n, v=1.0: torch.full((n,), v, device=dev)
+    return {
+        "bonds": bg.TruncatedNormalDistribution(one(21), one(21), torch.tensor(1e-5, device=dev),
+                                                torch.tensor(math.inf, device=dev)),
+        "angles": bg.TruncatedNormalDistribution(one(20, 0.5), one(20), torch.tensor(1e-5, device=dev),
+                                                 torch.tensor(1.0, device=dev)),
+        "torsions": bg.SloppyUniform(torch.zeros(19, device=dev), one(19)),
+        "fixed": torch.distributions.Normal(torch.zeros(9, device=dev), 20 * one(9)),
+        "augmented": torch.distributions.Normal(torch.zeros(10, device=dev), one(10)),
+    }

@@ -17,6 +17,7 @@ import bgflow_b200 as bg
 from bgflow_b200 import _lib
 from oracle import cdf as ocdf, ic as oic
 from conftest import load_golden
+from helpers import marginals
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -25,20 +26,6 @@ FIELDS = {"bonds": 21, "angles": 20, "torsions": 19, "fixed": 9, "augmented": 10
 
 def _t(a):
     return torch.from_numpy(np.asarray(a)).to(DEV)
-
-
-def marginals(dev=DEV):
-    """InternalCoordinateMarginals defaults (factory/icmarginals.py:14-77) with this package's classes."""
-    one = lambda n, v=1.0: torch.full((n,), v, device=dev)
-    return {
-        "bonds": bg.TruncatedNormalDistribution(one(21), one(21), torch.tensor(1e-5, device=dev),
-                                                torch.tensor(math.inf, device=dev)),
-        "angles": bg.TruncatedNormalDistribution(one(20, 0.5), one(20), torch.tensor(1e-5, device=dev),
-                                                 torch.tensor(1.0, device=dev)),
-        "torsions": bg.SloppyUniform(torch.zeros(19, device=dev), one(19)),
-        "fixed": torch.distributions.Normal(torch.zeros(9, device=dev), 20 * one(9)),
-        "augmented": torch.distributions.Normal(torch.zeros(10, device=dev), one(10)),
-    }
 
 
 def _check_icdf(x, dlogp, u, g, name):

@@ -15,8 +15,7 @@ import torch
 import bgflow_b200 as bg
 from bgflow_b200 import _lib
 from oracle import cdf as ocdf, flows as of, ic as oic
-from helpers import config4_blocks, transformer_from
-from test_gpu_cdf import marginals
+from helpers import config4_blocks, marginals, transformer_from
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
