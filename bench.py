@@ -483,6 +483,8 @@ def main():
         engine.config["precision"] = os.environ["BGX_PRECISION"]
     if os.environ.get("BGX_FORCE_SIMT"):
         engine.config["force_simt"] = True
+    if os.environ.get("BGX_SPLINE_KERNEL"):
+        engine.config["spline_kernel"] = os.environ["BGX_SPLINE_KERNEL"]
     config["kernel"] = ("fp32 SIMT" if engine.config["force_simt"] else
                         f"tcgen05 kind::f16, operands split into bf16 terms ({engine.config['precision']})")
     dev = torch.device(f"cuda:{local_rank}")

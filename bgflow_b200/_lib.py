@@ -21,6 +21,9 @@ ERRORS = {-1: "BGX_ERR_INVALID (bad argument / inconsistent shapes)",
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3
 FLAG_INVERSE, FLAG_PRESERVE_VOLUME, FLAG_CIRCULAR, FLAG_BF16X6, FLAG_FORCE_SIMT = 1, 2, 4, 8, 16
+FLAG_NO_PAIR, FLAG_FORCE_WIDE = 32, 64
+KERNEL_IDS = {"spline_pair": 0, "spline_pair_wide": 1, "spline_tc2": 2, "spline_tc": 3, "spline_simt": 4,
+              "affine_tc2": 5, "affine_tc": 6, "affine_simt": 7, "affine_pair": 8, "affine_pair_wide": 9}
 
 
 class bgx_mlp(C.Structure):
@@ -42,7 +45,8 @@ class bgx_packed_mlp(C.Structure):
                 ("raw_width", C.c_int32),
                 ("spline_dims_per_pass", C.c_int32), ("spline_stride", C.c_int32),
                 ("total_floats", C.c_int64),
-                ("Wb", (C.c_void_p * BGX_MAX_LAYERS) * 3)]
+                ("Wb", (C.c_void_p * BGX_MAX_LAYERS) * 3),
+                ("spline_bias", C.c_void_p), ("spline_bias_pad", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class bgx_spline_layout(C.Structure):
@@ -127,6 +131,7 @@ SYMBOLS = {
     "bgx_version": (C.c_char_p, []),
     "bgx_last_cuda_error": (C.c_char_p, []),
     "bgx_launch_count": (C.c_int64, []),
+    "bgx_kernel_count": (C.c_int64, [C.c_int]),
 }
 
 _lib = None
@@ -163,3 +168,9 @@ def check(rc, what):
 
 def launch_count():
     return int(load().bgx_launch_count())
+
+
+def kernel_counts():
+    """Coupling calls served so far per kernel family (``KERNEL_IDS``)."""
+    lib = load()
+    return {name: int(lib.bgx_kernel_count(i)) for name, i in KERNEL_IDS.items()}

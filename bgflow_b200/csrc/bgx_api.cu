@@ -9,6 +9,8 @@ int spline_coupling_simt(const bgx_coupling_io*, const bgx_packed_mlp*, const bg
 bool spline_tc_eligible(const bgx_packed_mlp*, const bgx_spline_cfg*, int);
 bool spline_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int);
 int spline_coupling_tc2(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int*, cudaStream_t);
+int spline_pair_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int);
+int spline_coupling_pair(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int, int*, cudaStream_t);
 void tc_set_trace(unsigned long long*, int);
 bool affine_tc_eligible(const bgx_packed_mlp*, const bgx_packed_mlp*, int);
 bool affine_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, int);
@@ -20,6 +22,9 @@ int spline_coupling_tc(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_
                        cudaStream_t);
 }  // namespace bgx
 
+static long long g_kernel_count[BGX_KERNEL_IDS] = {};
+extern "C" int64_t bgx_kernel_count(int id) { return (id >= 0 && id < BGX_KERNEL_IDS) ? g_kernel_count[id] : -1; }
+
 static int* g_status = nullptr;   // device flag raised by the tensor-core kernels on a pipeline timeout
 
 extern "C" int bgx_set_status_buffer(int32_t* device_int) {
@@ -30,22 +35,40 @@ extern "C" int bgx_set_status_buffer(int32_t* device_int) {
 extern "C" int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
                                    const bgx_packed_mlp* scale, float log_alpha, int flags, void* stream) {
   if (!io) return BGX_ERR_INVALID;
-  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc2_eligible(io, shift, scale, flags))
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc2_eligible(io, shift, scale, flags)) {
+    ++g_kernel_count[BGX_KERNEL_AFFINE_TC2];
     return bgx::affine_coupling_tc2(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
-  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc_eligible(shift, scale, flags))
+  }
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc_eligible(shift, scale, flags)) {
+    ++g_kernel_count[BGX_KERNEL_AFFINE_TC];
     return bgx::affine_coupling_tc(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
+  }
+  ++g_kernel_count[BGX_KERNEL_AFFINE_SIMT];
   return bgx::affine_coupling_simt(io, shift, scale, log_alpha, flags, (cudaStream_t)stream);
 }
 
 extern "C" int bgx_spline_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* params_net,
                                    const bgx_spline_cfg* cfg, int flags, void* stream) {
   if (!io || !params_net || !cfg) return BGX_ERR_INVALID;
-  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc2_eligible(io, params_net, cfg, flags))
+  if (!(flags & (BGX_FLAG_FORCE_SIMT | BGX_FLAG_NO_PAIR))) {
+    const int mode = bgx::spline_pair_eligible(io, params_net, cfg, flags);
+    if (mode) {
+      ++g_kernel_count[mode == 2 ? BGX_KERNEL_SPLINE_PAIR_WIDE : BGX_KERNEL_SPLINE_PAIR];
+      return bgx::spline_coupling_pair(io, params_net, cfg, flags, mode, cfg->status ? cfg->status : g_status,
+                                       (cudaStream_t)stream);
+    }
+  }
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc2_eligible(io, params_net, cfg, flags)) {
+    ++g_kernel_count[BGX_KERNEL_SPLINE_TC2];
     return bgx::spline_coupling_tc2(io, params_net, cfg, flags, cfg->status ? cfg->status : g_status,
                                     (cudaStream_t)stream);
-  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc_eligible(params_net, cfg, 0))
+  }
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc_eligible(params_net, cfg, 0)) {
+    ++g_kernel_count[BGX_KERNEL_SPLINE_TC];
     return bgx::spline_coupling_tc(io, params_net, cfg, flags, cfg->status ? cfg->status : g_status,
                                    (cudaStream_t)stream);
+  }
+  ++g_kernel_count[BGX_KERNEL_SPLINE_SIMT];
   return bgx::spline_coupling_simt(io, params_net, cfg, flags, (cudaStream_t)stream);
 }
 

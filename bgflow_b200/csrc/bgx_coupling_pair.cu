@@ -1,0 +1,580 @@
+// Tensor-core fused RQ-spline coupling block, PAIR kernel: one persistent CTA per SM works on TWO
+// 128-row tiles at a time ("slots") that ping-pong on the tensor pipe and share ONE weight ring.
+//
+// Why (measured on the two-CTAs-per-SM kernel, profiles/r1_spline_tc2_ncu_summary.txt + the ncu source
+// page): that kernel streams every weight tile from L2 once per 128-row tile (600 KB per tile, ~22 B per
+// cycle per SM = half of the L2 fabric's ~42 B/clk/SM share), a quarter of its executed instructions are
+// barrier polling loops of the producer / I/O thread, and inside a CTA the epilogue and the MMAs of a
+// tile are serialised.  Here
+//   * both slots consume a weight stage before it is released: half the L2 -> SM weight traffic;
+//   * the MMA issuer alternates slot 0 / slot 1 unit by unit, so the 16 epilogue warps work on one
+//     slot's accumulator while the tensor pipe fills the other one (explicit ping-pong instead of
+//     relying on a sibling CTA);
+//   * every role blocks on exactly one mbarrier at a time (no polling state machines);
+//   * the conditioner's first layer is k-tiled in groups of 128 inputs and the last layer runs any
+//     number of 128-column passes, with the transformed tile either resident in shared memory
+//     (narrow blocks: D_t + D_c <= ~80, bulk-TMA tile I/O) or read / written in place in global
+//     memory (WIDE: BASELINE config 5, D = 384 / 3072).
+//
+//   warps 0-15  epilogue: warp w owns TMEM lane quadrant w % 4 (rows 32 (w%4) .. +31 of a tile) and the
+//               column / dim share w / 4 of every unit
+//   warp 16     lane 0: weight producer (bulk TMA, 2 stages x 64 KB = one unit's k-tiles x 2 bf16 terms)
+//   warp 17     lane 0: tile I/O of the narrow mode (one bulk copy per tile and direction)
+//   warp 18     tcgen05.mma issuer (warp-wide loop, one elected lane issues); owns the TMEM allocation
+//
+// TMEM (512 columns): slot s at 256 s: [0,128) accumulator, [128,192) A term 1, [192,256) A term 2.
+// A "unit" is one accumulator's worth of MMAs: a 128-input group of layer 0, a hidden layer, or one
+// 128-column pass of the last layer (5 dims x 25 spline parameters).
+//
+// Reference arithmetic: bgflow/nn/flow/coupling.py:162-182, bgflow/nn/dense.py:47-48,
+// bgflow/nn/flow/transformer/spline.py:87-188 + nflows rational_quadratic_spline.
+#include <cstdlib>
+
+#include "bgx_coupling.cuh"
+#include "bgx_tc.cuh"
+#include "bgx_tc_epi.cuh"
+#include "bgx_spline_reg.cuh"
+
+namespace bgx {
+using namespace tc;
+
+constexpr int P_EPI_WARPS = 16;
+constexpr int P_THREADS = (P_EPI_WARPS + 3) * 32;     // 608
+constexpr int P_TM = 128;
+constexpr int P_STAGES = 2;
+constexpr uint32_t P_TILE_BYTES = 16384;              // one [128 x 64] bf16 k-tile of one term
+constexpr uint32_t P_KT_BYTES = 2 * P_TILE_BYTES;     // both terms
+constexpr uint32_t P_STAGE_BYTES = 2 * P_KT_BYTES;    // a unit has at most two k-tiles
+constexpr int P_SLOT = 256, P_ACC = 0, P_A = 128, P_A_STRIDE = 64;
+constexpr int P_NB = 8, P_PS = 3 * P_NB + 1, P_DPP = 5, P_BPAD = 28;
+
+struct PArgs {
+  long long B;
+  const float* cond;    // [B][K0raw] dense
+  const float* tin;     // [B][D_t] dense
+  float* tout;          // [B][D_t] dense
+  int D_t, K0raw;
+  DevMlp net;
+  const uint16_t* wb[2][BGX_MAX_LAYERS];
+  int ktiles[BGX_MAX_LAYERS];
+  int npass, G;         // last-layer passes, 128-input groups of layer 0
+  SplineK ck;
+  int* oob;
+  const float* dlogp_in;
+  float* dlogp_out;
+  int* status;
+  long long ntiles, npairs;
+  int hid_bias_floats, last_bias_floats;
+  const float* bias_last;     // [npass][5][28] (global)
+  int plain_cond;             // conditioner input map is the identity (no WrapPeriodic)
+};
+
+struct alignas(16) PSmem {
+  uint64_t w_full[P_STAGES], w_empty[P_STAGES];
+  uint64_t a_ready[2];     // 16: the slot's A operand is staged in TMEM
+  uint64_t acc_full[2];    // 1 (tcgen05.commit): the slot's accumulator holds a finished unit
+  uint64_t acc_empty[2];   // 16: last-layer pass pulled into registers
+  uint64_t y_full[2], c_full[2];   // 1 + tx (narrow mode)
+  uint64_t y_done[2], c_free[2];   // 16
+  uint32_t tmem_base, pad[3];
+  float dl_part[2][2][4][P_TM];    // [iteration parity][slot][dim share][row]
+};
+
+template <bool INVERSE, int ACT, bool WIDE>
+__global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(const PArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = base;
+  PSmem* S = (PSmem*)(base + P_STAGES * P_STAGE_BYTES);
+  float* bias_h = (float*)(S + 1);                          // hidden layers' biases
+  float* bias_l = bias_h + a.hid_bias_floats;               // narrow: last layer [npass][5][28]
+  float* ybuf = bias_l + (WIDE ? 0 : a.last_bias_floats);   // narrow: [2][128][D_t]
+  float* cbuf = ybuf + (WIDE ? 0 : 2 * P_TM * a.D_t);       // narrow: [2][128][K0raw]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.net.n_layers;
+  const int G = a.G, P = a.npass;
+  const long long n_my = (a.npairs > blockIdx.x) ? (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) {
+      mbar_init(&S->w_full[i], 1);
+      mbar_init(&S->w_empty[i], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&S->a_ready[s], P_EPI_WARPS);
+      mbar_init(&S->acc_full[s], 1);
+      mbar_init(&S->acc_empty[s], P_EPI_WARPS);
+      mbar_init(&S->y_full[s], 1);
+      mbar_init(&S->c_full[s], 1);
+      mbar_init(&S->y_done[s], P_EPI_WARPS);
+      mbar_init(&S->c_free[s], P_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  {
+    int off = 0;
+    for (int l = 0; l < L - 1; ++l) {
+      for (int i = threadIdx.x; i < a.net.Np[l]; i += P_THREADS) bias_h[off + i] = a.net.bias[l][i];
+      off += a.net.Np[l];
+    }
+    if (!WIDE)
+      for (int i = threadIdx.x; i < a.last_bias_floats; i += P_THREADS) bias_l[i] = a.bias_last[i];
+  }
+  if (warp == 18) tmem_alloc<512>(&S->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S->tmem_base;
+
+  // tile of slot s in CTA-local iteration `it`; a slot is active iff its tile exists
+  auto tile_of = [&](long long it, int s) { return 2 * (blockIdx.x + it * (long long)gridDim.x) + s; };
+  auto rows_of = [&](long long tile) { return (int)min((long long)P_TM, a.B - tile * P_TM); };
+
+  if (warp == 16) {
+    // ------------------------------------------------------------------ weight producer (one thread)
+    if (lane == 0) {
+      uint32_t ph_e[P_STAGES] = {0, 0};
+      int stage = 0;
+      long long nfill = 0;
+      auto fill = [&](int l, int c, int t0, int nt) -> bool {
+        if (nfill >= P_STAGES) {
+          if (!mbar_wait(&S->w_empty[stage], ph_e[stage], a.status)) return false;
+          ph_e[stage] ^= 1;
+        }
+        uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
+        mbar_expect_tx(&S->w_full[stage], (uint32_t)nt * P_KT_BYTES);
+        const int kt = a.ktiles[l];
+        for (int t = 0; t < nt; ++t) {
+          const long long src = ((long long)c * kt + t0 + t) * 8192;
+          bulk_g2s(dst + (size_t)t * P_KT_BYTES, a.wb[0][l] + src, P_TILE_BYTES, &S->w_full[stage]);
+          bulk_g2s(dst + (size_t)t * P_KT_BYTES + P_TILE_BYTES, a.wb[1][l] + src, P_TILE_BYTES, &S->w_full[stage]);
+        }
+        ++nfill;
+        stage ^= 1;
+        return true;
+      };
+      bool ok = true;
+      for (long long it = 0; it < n_my && ok; ++it) {
+        for (int g = 0; g < G && ok; ++g) ok = fill(0, 0, 2 * g, min(2, a.ktiles[0] - 2 * g));
+        for (int l = 1; l < L - 1 && ok; ++l) ok = fill(l, 0, 0, a.ktiles[l]);
+        for (int c = 0; c < P && ok; ++c) ok = fill(L - 1, c, 0, a.ktiles[L - 1]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ------------------------------------------------------------------ tile I/O, narrow mode (one thread)
+    if (!WIDE && lane == 0) {
+      const uint32_t ystride = (uint32_t)(P_TM * a.D_t), cstride = (uint32_t)(P_TM * a.K0raw);
+      auto load_c = [&](long long it, int s) {
+        const long long tile = tile_of(it, s);
+        if (tile >= a.ntiles) return;
+        const uint32_t nb = (uint32_t)(rows_of(tile) * a.K0raw * 4);
+        mbar_expect_tx(&S->c_full[s], nb);
+        bulk_g2s(cbuf + s * cstride, a.cond + tile * P_TM * (long long)a.K0raw, nb, &S->c_full[s]);
+      };
+      auto load_y = [&](long long it, int s) {
+        const long long tile = tile_of(it, s);
+        if (tile >= a.ntiles) return;
+        const uint32_t nb = (uint32_t)(rows_of(tile) * a.D_t * 4);
+        mbar_expect_tx(&S->y_full[s], nb);
+        bulk_g2s(ybuf + s * ystride, a.tin + tile * P_TM * (long long)a.D_t, nb, &S->y_full[s]);
+      };
+      uint32_t ph_cf[2] = {0, 0}, ph_yd[2] = {0, 0};
+      if (n_my > 0)
+        for (int s = 0; s < 2; ++s) { load_c(0, s); load_y(0, s); }
+      bool ok = true;
+      for (long long k = 0; k < n_my && ok; ++k) {
+        // conditioner tile of iteration k+1: the buffer is free once iteration k's operand is staged
+        for (int s = 0; s < 2 && ok; ++s) {
+          if (tile_of(k, s) >= a.ntiles || k + 1 >= n_my) continue;
+          ok = mbar_wait(&S->c_free[s], ph_cf[s], a.status);
+          ph_cf[s] ^= 1;
+          load_c(k + 1, s);
+        }
+        // transformed tile: store iteration k's result, then fetch iteration k+1's input
+        for (int s = 0; s < 2 && ok; ++s) {
+          const long long tile = tile_of(k, s);
+          if (tile >= a.ntiles) continue;
+          ok = mbar_wait(&S->y_done[s], ph_yd[s], a.status);
+          ph_yd[s] ^= 1;
+          if (!ok) break;
+          bulk_s2g(a.tout + tile * P_TM * (long long)a.D_t, ybuf + s * ystride, (uint32_t)(rows_of(tile) * a.D_t * 4));
+          bulk_store_wait_read();
+          if (k + 1 < n_my) load_y(k + 1, s);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == 18) {
+    // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
+    const uint32_t idesc = idesc_bf16(128, 128);
+    int stage = 0;
+    uint32_t ph_wf[P_STAGES] = {0, 0};
+    uint32_t ph_a[2] = {0, 0}, ph_e[2] = {0, 0};
+    bool ok = true;
+    // one unit on both slots: `wait_a` = a freshly staged A operand is needed, `wait_e` = the accumulator must
+    // have been pulled by the epilogue (a last-layer pass preceded), `accum` = keep the accumulator (layer-0 group > 0)
+    auto unit = [&](int nslots, int K, int kcol0, bool wait_a, bool wait_e, bool accum) {
+      if (!ok) return;
+      ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
+      ph_wf[stage] ^= 1;
+      const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
+      const int ksteps = (K + 15) / 16;
+      for (int s = 0; s < nslots && ok; ++s) {
+        if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
+        if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t acc_addr = tmem + s * P_SLOT + P_ACC;
+        uint32_t acc = accum ? 1u : 0u;
+        for (int t = 0; t * 4 < ksteps; ++t) {
+          const uint32_t b1 = sb + (uint32_t)t * P_KT_BYTES, b2 = b1 + P_TILE_BYTES;
+          const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);
+          const uint32_t a1 = tmem + s * P_SLOT + P_A + (uint32_t)(kcol0 + t * 32), a2 = a1 + P_A_STRIDE;
+          const int nk = min(4, ksteps - t * 4);
+          if (nk == 4) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma3_bf16x3_elect(acc_addr, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
+          } else {
+            for (int ks = 0; ks < nk; ++ks)
+              mma3_bf16x3_elect(acc_addr, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
+          }
+          acc = 1;
+        }
+        mma_commit_elect(&S->acc_full[s]);
+      }
+      mma_commit_elect(&S->w_empty[stage]);     // both slots' MMAs on this stage are issued: release it when they finish
+      stage ^= 1;
+    };
+    for (long long it = 0; it < n_my && ok; ++it) {
+      const int nslots = (tile_of(it, 1) < a.ntiles) ? 2 : 1;
+      for (int g = 0; g < G; ++g) unit(nslots, min(128, a.net.K[0] - 128 * g), 0, true, g == 0 && it > 0, g > 0);
+      for (int l = 1; l < L - 1; ++l) unit(nslots, a.net.K[l], 0, true, false, false);
+      for (int c = 0; c < P; ++c) unit(nslots, a.net.K[L - 1], 0, c == 0, c > 0, false);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (0..15)
+    const int q = warp & 3, j = warp >> 2;            // TMEM lane quadrant, column / dim share
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_acc[2] = {0, 0}, ph_c[2] = {0, 0}, ph_y[2] = {0, 0};
+    const int K0 = a.net.K[0];
+    bool ok = true;
+
+    // layer-0 operand: inputs 128 g + [32 j, 32 j + 32) of this thread's row -> two bf16 terms in TMEM
+    auto stage_x = [&](long long it, int s, int g) {
+      const long long tile = tile_of(it, s);
+      const long long row = tile * P_TM + r_in_tile;
+      const int kg = 128 * g;                 // first input of the group
+      const int kend = min(K0, kg + 128);     // one past the last real input of the group
+      if (!WIDE && g == 0) {
+        ok = ok && mbar_wait(&S->c_full[s], ph_c[s], a.status);
+        ph_c[s] ^= 1;
+      }
+      const float* crow = WIDE ? a.cond + row * (long long)a.K0raw : cbuf + (s * P_TM + r_in_tile) * a.K0raw;
+      const bool live = !WIDE || row < a.B;
+      auto cond_value = [&](int k) -> float {
+        if (k >= kend || !live) return 0.f;
+        if (a.plain_cond) return crow[k];
+        const int code = a.net.in_map[k];
+        const float v = crow[code & 0xffffff];
+        const int kind = code >> 24;
+        if (kind == 0) return v;
+        const float arg = (v - a.net.pleft) * a.net.pscale;
+        return kind == 1 ? cosf(arg) : sinf(arg);
+      };
+      // this warp's 32 inputs as two 16-input halves (8 packed columns each); a half is written iff the
+      // MMAs of the group read it (k-steps cover inputs [kg, round_up(kend, 16)))
+      for (int h = 0; h < 2; ++h) {
+        const int b0 = kg + j * 32 + h * 16;
+        if (b0 >= kend) break;
+        uint32_t t1[8], t2[8], t3[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_bf16(cond_value(b0 + 2 * i), cond_value(b0 + 2 * i + 1), 2, t1[i], t2[i], t3[i]);
+        const uint32_t col = tmem + lane_base + s * P_SLOT + P_A + (uint32_t)((b0 - kg) / 2);
+        tmem_st8(col, t1);
+        tmem_st8(col + P_A_STRIDE, t2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&S->a_ready[s]);
+        if (!WIDE && g == 0) mbar_arrive(&S->c_free[s]);
+      }
+    };
+
+    // hidden layer: accumulator columns [32 j, 32 j + 32) -> bias, activation, exact bf16 split -> A operand
+    auto hidden = [&](int s, int boff) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
+      tmem_ld_wait();
+      uint32_t t1[16], t2[16], t3[16];
+      const float4* b4 = reinterpret_cast<const float4*>(bias_h + boff + j * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = b4[i];
+        const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
+        const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
+        const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
+        const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
+        split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
+        split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
+      }
+      const uint32_t acol = tmem + lane_base + s * P_SLOT + P_A + j * 16;
+      tmem_st16(acol, t1);
+      tmem_st16(acol + P_A_STRIDE, t2);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->a_ready[s]);
+    };
+
+    auto wait_acc = [&](int s) {
+      ok = ok && mbar_wait(&S->acc_full[s], ph_acc[s], a.status);
+      ph_acc[s] ^= 1;
+      tc_fence_after();
+    };
+
+    float ld[2];
+    int n_oob = 0;
+    for (long long it = 0; it < n_my; ++it) {
+      const int nslots = (tile_of(it, 1) < a.ntiles) ? 2 : 1;
+      if (it == 0)
+        for (int s = 0; s < nslots; ++s) stage_x(0, s, 0);
+      // ---- layer 0: groups of 128 inputs; the last group's accumulator is the hidden layer's input
+      for (int g = 0; g < G; ++g)
+        for (int s = 0; s < nslots; ++s) {
+          wait_acc(s);
+          if (g < G - 1) stage_x(it, s, g + 1);
+          else hidden(s, 0);
+        }
+      // ---- hidden layers 1 .. L-2
+      int boff = a.net.Np[0];
+      for (int l = 1; l < L - 1; ++l) {
+        for (int s = 0; s < nslots; ++s) {
+          wait_acc(s);
+          hidden(s, boff);
+        }
+        boff += a.net.Np[l];
+      }
+      // ---- last layer: pass c holds dims 5c .. 5c+4; this warp takes the dims i with (i + c) % 4 == j
+      ld[0] = ld[1] = 0.f;
+      for (int c = 0; c < P; ++c) {
+        const int i0 = (j - c) & 3;
+        for (int s = 0; s < nslots; ++s) {
+          const long long row = tile_of(it, s) * P_TM + r_in_tile;
+          const bool live = row < a.B;
+          if (!WIDE && c == 0) {
+            ok = ok && mbar_wait(&S->y_full[s], ph_y[s], a.status);
+            ph_y[s] ^= 1;
+          }
+          const int d0 = P_DPP * c + i0;                 // first dim of this warp in the pass (second: d0 + 4, only if i0 == 0)
+          const int n_mine = (d0 < a.D_t ? 1 : 0) + ((i0 == 0 && d0 + 4 < a.D_t) ? 1 : 0);
+          // operands that do not depend on the accumulator first: the transformed inputs and (wide) the bias
+          float xin[2] = {0.f, 0.f};
+          if (WIDE) {
+            if (live && n_mine > 0) xin[0] = a.tin[row * (long long)a.D_t + d0];
+            if (live && n_mine > 1) xin[1] = a.tin[row * (long long)a.D_t + d0 + 4];
+          } else {
+            const float* yrow = ybuf + (s * P_TM + r_in_tile) * a.D_t;
+            if (n_mine > 0) xin[0] = yrow[d0];
+            if (n_mine > 1) xin[1] = yrow[d0 + 4];
+          }
+          const float* bsrc = (WIDE ? a.bias_last : bias_l) + ((size_t)c * P_DPP + i0) * P_BPAD;
+          float p[P_BPAD];
+          if (n_mine > 0) {
+            const float4* b4 = reinterpret_cast<const float4*>(bsrc);
+#pragma unroll
+            for (int qq = 0; qq < 7; ++qq) {
+              const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
+              p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
+            }
+          }
+          wait_acc(s);
+          const uint32_t acc_addr = tmem + lane_base + s * P_SLOT + P_ACC;
+          for (int m = 0; m < n_mine; ++m) {
+            const int i = i0 + 4 * m;
+            uint32_t v[32];
+            tmem_ld32(acc_addr + i * P_PS, v);
+            tmem_ld_wait();
+            if (m == n_mine - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S->acc_empty[s]);
+            }
+            if (m == 1) {
+              const float4* b4 = reinterpret_cast<const float4*>(bsrc + 4 * P_BPAD);
+#pragma unroll
+              for (int qq = 0; qq < 7; ++qq) {
+                const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
+                p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
+              }
+            }
+            float pp[P_PS];
+#pragma unroll
+            for (int k = 0; k < P_PS; ++k) pp[k] = __uint_as_float(v[k]) + p[k];
+            float x = xin[m];
+            n_oob += (live && (x < a.ck.left || x > a.ck.right)) ? 1 : 0;
+            x = fminf(fmaxf(x, a.ck.left), a.ck.right);
+            float y, lad;
+            rqs_eval_reg<!INVERSE, true>(pp, a.ck, x, y, lad);
+            if (WIDE) {
+              if (live) a.tout[row * (long long)a.D_t + P_DPP * c + i] = y;
+            } else {
+              ybuf[(s * P_TM + r_in_tile) * a.D_t + P_DPP * c + i] = y;
+            }
+            ld[s] += lad;
+          }
+          if (n_mine == 0) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->acc_empty[s]);
+          }
+          if (c == P - 1) {
+            // ---- end of this slot's tile: hand the output tile to the I/O thread, reduce the log-det over
+            // the four dim shares, and stage the next tile's layer-0 operand (every MMA of the tile is done)
+            if (!WIDE) {
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S->y_done[s]);
+            }
+            float* dl = &S->dl_part[it & 1][s][0][0];
+            dl[j * P_TM + r_in_tile] = ld[s];
+            asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
+            if (j == 0 && live) {
+              const float base_dl = a.dlogp_in ? a.dlogp_in[row] : 0.f;
+              a.dlogp_out[row] = base_dl + ((dl[r_in_tile] + dl[P_TM + r_in_tile]) +
+                                            (dl[2 * P_TM + r_in_tile] + dl[3 * P_TM + r_in_tile]));
+            }
+            if (it + 1 < n_my && tile_of(it + 1, s) < a.ntiles) stage_x(it + 1, s, 0);
+          }
+        }
+      }
+    }
+    if (n_oob && a.oob) atomicAdd(a.oob, n_oob);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 18) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+static size_t pair_smem_bytes(const bgx_packed_mlp* net, int d_t, int k0raw, bool wide) {
+  const int L = net->n_layers;
+  size_t hid = 0;
+  for (int l = 0; l + 1 < L; ++l) hid += net->Np[l];
+  const size_t last = wide ? 0 : (size_t)(net->Np[L - 1] / 128) * P_DPP * P_BPAD;
+  const size_t tiles = wide ? 0 : (size_t)2 * P_TM * (d_t + k0raw);
+  return 1024 + P_STAGES * P_STAGE_BYTES + sizeof(PSmem) + 4 * (hid + last + tiles) + 64;
+}
+
+static int pair_mode() {   // BGX_PAIR: 0 = off, 1 = on (default), 2 = wide mode even where the narrow one fits
+  static const int m = [] { const char* e = getenv("BGX_PAIR"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
+// 0 = not eligible, 1 = narrow (tiles in shared memory), 2 = wide (in-place global access)
+int spline_pair_eligible(const bgx_coupling_io* io, const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, int flags) {
+  if (!io || !net || !cfg || cfg->n_bins != P_NB || (flags & BGX_FLAG_BF16X6) || !pair_mode()) return 0;
+  const int L = net->n_layers;
+  if (L < 2 || L > 6) return 0;
+  for (int l = 0; l + 1 < L; ++l)
+    if (net->N[l] != 128) return 0;
+  for (int l = 0; l < L; ++l)
+    if (!net->Wb[0][l] || !net->Wb[1][l]) return 0;
+  if (net->spline_dims_per_pass != P_DPP || net->spline_stride != P_PS || net->spline_bias_pad != P_BPAD ||
+      !net->spline_bias)
+    return 0;
+  if (io->n_cond != 1 || io->n_tr != 1) return 0;
+  auto dense = [](const bgx_seg& s) { return s.stride == s.width; };
+  if (!dense(io->cond[0]) || !dense(io->tr_in[0]) || !dense(io->tr_out[0])) return 0;
+  if (io->cond[0].width != net->raw_width) return 0;
+  auto al16 = [](const bgx_seg& s) { return ((uintptr_t)s.ptr & 15) == 0; };
+  const bool narrow_ok = net->K[0] <= 128 && io->batch % 4 == 0 && al16(io->cond[0]) && al16(io->tr_in[0]) &&
+                         al16(io->tr_out[0]) &&
+                         pair_smem_bytes(net, io->tr_in[0].width, io->cond[0].width, false) <= 227 * 1024;
+  if (narrow_ok && pair_mode() != 2 && !(flags & BGX_FLAG_FORCE_WIDE)) return 1;
+  return pair_smem_bytes(net, io->tr_in[0].width, io->cond[0].width, true) <= 227 * 1024 ? 2 : 0;
+}
+
+int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, int flags,
+                         int mode, int* status, cudaStream_t st) {
+  const int L = net->n_layers;
+  const int d_t = io->tr_in[0].width;
+  if (net->N[L - 1] != ceil_div(d_t, P_DPP) * 128 || io->tr_out[0].width != d_t || !io->dlogp_out) return BGX_ERR_INVALID;
+  if (net->act < 0 || net->act > 3) return BGX_ERR_INVALID;
+  if (io->batch == 0) return BGX_OK;
+  const bool wide = mode == 2;
+  PArgs a{};
+  a.B = io->batch;
+  a.cond = io->cond[0].ptr; a.tin = io->tr_in[0].ptr; a.tout = const_cast<float*>(io->tr_out[0].ptr);
+  a.D_t = d_t; a.K0raw = io->cond[0].width;
+  mlp_to_dev(net, a.net);
+  int hid = 0;
+  for (int l = 0; l < L; ++l) {
+    a.wb[0][l] = (const uint16_t*)net->Wb[0][l];
+    a.wb[1][l] = (const uint16_t*)net->Wb[1][l];
+    a.ktiles[l] = ceil_div(net->K[l], 64);
+    if (l < L - 1) hid += net->Np[l];
+  }
+  a.hid_bias_floats = hid;
+  a.npass = net->N[L - 1] / 128;
+  a.last_bias_floats = a.npass * P_DPP * P_BPAD;
+  a.bias_last = net->spline_bias;
+  a.G = ceil_div(net->K[0], 128);
+  a.plain_cond = (net->K[0] == net->raw_width && net->periodic_scale == 0.f) ? 1 : 0;
+  SplineParams sp;
+  spline_params_from_cfg(cfg, sp);
+  {
+    const float wx = sp.right - sp.left, hy = sp.top - sp.bottom;
+    a.ck.left = sp.left; a.ck.right = sp.right; a.ck.bottom = sp.bottom; a.ck.top = sp.top;
+    a.ck.wscale = wx * (1.f - sp.min_w * P_NB); a.ck.hscale = hy * (1.f - sp.min_h * P_NB);
+    a.ck.wstep = wx * sp.min_w; a.ck.hstep = hy * sp.min_h;
+    a.ck.min_d = sp.min_d; a.ck.beta = sp.beta; a.ck.beta_l2e = sp.beta * LOG2E;
+    a.ck.ln2_over_beta = LN2 * sp.inv_beta;
+  }
+  a.oob = sp.oob;
+  a.dlogp_in = io->dlogp_in;
+  a.dlogp_out = io->dlogp_out;
+  a.status = status;
+  a.ntiles = (a.B + P_TM - 1) / P_TM;
+  a.npairs = (a.ntiles + 1) / 2;
+  const size_t smem = pair_smem_bytes(net, d_t, a.K0raw, wide);
+  static int sm_count = 0;
+  int rc;
+  if (!sm_count) {
+    int dev = 0;
+    rc = check(cudaGetDevice(&dev));
+    if (rc) return rc;
+    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (rc) return rc;
+  }
+  using KernT = void (*)(const PArgs);
+#define BGX_P_ROW(INV, W) \
+  {spline_coupling_pair_kernel<INV, 0, W>, spline_coupling_pair_kernel<INV, 1, W>, \
+   spline_coupling_pair_kernel<INV, 2, W>, spline_coupling_pair_kernel<INV, 3, W>}
+  static const KernT kerns[2][2][4] = {{BGX_P_ROW(false, false), BGX_P_ROW(true, false)},
+                                       {BGX_P_ROW(false, true), BGX_P_ROW(true, true)}};
+#undef BGX_P_ROW
+  const int inv = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
+  KernT kern = kerns[wide ? 1 : 0][inv][net->act];
+  static size_t configured[2][2][4] = {};
+  if (smem > configured[wide ? 1 : 0][inv][net->act]) {
+    rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    configured[wide ? 1 : 0][inv][net->act] = smem;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(a.npairs, (long long)sm_count);
+  kern<<<grid, P_THREADS, smem, st>>>(a);
+  return post_launch();
+}
+
+}  // namespace bgx

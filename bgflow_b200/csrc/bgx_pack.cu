@@ -59,6 +59,15 @@ __global__ void pack_tc_tiles_kernel(const float* __restrict__ W, const int* __r
   t3[off] = b3;
 }
 
+// last-layer bias of a spline net once more, 16-byte aligned per dim: [pass][dim][pad]
+__global__ void pack_bias_pad_kernel(const float* __restrict__ bias, int npass, int dpp, int ps, int pad,
+                                     float* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npass * dpp * pad) return;
+  int c = idx / (dpp * pad), r = idx - c * (dpp * pad), d = r / pad, k = r - d * pad;
+  out[idx] = (k < ps) ? bias[c * 128 + d * ps + k] : 0.f;
+}
+
 static int spline_dims_per_pass(int n_bins) { return 128 / (3 * n_bins + 1); }
 
 }  // namespace bgx
@@ -130,6 +139,12 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
       off += (int64_t)kp64[l] * pk.Np[l] / 2;
     }
   }
+  int64_t o_bpad = off;
+  if (is_spline) {
+    pk.spline_bias_pad = round_up(pk.spline_stride, 4);
+    off += (int64_t)(pk.Np[L - 1] / 128) * pk.spline_dims_per_pass * pk.spline_bias_pad;
+    off = (off + 3) / 4 * 4;
+  }
   int64_t o_inmap = off; off += round_up(pk.Kp[0], 4);
   int64_t o_lastmap = off; off += (int64_t)last_map.size();
   off = (off + 3) / 4 * 4;
@@ -193,6 +208,14 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
     pk.Wt[l] = wt;
     pk.bias[l] = bb;
     for (int term = 0; term < 3; ++term) pk.Wb[term][l] = dst + o_t[term][l];
+    if (l == L - 1 && is_spline) {
+      const int npass = pk.Np[l] / 128, n = npass * pk.spline_dims_per_pass * pk.spline_bias_pad;
+      pack_bias_pad_kernel<<<(n + 255) / 256, 256, 0, st>>>(bb, npass, pk.spline_dims_per_pass, pk.spline_stride,
+                                                          pk.spline_bias_pad, dst + o_bpad);
+      rc = post_launch();
+      if (rc) return rc;
+      pk.spline_bias = dst + o_bpad;
+    }
   }
   *out = pk;
   return BGX_OK;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
     *done_flag = 0;
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -71,13 +71,39 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
 
   if (warp == 4) {
     if (lane == 0) {
-      const int nt = mode == 3 ? (K + 63) / 64 : ntile;     // bf16 tiles are 64 wide
+      const int nt = mode >= 3 ? (K + 63) / 64 : ntile;     // bf16 tiles are 64 wide
       const long long tb0 = clock64();
       mbar_expect_tx(b_full, (uint32_t)nt * 16384u);
       for (int t = 0; t < nt; ++t) bulk_g2s(Bs + t * 4096, Wsw + t * 4096, 16384u, b_full);
       mbar_wait(b_full, 0, status);
       status[2] = (int)(clock64() - tb0);     // cycles until all operand tiles have landed
       status[3] = nt;
+    }
+    __syncwarp();
+  } else if (warp == 5 && mode >= 4) {
+    // throughput probes of the production issue pattern: every lane runs the loop, one elected lane issues
+    // three bf16 products per k-step (mma3_bf16x3_elect); mode 4: N = 128, mode 5: N = 256 (accumulator
+    // columns [0,256), A operand at column 256; operands are whatever the tiles hold — timing only)
+    bool ok = mbar_wait(b_full, 0, status) && mbar_wait(a_ready, 0, status);
+    tc_fence_after();
+    const int N = mode == 5 ? 256 : 128;
+    const uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t acol = mode == 5 ? 256 : ST_A_COL;
+    const long long t0 = clock64();
+    if (ok)
+      for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t d1 = smem_desc_sw128(smem_u32(Bs)) + 2 * ks, d2 = smem_desc_sw128(smem_u32(Bs) + 32768) + 2 * ks;
+          mma3_bf16x3_elect(tmem + ST_ACC_COL, tmem + acol + ks * 8, tmem + acol + 64 + ks * 8, d1, d2, idesc, 1u);
+        }
+        if (v_commit && (rep % 2) == 1) mma_commit_elect(dummy_bar);     // one commit per 24 MMAs, as the kernels do
+      }
+    mma_commit_elect(acc_full);
+    mbar_wait(acc_full, 0, status);
+    if (lane == 0) {
+      status[1] = (int)(clock64() - t0);
+      *done_flag = 1;
     }
     __syncwarp();
   } else if (warp == 5) {
@@ -91,7 +117,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
         for (int rep = 0; rep < reps; ++rep)
           for (int ks = 0; ks < K / 16; ++ks) {
             const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
-            const uint32_t acol = ST_A_COL + ks * 8 + ((v_alt && (n & 1)) ? 64 : 0);
+            const uint32_t acol = ST_A_COL + ks * 8 + ((v_alt && (n & 1)) ? 64 : 0);   // (mode 3 only)
             mma_bf16_ts(tmem + ST_ACC_COL, tmem + acol, smem_desc_sw128(smem_u32(Bs) + off), idesc, (ks | rep) > 0);
             if (v_commit && (++n % 12) == 0) mma_commit(dummy_bar);
           }
@@ -121,7 +147,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
     // warps 0..3: TMEM lane quadrant = warp id
     const int row = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    if (mode == 3) {
+    if (mode >= 3) {
       for (int c = 0; c < K / 32; ++c) {       // 32 elements -> 16 packed columns
         uint32_t r[16];
 #pragma unroll
@@ -183,7 +209,7 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem);
+    tmem_dealloc<512>(tmem);
   }
 }
 
@@ -196,10 +222,10 @@ using namespace bgx;
 // loop when the mode carries a repeat count (mode | reps << 4; throughput probe, results then meaningless).
 extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                                int* status, void* stream) {
-  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 3 || mode < 0 || ((mode & 15) == 3 && K % 64))
+  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 5 || mode < 0 || ((mode & 15) >= 3 && K % 64))
     return BGX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  if ((mode & 15) == 3) st_swizzle_w_bf16<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, (unsigned short*)scratch);
+  if ((mode & 15) >= 3) st_swizzle_w_bf16<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, (unsigned short*)scratch);
   else st_swizzle_w<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, scratch);
   int rc = post_launch();
   if (rc) return rc;

@@ -41,7 +41,10 @@ config = {"precision": "bf16x3", "force_simt": False,
           # couplings over several / strided tensors: gather each side into one dense buffer first when
           # the batch is large, so that the two-CTAs-per-SM kernels (dense single tensors only) apply;
           # the copies cost ~5 % of a block, the one-CTA kernel ~25 %
-          "gather_segments": True, "gather_min_rows": 4096}
+          "gather_segments": True, "gather_min_rows": 4096,
+          # spline blocks: "auto" (pair kernel where eligible), "pair_wide" (pair kernel, tiles accessed in
+          # place in global memory even where they fit shared memory), "tc2" (skip the pair kernel; A/B)
+          "spline_kernel": "auto"}
 
 _status = {}
 
@@ -70,6 +73,13 @@ def _mode_flags():
         f |= _lib.FLAG_BF16X6
     elif config.get("precision") != "bf16x3":
         raise ValueError("engine.config['precision'] must be 'bf16x6' or 'bf16x3'")
+    sk = config.get("spline_kernel", "auto")
+    if sk == "tc2":
+        f |= _lib.FLAG_NO_PAIR
+    elif sk == "pair_wide":
+        f |= _lib.FLAG_FORCE_WIDE
+    elif sk != "auto":
+        raise ValueError("engine.config['spline_kernel'] must be 'auto', 'pair_wide' or 'tc2'")
     return f
 
 

@@ -89,6 +89,10 @@ typedef struct bgx_packed_mlp {
   /* tensor-core layout (tcgen05 path): W = b1 + b2 + b3 exactly, three bf16 terms; per term
    * 16 KB SWIZZLE_128B tiles [Np/128][ceil(K/64)][128 x 64] bf16 (device pointers) */
   const void* Wb[3][BGX_MAX_LAYERS];
+  /* spline nets: the last layer's bias once more as [Np/128][dims_per_pass][spline_bias_pad] with
+   * spline_bias_pad = round_up(spline_stride, 4) (zero padded: 16-byte vector loads per dim) */
+  const float* spline_bias;
+  int32_t spline_bias_pad, reserved_;
 } bgx_packed_mlp;
 
 /* Last-layer re-layout request for a spline conditioner: the raw column layout of
@@ -130,6 +134,8 @@ typedef struct bgx_coupling_io {
 #define BGX_FLAG_CIRCULAR 4         /* affine.py:56-57: y %= 1 (shift-only) */
 #define BGX_FLAG_BF16X6 8           /* tensor-core path: 6 bf16 products (fp32-equivalent); default 3 (~2^-16) */
 #define BGX_FLAG_FORCE_SIMT 16      /* always use the generic fp32 SIMT kernel */
+#define BGX_FLAG_NO_PAIR 32         /* spline: skip the pair kernel (A/B against the two-CTAs-per-SM kernel) */
+#define BGX_FLAG_FORCE_WIDE 64      /* spline pair kernel: in-place global tile access even where the tile fits shared memory */
 
 /* y' = y * exp(ls) + mu   (forward)   |   y' = (y - mu) * exp(-ls)   (inverse)
  * mu = shift(cond), ls = tanh(scale(cond)) * exp(log_alpha);  dlogp = +-sum(ls).
@@ -302,6 +308,20 @@ int bgx_set_status_buffer(int32_t* device_int);
 /* Debug: subsequent tensor-core launches record a timeline of CTA 0 into `device_buffer`
  * ([0] = event count, then (clock64, code) pairs; 1 + 2*capacity uint64).  NULL disables. */
 int bgx_debug_set_trace(uint64_t* device_buffer, int capacity);
+
+/* Which kernel family served the coupling calls so far (tests assert the tensor-core path ran). */
+#define BGX_KERNEL_SPLINE_PAIR 0        /* spline_coupling_pair_kernel, tiles in shared memory */
+#define BGX_KERNEL_SPLINE_PAIR_WIDE 1   /* spline_coupling_pair_kernel, wide (config 5) mode */
+#define BGX_KERNEL_SPLINE_TC2 2
+#define BGX_KERNEL_SPLINE_TC 3
+#define BGX_KERNEL_SPLINE_SIMT 4
+#define BGX_KERNEL_AFFINE_TC2 5
+#define BGX_KERNEL_AFFINE_TC 6
+#define BGX_KERNEL_AFFINE_SIMT 7
+#define BGX_KERNEL_AFFINE_PAIR 8
+#define BGX_KERNEL_AFFINE_PAIR_WIDE 9
+#define BGX_KERNEL_IDS 16
+int64_t bgx_kernel_count(int kernel_id);
 
 const char* bgx_version(void);
 const char* bgx_last_cuda_error(void);

@@ -1,0 +1,125 @@
+"""The pair kernel (bgx_coupling_pair.cu): narrow (tiles in shared memory) and wide (BASELINE config 5:
+D = 384 / 3072, tiles accessed in place) against the fp64 oracle and the reference goldens, both
+directions, ragged / odd tile counts, and proof that the TENSOR-CORE kernel served the call
+(``bgx_kernel_count``), not the SIMT fallback.
+
+Tolerances as tests/test_gpu_coupling.py: y 1e-5 abs+rel per block, dlogp 1e-3 over a stack (the log-det of a
+D_t = 1536 block sums 1536 terms: 2e-3 there)."""
+
+import numpy as np
+import pytest
+import torch
+
+from bgflow_b200 import _lib, engine
+from oracle import flows as of
+from conftest import load_golden
+from helpers import stack_from
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _status_check():
+    old = dict(engine.config)
+    yield
+    engine.check_pipeline_status(DEV)
+    engine.config.clear()
+    engine.config.update(old)
+
+
+def _delta(before, after):
+    return {k: after[k] - before[k] for k in after if after[k] != before[k]}
+
+
+def _run_vs_oracle(dim, n_blocks, batch, seed, ytol, dtol):
+    blocks, split = of.make_stack("spline", dim, n_blocks, seed=seed)
+    blocks64, _ = of.make_stack("spline", dim, n_blocks, seed=seed, dtype=torch.float64)
+    flow = stack_from(blocks, split, DEV)
+    g = torch.Generator().manual_seed(seed + batch)
+    z = torch.rand(batch, dim, generator=g)
+    x_ref, d_ref = of.coupling_stack(blocks64, z.double(), split)
+    zi_ref, di_ref = of.coupling_stack(blocks64, z.double(), split, inverse=True)
+    with torch.no_grad():
+        x, d = flow(z.to(DEV))
+        zi, di = flow(z.to(DEV), inverse=True)
+    np.testing.assert_allclose(x.cpu().double().numpy(), x_ref.numpy(), atol=ytol, rtol=ytol, err_msg="forward x")
+    np.testing.assert_allclose(d.cpu().double().numpy(), d_ref.numpy(), atol=dtol, rtol=1e-5, err_msg="forward dlogp")
+    np.testing.assert_allclose(zi.cpu().double().numpy(), zi_ref.numpy(), atol=ytol, rtol=ytol, err_msg="inverse x")
+    np.testing.assert_allclose(di.cpu().double().numpy(), di_ref.numpy(), atol=dtol, rtol=1e-5, err_msg="inverse dlogp")
+
+
+@pytest.mark.parametrize("dim,batch", [(384, 300), (384, 1), (384, 129), (3072, 260), (66, 515), (130, 1000)])
+def test_wide_mode_against_fp64_oracle(dim, batch):
+    """Config 5 shapes: conditioner 192-128-128-4800 / 1536-128-128-38400 (layer 0 k-tiled in groups of 128,
+    last layer 39 / 308 passes), ragged batches (not multiples of 4 or 128), odd tile counts."""
+    engine.config["spline_kernel"] = "pair_wide" if dim <= 130 else "auto"
+    before = _lib.kernel_counts()
+    _run_vs_oracle(dim, 2, batch, seed=3, ytol=2e-5, dtol=2e-3 if dim > 1000 else 1e-3)
+    got = _delta(before, _lib.kernel_counts())
+    assert got == {"spline_pair_wide": 4}, got      # 2 blocks x 2 directions, all on the tensor-core kernel
+
+
+@pytest.mark.parametrize("batch", [4, 128, 132, 256 + 128 + 8, 4096 + 4])
+def test_narrow_mode_against_fp64_oracle(batch):
+    """D = 66 (33 | 33): tiles staged in shared memory by bulk TMA; one / two / odd numbers of tiles."""
+    before = _lib.kernel_counts()
+    _run_vs_oracle(66, 3, batch, seed=5, ytol=2e-5, dtol=1e-3)
+    got = _delta(before, _lib.kernel_counts())
+    assert got == {"spline_pair": 6}, got
+
+
+@pytest.mark.parametrize("mode", ["auto", "pair_wide"])
+def test_reference_golden_on_the_pair_kernel(mode):
+    engine.config["spline_kernel"] = mode
+    g = load_golden("spline_d66_8blk")
+    dim, n_blocks, batch, seed = (int(v) for v in g["meta"][:4])
+    hidden = tuple(int(v) for v in g["meta"][4:])
+    blocks, split = of.make_stack("spline", dim, n_blocks, hidden=hidden, seed=seed)
+    flow = stack_from(blocks, split, DEV)
+    before = _lib.kernel_counts()
+    with torch.no_grad():
+        x, dlogp = flow(torch.from_numpy(g["z_f32"]).to(DEV))
+        zi, dlogpi = flow(torch.from_numpy(g["x_f32"]).to(DEV), inverse=True)
+    got = _delta(before, _lib.kernel_counts())
+    assert got == {"spline_pair_wide" if mode == "pair_wide" or batch % 4 else "spline_pair": 2 * n_blocks}, got
+    np.testing.assert_allclose(x.cpu().double().numpy(), g["x_f64"], atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(dlogp.cpu().double().numpy(), g["dlogp_f64"], atol=1e-3, rtol=1e-4)
+    np.testing.assert_allclose(zi.cpu().double().numpy(), g["zi_f64"], atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(dlogpi.cpu().double().numpy(), g["dlogpi_f64"], atol=1e-3, rtol=1e-4)
+
+
+def test_pair_kernel_matches_two_cta_kernel_bitwise():
+    """Same operand splits, same MMA order, same epilogue arithmetic: the pair kernel (both modes) and the
+    two-CTAs-per-SM kernel must agree bit for bit, over many tiles per CTA (B = 2^17 + 4: 1025 tiles)."""
+    blocks, split = of.make_stack("spline", 66, 2, seed=0)
+    flow = stack_from(blocks, split, DEV)
+    g = torch.Generator().manual_seed(9)
+    z = torch.rand((1 << 17) + 4, 66, generator=g).to(DEV)
+    out = {}
+    with torch.no_grad():
+        for mode in ("tc2", "auto", "pair_wide"):
+            engine.config["spline_kernel"] = mode
+            out[mode] = flow(z) + flow(z, inverse=True)
+    for mode in ("auto", "pair_wide"):
+        for a, b in zip(out["tc2"], out[mode]):
+            assert torch.equal(a, b), (mode, float((a - b).abs().max()))
+
+
+def test_out_of_domain_inputs_are_clamped_and_counted():
+    """spline.py:145-155: inputs outside [left, right] are clamped (and counted on the device)."""
+    import bgflow_b200 as bg
+    blocks, split = of.make_stack("spline", 384, 1, seed=1)
+    flow = stack_from(blocks, split, DEV)
+    z = torch.rand(200, 384, generator=torch.Generator().manual_seed(2))
+    z[5, 200] = 1.5        # second half = the transformed side of block 0
+    z[7, 300] = -0.25
+    with torch.no_grad():
+        x, d = flow(z.to(DEV))
+    tr = [m for m in flow.modules() if isinstance(m, bg.ConditionalSplineTransformer)][0]
+    with pytest.warns(UserWarning):
+        assert tr.out_of_domain_count() == 2
+    blocks64, _ = of.make_stack("spline", 384, 1, seed=1, dtype=torch.float64)
+    x_ref, d_ref = of.coupling_stack(blocks64, z.clamp(0.0, 1.0).double(), split)
+    np.testing.assert_allclose(x.cpu().double().numpy(), x_ref.numpy(), atol=2e-5, rtol=2e-5)
+    np.testing.assert_allclose(d.cpu().double().numpy(), d_ref.numpy(), atol=1e-3, rtol=1e-5)

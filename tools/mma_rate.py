@@ -38,3 +38,15 @@ for label, bits in (("baseline", 0), ("commit every 12", 1 << 28), ("alternate A
     torch.cuda.synchronize()
     n = reps * K // 16
     print(f"{label:24s}: {int(st[1]) / n:.1f} cycles/MMA (rc={rc}, timeout={int(st[0])})")
+
+print("--- production issue pattern (warp-wide loop, elected lane, 3 products per k-step), 12 MMAs per rep")
+for mode, name, cols in ((4, "bf16x3 TS N=128", 128), (5, "bf16x3 TS N=256", 256)):
+    for label, bits in (("no commits", 0), ("commit every 24 MMAs", 1 << 28)):
+        st = torch.zeros(4, dtype=torch.int32, device=dev)
+        reps = 512
+        word = mode | (reps << 4) | bits
+        rc = lib.bgx_tc_selftest(word, A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(), st.data_ptr(), None)
+        torch.cuda.synchronize()
+        n = reps * 12
+        cyc = int(st[1]) / n
+        print(f"{name:18s} {label:22s}: {cyc:6.1f} cycles/MMA = {cyc * 128 / cols:6.1f} per 128x128x16 (rc={rc}, timeout={int(st[0])})")
