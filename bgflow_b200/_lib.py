@@ -111,6 +111,7 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "bgx_cdf_col_init": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, P(bgx_cdf_col)]),
+    "bgx_cdf_col_set_truncation": (C.c_int, [P(bgx_cdf_col), C.c_double, C.c_double]),
     "bgx_cdf_map": (C.c_int, [C.c_int64, C.c_int32, P(bgx_seg), P(bgx_seg), C.c_void_p, C.c_float, C.c_float,
                               C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_ic_to_xyz_mapped": (C.c_int, [P(bgx_zplan), C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64,

@@ -48,10 +48,14 @@ class _FusedCoupling(torch.autograd.Function):
                 tr = [x.detach().requires_grad_(True) for x in saved[ctx.n_cond:]]
                 out, dlogp = _torch_math.affine(t, torch.cat(cond, dim=-1), torch.cat(tr, dim=-1), ctx.inverse)
                 outs = torch.split(out, [x.shape[-1] for x in tr], dim=-1)
-                g_all = torch.autograd.grad([*outs, dlogp], [*cond, *tr, *params],
-                                            grad_outputs=[g if g is not None else torch.zeros_like(o)
-                                                          for g, o in zip(grads, [*outs, dlogp])],
-                                            allow_unused=True)
+                # only outputs that carry a graph and an upstream gradient: for a shift-only (NICE) or
+                # identity transformer dlogp is a constant zero without a grad_fn (affine.py:41-47)
+                pairs = [(o, g) for o, g in zip([*outs, dlogp], grads) if g is not None and o.requires_grad]
+                if pairs:
+                    g_all = torch.autograd.grad([o for o, _ in pairs], [*cond, *tr, *params],
+                                                grad_outputs=[g for _, g in pairs], allow_unused=True)
+                else:
+                    g_all = (None,) * (ctx.n_cond + ctx.n_tr + len(params))
                 g_tr = g_all[ctx.n_cond:ctx.n_cond + ctx.n_tr]
                 gin = (*g_all[:ctx.n_cond], *g_all[ctx.n_cond + ctx.n_tr:])
         g_cond = gin[:ctx.n_cond]

@@ -165,7 +165,13 @@ def marginal_columns(distribution, width):
     if all(isinstance(getattr(d, a, None), torch.Tensor) for a in ("_mu", "_logsigma", "_lower_bound", "_upper_bound")):
         mu, sg = _per_column(d._mu, width), _per_column(torch.exp(d._logsigma), width)
         lo, hi = _per_column(d._lower_bound, width), _per_column(d._upper_bound, width)
-        return [(_lib.DIST_TRUNCNORMAL, m, s, l, h) for m, s, l, h in zip(mu, sg, lo, hi)]
+        cols = [(_lib.DIST_TRUNCNORMAL, m, s, l, h) for m, s, l, h in zip(mu, sg, lo, hi)]
+        # the reference evaluates cdf / icdf / log_prob with the Phi bounds frozen at construction
+        # (normal.py:148-151, possibly stale after training or a checkpoint load): hand exactly those over
+        clo, chi = getattr(d, "_cdf_lower_bound", None), getattr(d, "_cdf_upper_bound", None)
+        if isinstance(clo, torch.Tensor) and isinstance(chi, torch.Tensor):
+            cols = [c + (a, b) for c, a, b in zip(cols, _per_column(clo, width), _per_column(chi, width))]
+        return cols
     if isinstance(d, torch.distributions.Normal):
         return [(_lib.DIST_NORMAL, m, s, 0.0, 0.0)
                 for m, s in zip(_per_column(d.loc, width), _per_column(d.scale, width))]
@@ -180,7 +186,8 @@ def marginal_columns(distribution, width):
 
 def _dist_tensors(distribution):
     d = distribution
-    names = ("_mu", "_logsigma", "_lower_bound", "_upper_bound", "loc", "scale", "low", "high")
+    names = ("_mu", "_logsigma", "_lower_bound", "_upper_bound", "_cdf_lower_bound", "_cdf_upper_bound", "loc", "scale",
+             "low", "high")
     if isinstance(d, torch.distributions.Independent):
         d = d.base_dist
     return [getattr(d, n) for n in names if isinstance(getattr(d, n, None), torch.Tensor)]

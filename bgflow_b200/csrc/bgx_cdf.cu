@@ -109,6 +109,16 @@ extern "C" int bgx_cdf_col_init(int32_t kind, double a, double b, double lower, 
   return cdf_col_init_host(kind, a, b, lower, upper, out);
 }
 
+extern "C" int bgx_cdf_col_set_truncation(bgx_cdf_col* col, double cdf_lower, double cdf_upper) {
+  if (!col || col->kind != BGX_DIST_TRUNCNORMAL) return BGX_ERR_INVALID;
+  const double Z = cdf_upper - cdf_lower;
+  if (!(Z > 0.0)) return BGX_ERR_INVALID;
+  col->p[CP_CDF_LO] = (float)cdf_lower;
+  col->p[CP_Z] = (float)Z;
+  col->p[CP_LOGNORM] = (float)(::log(Z * (double)col->p[CP_SCALE]) + 0.91893853320467274178);
+  return BGX_OK;
+}
+
 extern "C" int bgx_cdf_map(int64_t batch, int32_t n_seg, const bgx_seg* in, const bgx_seg* out,
                            const bgx_cdf_col* cols, float clamp_lo, float clamp_hi, float logdet_min, int flags,
                            const float* dlogp_in, float* dlogp_out, void* stream) {

@@ -39,7 +39,7 @@ namespace bgx {
 using namespace tc;
 
 constexpr int P_EPI_WARPS = 16;
-constexpr int P_THREADS = (P_EPI_WARPS + 3) * 32;     // 608
+constexpr int P_THREADS = (P_EPI_WARPS + 4) * 32;     // 640
 constexpr int P_TM = 128;
 constexpr int P_STAGES = 2;
 constexpr uint32_t P_TILE_BYTES = 16384;              // one [128 x 64] bf16 k-tile of one term
@@ -76,12 +76,59 @@ struct alignas(16) PSmem {
   uint64_t acc_empty[2];   // 16: last-layer pass pulled into registers
   uint64_t y_full[2], c_full[2];   // 1 + tx (narrow mode)
   uint64_t y_done[2], c_free[2];   // 16
+  uint64_t dl_ready[2];    // 16: the four dim shares of every row's log-det are written
+  uint64_t dl_free[2];     // 1: ... and summed (the buffer may be rewritten)
   uint32_t tmem_base, pad[3];
-  float dl_part[2][2][4][P_TM];    // [iteration parity][slot][dim share][row]
+  float dl_part[2][4][P_TM];       // [slot][dim share][row]
 };
 
+// Layer-0 operand of one slot: inputs 128 g + [32 j, 32 j + 32) of this thread's row -> two exact bf16 terms in
+// tensor memory.  Out of line on purpose: three call sites, and the epilogue's hot loop has to stay inside
+// the instruction cache (the first version of this kernel inlined it everywhere and lost 27 % of its warp
+// samples to instruction fetch).  WrapPeriodic (periodic.py:30-37) through sinpi / cospi: no slow path.
+__device__ __noinline__ void pair_stage_x(const PArgs& a, const float* crow, bool live, int g, int j, uint32_t a_col) {
+  const int K0 = a.net.K[0];
+  const int kg = 128 * g;                 // first input of the group
+  const int kend = min(K0, kg + 128);     // one past the last real input of the group
+  const float inv_pi_scale = a.net.pscale * 0.3183098861837907f;
+  // this warp's 32 inputs as two 16-input halves (8 packed columns each); a half is written iff the MMAs of
+  // the group read it (their k-steps cover inputs [kg, round_up(kend, 16)))
+  for (int h = 0; h < 2; ++h) {
+    const int b0 = kg + j * 32 + h * 16;
+    if (b0 >= kend) break;
+    float xv[16];
+    if (a.plain_cond) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) xv[i] = (live && b0 + i < kend) ? crow[b0 + i] : 0.f;
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 16; ++i) {
+        float v = 0.f;
+        if (live && b0 + i < kend) {
+          const int code = a.net.in_map[b0 + i];
+          v = crow[code & 0xffffff];
+          const int kind = code >> 24;
+          if (kind) {
+            const float t = (v - a.net.pleft) * inv_pi_scale;
+            v = kind == 1 ? cospif(t) : sinpif(t);
+          }
+        }
+        xv[i] = v;
+      }
+    }
+    uint32_t t1[8], t2[8], t3[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16(xv[2 * i], xv[2 * i + 1], 2, t1[i], t2[i], t3[i]);
+    const uint32_t col = a_col + (uint32_t)((b0 - kg) / 2);
+    tmem_st8(col, t1);
+    tmem_st8(col + P_A_STRIDE, t2);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+}
+
 template <bool INVERSE, int ACT, bool WIDE>
-__global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(const PArgs a) {
+__global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(const __grid_constant__ PArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = base;
@@ -108,6 +155,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       mbar_init(&S->c_full[s], 1);
       mbar_init(&S->y_done[s], P_EPI_WARPS);
       mbar_init(&S->c_free[s], P_EPI_WARPS);
+      mbar_init(&S->dl_ready[s], P_EPI_WARPS);
+      mbar_init(&S->dl_free[s], 1);
     }
     fence_mbar_init();
   }
@@ -138,7 +187,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       long long nfill = 0;
       auto fill = [&](int l, int c, int t0, int nt) -> bool {
         if (nfill >= P_STAGES) {
-          if (!mbar_wait(&S->w_empty[stage], ph_e[stage], a.status)) return false;
+          if (!mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status)) return false;
           ph_e[stage] ^= 1;
         }
         uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
@@ -187,7 +236,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
         // conditioner tile of iteration k+1: the buffer is free once iteration k's operand is staged
         for (int s = 0; s < 2 && ok; ++s) {
           if (tile_of(k, s) >= a.ntiles || k + 1 >= n_my) continue;
-          ok = mbar_wait(&S->c_free[s], ph_cf[s], a.status);
+          ok = mbar_wait_sleep(&S->c_free[s], ph_cf[s], a.status);
           ph_cf[s] ^= 1;
           load_c(k + 1, s);
         }
@@ -195,7 +244,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
         for (int s = 0; s < 2 && ok; ++s) {
           const long long tile = tile_of(k, s);
           if (tile >= a.ntiles) continue;
-          ok = mbar_wait(&S->y_done[s], ph_yd[s], a.status);
+          ok = mbar_wait_sleep(&S->y_done[s], ph_yd[s], a.status);
           ph_yd[s] ^= 1;
           if (!ok) break;
           bulk_s2g(a.tout + tile * P_TM * (long long)a.D_t, ybuf + s * ystride, (uint32_t)(rows_of(tile) * a.D_t * 4));
@@ -206,6 +255,29 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
+  } else if (warp == 19) {
+    // ------------------------------------------------------------------ log-det reducer: sums the four dim shares
+    // of every row in a fixed order (deterministic) and adds the running dlogp; keeps that wait off the epilogue warps
+    uint32_t ph_r[2] = {0, 0};
+    bool ok = true;
+    for (long long it = 0; it < n_my && ok; ++it)
+      for (int s = 0; s < 2 && ok; ++s) {
+        const long long tile = tile_of(it, s);
+        if (tile >= a.ntiles) continue;
+        ok = mbar_wait_sleep(&S->dl_ready[s], ph_r[s], a.status);
+        ph_r[s] ^= 1;
+        const float* dl = &S->dl_part[s][0][0];
+#pragma unroll
+        for (int r = lane; r < P_TM; r += 32) {
+          const long long row = tile * P_TM + r;
+          if (row < a.B) {
+            const float base_dl = a.dlogp_in ? a.dlogp_in[row] : 0.f;
+            a.dlogp_out[row] = base_dl + ((dl[r] + dl[P_TM + r]) + (dl[2 * P_TM + r] + dl[3 * P_TM + r]));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->dl_free[s]);
+      }
   } else if (warp == 18) {
     // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
     const uint32_t idesc = idesc_bf16(128, 128);
@@ -215,12 +287,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
     bool ok = true;
     // one unit on both slots: `wait_a` = a freshly staged A operand is needed, `wait_e` = the accumulator must
     // have been pulled by the epilogue (a last-layer pass preceded), `accum` = keep the accumulator (layer-0 group > 0)
-    auto unit = [&](int nslots, int K, int kcol0, bool wait_a, bool wait_e, bool accum) {
+    auto unit = [&](int nslots, int K, bool wait_a, bool wait_e, bool accum) {
       if (!ok) return;
       ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
       ph_wf[stage] ^= 1;
       const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
       const int ksteps = (K + 15) / 16;
+#pragma unroll 1
       for (int s = 0; s < nslots && ok; ++s) {
         if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
         if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
@@ -228,16 +301,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
         tc_fence_after();
         const uint32_t acc_addr = tmem + s * P_SLOT + P_ACC;
         uint32_t acc = accum ? 1u : 0u;
+#pragma unroll 1
         for (int t = 0; t * 4 < ksteps; ++t) {
           const uint32_t b1 = sb + (uint32_t)t * P_KT_BYTES, b2 = b1 + P_TILE_BYTES;
           const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);
-          const uint32_t a1 = tmem + s * P_SLOT + P_A + (uint32_t)(kcol0 + t * 32), a2 = a1 + P_A_STRIDE;
+          const uint32_t a1 = tmem + s * P_SLOT + P_A + (uint32_t)(t * 32), a2 = a1 + P_A_STRIDE;
           const int nk = min(4, ksteps - t * 4);
           if (nk == 4) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               mma3_bf16x3_elect(acc_addr, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
           } else {
+#pragma unroll 1
             for (int ks = 0; ks < nk; ++ks)
               mma3_bf16x3_elect(acc_addr, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
           }
@@ -248,11 +323,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       mma_commit_elect(&S->w_empty[stage]);     // both slots' MMAs on this stage are issued: release it when they finish
       stage ^= 1;
     };
+    const int U = G + (L - 2) + P;
     for (long long it = 0; it < n_my && ok; ++it) {
       const int nslots = (tile_of(it, 1) < a.ntiles) ? 2 : 1;
-      for (int g = 0; g < G; ++g) unit(nslots, min(128, a.net.K[0] - 128 * g), 0, true, g == 0 && it > 0, g > 0);
-      for (int l = 1; l < L - 1; ++l) unit(nslots, a.net.K[l], 0, true, false, false);
-      for (int c = 0; c < P; ++c) unit(nslots, a.net.K[L - 1], 0, c == 0, c > 0, false);
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+        if (u < G) unit(nslots, min(128, a.net.K[0] - 128 * u), true, u == 0 && it > 0, u > 0);
+        else if (u < G + L - 2) unit(nslots, a.net.K[u - G + 1], true, false, false);
+        else unit(nslots, a.net.K[L - 1], u == G + L - 2, u > G + L - 2, false);
+      }
     }
     __syncwarp();
   } else {
@@ -260,197 +339,157 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
     const int q = warp & 3, j = warp >> 2;            // TMEM lane quadrant, column / dim share
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t ph_acc[2] = {0, 0}, ph_c[2] = {0, 0}, ph_y[2] = {0, 0};
-    const int K0 = a.net.K[0];
+    uint32_t ph_acc[2] = {0, 0}, ph_c[2] = {0, 0}, ph_y[2] = {0, 0}, ph_df[2] = {0, 0};
     bool ok = true;
 
-    // layer-0 operand: inputs 128 g + [32 j, 32 j + 32) of this thread's row -> two bf16 terms in TMEM
     auto stage_x = [&](long long it, int s, int g) {
-      const long long tile = tile_of(it, s);
-      const long long row = tile * P_TM + r_in_tile;
-      const int kg = 128 * g;                 // first input of the group
-      const int kend = min(K0, kg + 128);     // one past the last real input of the group
+      const long long row = tile_of(it, s) * P_TM + r_in_tile;
       if (!WIDE && g == 0) {
-        ok = ok && mbar_wait(&S->c_full[s], ph_c[s], a.status);
+        ok = ok && mbar_wait_sleep(&S->c_full[s], ph_c[s], a.status);
         ph_c[s] ^= 1;
       }
       const float* crow = WIDE ? a.cond + row * (long long)a.K0raw : cbuf + (s * P_TM + r_in_tile) * a.K0raw;
-      const bool live = !WIDE || row < a.B;
-      auto cond_value = [&](int k) -> float {
-        if (k >= kend || !live) return 0.f;
-        if (a.plain_cond) return crow[k];
-        const int code = a.net.in_map[k];
-        const float v = crow[code & 0xffffff];
-        const int kind = code >> 24;
-        if (kind == 0) return v;
-        const float arg = (v - a.net.pleft) * a.net.pscale;
-        return kind == 1 ? cosf(arg) : sinf(arg);
-      };
-      // this warp's 32 inputs as two 16-input halves (8 packed columns each); a half is written iff the
-      // MMAs of the group read it (k-steps cover inputs [kg, round_up(kend, 16)))
-      for (int h = 0; h < 2; ++h) {
-        const int b0 = kg + j * 32 + h * 16;
-        if (b0 >= kend) break;
-        uint32_t t1[8], t2[8], t3[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split_bf16(cond_value(b0 + 2 * i), cond_value(b0 + 2 * i + 1), 2, t1[i], t2[i], t3[i]);
-        const uint32_t col = tmem + lane_base + s * P_SLOT + P_A + (uint32_t)((b0 - kg) / 2);
-        tmem_st8(col, t1);
-        tmem_st8(col + P_A_STRIDE, t2);
-      }
-      tmem_st_wait();
-      tc_fence_before();
+      pair_stage_x(a, crow, !WIDE || row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&S->a_ready[s]);
         if (!WIDE && g == 0) mbar_arrive(&S->c_free[s]);
       }
     };
-
-    // hidden layer: accumulator columns [32 j, 32 j + 32) -> bias, activation, exact bf16 split -> A operand
-    auto hidden = [&](int s, int boff) {
-      uint32_t v[32];
-      tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
-      tmem_ld_wait();
-      uint32_t t1[16], t2[16], t3[16];
-      const float4* b4 = reinterpret_cast<const float4*>(bias_h + boff + j * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 bb = b4[i];
-        const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
-        const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
-        const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
-        const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
-        split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
-        split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
-      }
-      const uint32_t acol = tmem + lane_base + s * P_SLOT + P_A + j * 16;
-      tmem_st16(acol, t1);
-      tmem_st16(acol + P_A_STRIDE, t2);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S->a_ready[s]);
-    };
-
     auto wait_acc = [&](int s) {
-      ok = ok && mbar_wait(&S->acc_full[s], ph_acc[s], a.status);
+      ok = ok && mbar_wait_sleep(&S->acc_full[s], ph_acc[s], a.status);
       ph_acc[s] ^= 1;
       tc_fence_after();
     };
 
     float ld[2];
     int n_oob = 0;
+    const int U = (G - 1) + (L - 1) + P;      // staging events of layer-0 groups 1.., hidden layers, last-layer passes
     for (long long it = 0; it < n_my; ++it) {
       const int nslots = (tile_of(it, 1) < a.ntiles) ? 2 : 1;
       if (it == 0)
         for (int s = 0; s < nslots; ++s) stage_x(0, s, 0);
-      // ---- layer 0: groups of 128 inputs; the last group's accumulator is the hidden layer's input
-      for (int g = 0; g < G; ++g)
-        for (int s = 0; s < nslots; ++s) {
-          wait_acc(s);
-          if (g < G - 1) stage_x(it, s, g + 1);
-          else hidden(s, 0);
-        }
-      // ---- hidden layers 1 .. L-2
-      int boff = a.net.Np[0];
-      for (int l = 1; l < L - 1; ++l) {
-        for (int s = 0; s < nslots; ++s) {
-          wait_acc(s);
-          hidden(s, boff);
-        }
-        boff += a.net.Np[l];
-      }
-      // ---- last layer: pass c holds dims 5c .. 5c+4; this warp takes the dims i with (i + c) % 4 == j
       ld[0] = ld[1] = 0.f;
-      for (int c = 0; c < P; ++c) {
-        const int i0 = (j - c) & 3;
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+#pragma unroll 1
         for (int s = 0; s < nslots; ++s) {
-          const long long row = tile_of(it, s) * P_TM + r_in_tile;
-          const bool live = row < a.B;
-          if (!WIDE && c == 0) {
-            ok = ok && mbar_wait(&S->y_full[s], ph_y[s], a.status);
-            ph_y[s] ^= 1;
-          }
-          const int d0 = P_DPP * c + i0;                 // first dim of this warp in the pass (second: d0 + 4, only if i0 == 0)
-          const int n_mine = (d0 < a.D_t ? 1 : 0) + ((i0 == 0 && d0 + 4 < a.D_t) ? 1 : 0);
-          // operands that do not depend on the accumulator first: the transformed inputs and (wide) the bias
-          float xin[2] = {0.f, 0.f};
-          if (WIDE) {
-            if (live && n_mine > 0) xin[0] = a.tin[row * (long long)a.D_t + d0];
-            if (live && n_mine > 1) xin[1] = a.tin[row * (long long)a.D_t + d0 + 4];
-          } else {
-            const float* yrow = ybuf + (s * P_TM + r_in_tile) * a.D_t;
-            if (n_mine > 0) xin[0] = yrow[d0];
-            if (n_mine > 1) xin[1] = yrow[d0 + 4];
-          }
-          const float* bsrc = (WIDE ? a.bias_last : bias_l) + ((size_t)c * P_DPP + i0) * P_BPAD;
-          float p[P_BPAD];
-          if (n_mine > 0) {
-            const float4* b4 = reinterpret_cast<const float4*>(bsrc);
-#pragma unroll
-            for (int qq = 0; qq < 7; ++qq) {
-              const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
-              p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
-            }
-          }
-          wait_acc(s);
-          const uint32_t acc_addr = tmem + lane_base + s * P_SLOT + P_ACC;
-          for (int m = 0; m < n_mine; ++m) {
-            const int i = i0 + 4 * m;
+          if (u < G - 1) {
+            // ---- layer 0, group u done (its commit frees the A operand): stage group u + 1
+            wait_acc(s);
+            stage_x(it, s, u + 1);
+          } else if (u < G + L - 2) {
+            // ---- hidden layer l: accumulator columns [32 j, 32 j + 32) -> bias, activation, exact bf16 split -> A
+            const int l = u - (G - 1);
+            wait_acc(s);
             uint32_t v[32];
-            tmem_ld32(acc_addr + i * P_PS, v);
+            tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
             tmem_ld_wait();
-            if (m == n_mine - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&S->acc_empty[s]);
+            uint32_t t1[16], t2[16], t3[16];
+            const float4* b4 = reinterpret_cast<const float4*>(bias_h + l * 128 + j * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = b4[i];
+              const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
+              const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
+              const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
+              const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
+              split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
+              split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
             }
-            if (m == 1) {
-              const float4* b4 = reinterpret_cast<const float4*>(bsrc + 4 * P_BPAD);
+            const uint32_t acol = tmem + lane_base + s * P_SLOT + P_A + j * 16;
+            tmem_st16(acol, t1);
+            tmem_st16(acol + P_A_STRIDE, t2);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->a_ready[s]);
+          } else {
+            // ---- last layer: pass c holds dims 5c .. 5c+4; this warp takes the dims i with (i + c) % 4 == j
+            const int c = u - (G + L - 2);
+            const int i0 = (j - c) & 3;
+            const long long row = tile_of(it, s) * P_TM + r_in_tile;
+            const bool live = row < a.B;
+            if (!WIDE && c == 0) {
+              ok = ok && mbar_wait_sleep(&S->y_full[s], ph_y[s], a.status);
+              ph_y[s] ^= 1;
+            }
+            const int d0 = P_DPP * c + i0;               // first dim of this warp in the pass (second: d0 + 4, only if i0 == 0)
+            const int n_mine = (d0 < a.D_t ? 1 : 0) + ((i0 == 0 && d0 + 4 < a.D_t) ? 1 : 0);
+            float* yrow = WIDE ? a.tout + row * (long long)a.D_t : ybuf + (s * P_TM + r_in_tile) * a.D_t;
+            // operands that do not depend on the accumulator first: the transformed inputs and the bias
+            float xin[2] = {0.f, 0.f};
+            if (WIDE) {
+              if (live && n_mine > 0) xin[0] = a.tin[row * (long long)a.D_t + d0];
+              if (live && n_mine > 1) xin[1] = a.tin[row * (long long)a.D_t + d0 + 4];
+            } else {
+              if (n_mine > 0) xin[0] = yrow[d0];
+              if (n_mine > 1) xin[1] = yrow[d0 + 4];
+            }
+            const float* bsrc = (WIDE ? a.bias_last : bias_l) + ((size_t)c * P_DPP + i0) * P_BPAD;
+            float p[P_BPAD];
+            if (n_mine > 0) {
+              const float4* b4 = reinterpret_cast<const float4*>(bsrc);
 #pragma unroll
               for (int qq = 0; qq < 7; ++qq) {
                 const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
                 p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
               }
             }
-            float pp[P_PS];
+            wait_acc(s);
+            const uint32_t acc_addr = tmem + lane_base + s * P_SLOT + P_ACC;
+#pragma unroll 1
+            for (int m = 0; m < n_mine; ++m) {
+              const int i = i0 + 4 * m;
+              uint32_t v[32];
+              tmem_ld32(acc_addr + i * P_PS, v);
+              tmem_ld_wait();
+              if (m == n_mine - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S->acc_empty[s]);
+              }
+              if (m == 1) {
+                const float4* b4 = reinterpret_cast<const float4*>(bsrc + 4 * P_BPAD);
 #pragma unroll
-            for (int k = 0; k < P_PS; ++k) pp[k] = __uint_as_float(v[k]) + p[k];
-            float x = xin[m];
-            n_oob += (live && (x < a.ck.left || x > a.ck.right)) ? 1 : 0;
-            x = fminf(fmaxf(x, a.ck.left), a.ck.right);
-            float y, lad;
-            rqs_eval_reg<!INVERSE, true>(pp, a.ck, x, y, lad);
-            if (WIDE) {
-              if (live) a.tout[row * (long long)a.D_t + P_DPP * c + i] = y;
-            } else {
-              ybuf[(s * P_TM + r_in_tile) * a.D_t + P_DPP * c + i] = y;
+                for (int qq = 0; qq < 7; ++qq) {
+                  const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
+                  p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
+                }
+              }
+              float pp[P_PS];
+#pragma unroll
+              for (int k = 0; k < P_PS; ++k) pp[k] = __uint_as_float(v[k]) + p[k];
+              float x = xin[m];
+              n_oob += (live && (x < a.ck.left || x > a.ck.right)) ? 1 : 0;
+              x = fminf(fmaxf(x, a.ck.left), a.ck.right);
+              float y, lad;
+              rqs_eval_reg<!INVERSE, true>(pp, a.ck, x, y, lad);
+              if (!WIDE || live) yrow[P_DPP * c + i] = y;
+              ld[s] += lad;
             }
-            ld[s] += lad;
-          }
-          if (n_mine == 0) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S->acc_empty[s]);
-          }
-          if (c == P - 1) {
-            // ---- end of this slot's tile: hand the output tile to the I/O thread, reduce the log-det over
-            // the four dim shares, and stage the next tile's layer-0 operand (every MMA of the tile is done)
-            if (!WIDE) {
-              fence_async_smem();
+            if (n_mine == 0) {
+              tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&S->y_done[s]);
+              if (lane == 0) mbar_arrive(&S->acc_empty[s]);
             }
-            float* dl = &S->dl_part[it & 1][s][0][0];
-            dl[j * P_TM + r_in_tile] = ld[s];
-            asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory");
-            if (j == 0 && live) {
-              const float base_dl = a.dlogp_in ? a.dlogp_in[row] : 0.f;
-              a.dlogp_out[row] = base_dl + ((dl[r_in_tile] + dl[P_TM + r_in_tile]) +
-                                            (dl[2 * P_TM + r_in_tile] + dl[3 * P_TM + r_in_tile]));
+            if (c == P - 1) {
+              // ---- end of this slot's tile: hand the output tile to the I/O thread and the log-det shares to the
+              // reducer, then stage the next tile's layer-0 operand (every MMA of this tile is complete)
+              if (!WIDE) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S->y_done[s]);
+              }
+              if (it > 0) {
+                ok = ok && mbar_wait_sleep(&S->dl_free[s], ph_df[s], a.status);
+                ph_df[s] ^= 1;
+              }
+              S->dl_part[s][j][r_in_tile] = ld[s];
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&S->dl_ready[s]);
+              if (it + 1 < n_my && tile_of(it + 1, s) < a.ntiles) stage_x(it + 1, s, 0);
             }
-            if (it + 1 < n_my && tile_of(it + 1, s) < a.ntiles) stage_x(it + 1, s, 0);
           }
         }
       }

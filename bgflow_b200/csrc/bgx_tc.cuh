@@ -45,6 +45,31 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* t
   return false;
 }
 
+// Sleeping variant for roles that wait long (epilogue warps on an accumulator, producers on a free slot):
+// try_wait with a suspend-time hint parks the thread in hardware until the phase completes or the hint
+// expires, instead of re-issuing the poll every few cycles (the polling loops of the first kernels were a
+// quarter of all executed instructions and competed with the working warps for issue slots).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_sleep(uint64_t* bar, uint32_t parity, int* timeout_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  for (uint32_t it = 0; it < (1u << 18); ++it) {
+    if (mbar_try_wait_hint(bar, parity, 4000u)) return true;
+    if ((it & 0x3f) == 0x3f && timeout_flag && *(volatile int*)timeout_flag) return false;
+  }
+  if (timeout_flag) atomicExch(timeout_flag, 1);
+  return false;
+}
+
 // ---------------------------------------------------------------- bulk copy (TMA engine, no tensor map)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -6,6 +6,7 @@ in ``libbgflow_b200.so``.  Everything requires CUDA fp32 tensors — there is no
 """
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -32,6 +33,52 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _device_guard(fn):
+    """Every launch runs with the tensors' device current (the C ABI launches on the current device and
+    ``_stream()`` reads that device's current stream); tensors of one call must share their device."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+
+        def visit(a):
+            nonlocal dev
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    if dev is None:
+                        dev = a.device
+                    elif a.device != dev:
+                        raise RuntimeError(f"all tensors of one bgflow_b200 call must live on the same CUDA "
+                                           f"device (got {dev} and {a.device})")
+            elif isinstance(a, (list, tuple)):
+                for x in a:
+                    visit(x)
+        for a in args:
+            visit(a)
+        for a in kwargs.values():
+            visit(a)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+def _dlogp_arg(dlogp_in, B, device):
+    """Validate a running log-det accumulator: fp32, on ``device``, one value per sample (a broadcastable
+    ``[1, 1]`` is expanded).  Returns a dense ``[B]`` tensor or None."""
+    if dlogp_in is None:
+        return None
+    require_cuda_fp32(dlogp_in)
+    if dlogp_in.device != device:
+        raise RuntimeError("dlogp accumulator lives on another device than the flow state")
+    d = dlogp_in.reshape(-1)
+    if d.shape[0] == 1 and B != 1:
+        d = d.expand(B)
+    if d.shape[0] != B:
+        raise ValueError("dlogp accumulator has the wrong batch size")
+    return d.contiguous()
+
+
 #: kernel selection: ``precision`` "bf16x3" (default: fp32 operands split exactly into bf16 terms
 #: x = x1 + x2 (+ x3); three tensor-core products a1b1 + a2b1 + a1b2 with fp32 accumulation:
 #: ~2^-16 relative per product, measured 6e-7 max abs error over the 8-block golden stack) or
@@ -53,10 +100,36 @@ def pipeline_status(device):
     """Device int32 flag the tensor-core kernels raise if their internal barrier protocol
     times out (a bug, never an input property).  ``check_pipeline_status`` reads it back."""
     key = torch.device(device)
+    if key.index is None:
+        key = torch.device("cuda", torch.cuda.current_device())
     if key not in _status:
         _status[key] = torch.zeros(1, dtype=torch.int32, device=key)
-        _lib.load().bgx_set_status_buffer(C.c_void_p(_status[key].data_ptr()))   # one process per GPU
     return _status[key]
+
+
+_poll = {}
+
+
+def _poll_pipeline_status(device, every=64):
+    """Asynchronous check on the product path: every ``every`` tensor-core launches the flag is copied to
+    pinned host memory on the launch stream; the copy issued at the PREVIOUS poll is inspected (if it has
+    completed) — no host synchronisation, and a pipeline timeout surfaces as an exception at most two polls later."""
+    key = torch.device(device)
+    st = _poll.get(key)
+    if st is None:
+        st = _poll[key] = {"n": 0, "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "event": None}
+    st["n"] += 1
+    if st["n"] % every:
+        return
+    if st["event"] is not None:
+        if not st["event"].query():
+            return                      # previous copy still in flight: look again at the next poll
+        if int(st["host"][0]) != 0:
+            raise _lib.BgxError("tensor-core coupling kernel reported an internal pipeline timeout "
+                                "(results since the last check are invalid)")
+    st["host"].copy_(pipeline_status(key), non_blocking=True)
+    st["event"] = torch.cuda.Event()
+    st["event"].record(torch.cuda.current_stream(key))
 
 
 def check_pipeline_status(device):
@@ -98,14 +171,22 @@ class PackedNet:
     def __init__(self):
         self._key = None
         self._buf = None
+        self._event = None
+        self._pack_stream = None
+        self._seen = set()
         self.packed = _lib.bgx_packed_mlp()
 
+    @_device_guard
     def refresh(self, weights, biases, act_code, periodic=None, spline=None):
         """weights[i]: [out,in] fp32 CUDA (nn.Linear.weight), biases[i]: [out].
         periodic: None or (indices, left, right, raw_width); spline: None or (d_t, n_bins, circ mask)."""
         key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
         key = (key, act_code, repr(periodic), repr(spline), weights[0].device)
         if key == self._key:
+            cur = torch.cuda.current_stream(weights[0].device)
+            if cur != self._pack_stream and cur not in self._seen:
+                cur.wait_event(self._event)       # first use on another stream than the packing one
+                self._seen.add(cur)
             return self.packed
         lib = _lib.load()
         require_cuda_fp32(*weights, *biases)
@@ -159,6 +240,13 @@ class PackedNet:
         rc = lib.bgx_pack_mlp(C.byref(src), lay_p, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(out),
                               _stream())
         _lib.check(rc, "bgx_pack_mlp")
+        if self._buf is not None:
+            for st in self._seen:                 # launches on other streams may still read the old layout
+                self._buf.record_stream(st)
+        self._pack_stream = torch.cuda.current_stream(ws[0].device)
+        self._event = torch.cuda.Event()
+        self._event.record(self._pack_stream)
+        self._seen = set()
         self._buf, self.packed, self._key = buf, out, key
         return out
 
@@ -215,18 +303,15 @@ def _fill_io(cond, tr, dlogp_in):
         io.tr_in[0].ptr, io.tr_in[0].width, io.tr_in[0].stride = tr2[0].data_ptr(), col, col
         io.tr_out[0].ptr, io.tr_out[0].width, io.tr_out[0].stride = out.data_ptr(), col, col
     keep = [cond2, tr2]
-    if dlogp_in is not None:
-        require_cuda_fp32(dlogp_in)
-        d = dlogp_in.reshape(-1)
-        if d.shape[0] != B:
-            raise ValueError("dlogp accumulator has the wrong batch size")
-        d = d.contiguous()
+    d = _dlogp_arg(dlogp_in, B, tr2[0].device)
+    if d is not None:
         keep.append(d)
         io.dlogp_in = d.data_ptr()
     io.dlogp_out = dlogp.data_ptr()
     return io, outs, dlogp.reshape(*batch_shape, 1), keep
 
 
+@_device_guard
 def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_volume=False,
                     is_circular=False, dlogp_in=None, flags=0):
     """cond / tr: lists of tensors (concatenated along the last dim by the kernel);
@@ -235,15 +320,18 @@ def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_v
     io, outs, dlogp, keep = _fill_io(cond, tr, dlogp_in)
     if io.batch == 0:
         return outs, dlogp
-    pipeline_status(tr[0].device)
+    # (the affine entry point has no per-call status argument: point the library at THIS device's flag)
+    lib.bgx_set_status_buffer(C.c_void_p(pipeline_status(tr[0].device).data_ptr()))
     f = flags | _mode_flags() | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
         | (_lib.FLAG_CIRCULAR if is_circular else 0)
     rc = lib.bgx_affine_coupling(C.byref(io), C.byref(shift) if shift is not None else None,
                                  C.byref(scale) if scale is not None else None, float(log_alpha), f, _stream())
     _lib.check(rc, "bgx_affine_coupling")
+    _poll_pipeline_status(tr[0].device)
     return outs, dlogp
 
 
+@_device_guard
 def spline_coupling(cond, tr, net, n_bins, inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0,
                     min_bin_width=1e-3, min_bin_height=1e-3, min_derivative=1e-3, identity_init=True,
                     oob_counter=None, dlogp_in=None, flags=0):
@@ -261,9 +349,11 @@ def spline_coupling(cond, tr, net, n_bins, inverse=False, left=0.0, right=1.0, b
     f = flags | _mode_flags() | (_lib.FLAG_INVERSE if inverse else 0)
     rc = lib.bgx_spline_coupling(C.byref(io), C.byref(net), C.byref(cfg), f, _stream())
     _lib.check(rc, "bgx_spline_coupling")
+    _poll_pipeline_status(tr[0].device)
     return outs, dlogp
 
 
+@_device_guard
 def spline_backward(params, y, g_out, g_dlogp, end_slope_col, n_bins, inverse=False, left=0.0, right=1.0,
                     bottom=0.0, top=1.0, min_bin_width=1e-3, min_bin_height=1e-3, min_derivative=1e-3,
                     identity_init=True):
@@ -360,6 +450,7 @@ class ZPlan:
         return self._dev[key][0]
 
 
+@_device_guard
 def ic_to_xyz(plan, bonds, angles, torsions, x0, R, dlogp_in=None):
     lib = _lib.load()
     require_cuda_fp32(bonds, angles, torsions, x0, R)
@@ -374,7 +465,7 @@ def ic_to_xyz(plan, bonds, angles, torsions, x0, R, dlogp_in=None):
         raise ValueError("x0 must be [B,1,3] (or [1,3]) and R [B,3]")
     xyz = torch.empty(B, 3 * n, dtype=torch.float32, device=bonds.device)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
-    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    din = _dlogp_arg(dlogp_in, B, bonds.device)
     if B == 0:
         return xyz, dlogp
     rc = lib.bgx_ic_to_xyz(C.byref(plan.device_plan(bonds.device)), B, bonds.data_ptr(), angles.data_ptr(),
@@ -385,6 +476,7 @@ def ic_to_xyz(plan, bonds, angles, torsions, x0, R, dlogp_in=None):
     return xyz, dlogp
 
 
+@_device_guard
 def ic_from_xyz(plan, xyz, dlogp_in=None):
     lib = _lib.load()
     require_cuda_fp32(xyz)
@@ -400,7 +492,7 @@ def ic_from_xyz(plan, xyz, dlogp_in=None):
     x0 = torch.empty(B, 1, 3, dtype=torch.float32, device=dev)
     R = torch.empty(B, 3, dtype=torch.float32, device=dev)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
-    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    din = _dlogp_arg(dlogp_in, B, dev)
     if B == 0:
         return bonds, angles, torsions, x0, R, dlogp
     rc = lib.bgx_ic_from_xyz(C.byref(plan.device_plan(dev)), B, x.data_ptr(), bonds.data_ptr(), angles.data_ptr(),
@@ -424,15 +516,18 @@ def _clamp_args(eps):
 class CdfTable:
     """Device table of ``bgx_cdf_col`` entries, one per tensor column.
 
-    ``columns``: sequence of ``(kind, a, b, lower, upper)`` with kind in
+    ``columns``: sequence of ``(kind, a, b, lower, upper[, cdf_lower, cdf_upper])`` with kind in
     ``_lib.DIST_NONE / DIST_NORMAL / DIST_TRUNCNORMAL / DIST_UNIFORM`` (see ``bgx_cdf_col_init``)."""
 
     def __init__(self, columns):
         lib = _lib.load()
         self.n = len(columns)
         arr = (_lib.bgx_cdf_col * max(self.n, 1))()
-        for i, (kind, a, b, lower, upper) in enumerate(columns):
+        for i, col in enumerate(columns):
+            kind, a, b, lower, upper = col[:5]
             rc = lib.bgx_cdf_col_init(int(kind), float(a), float(b), float(lower), float(upper), C.byref(arr[i]))
+            if rc == 0 and len(col) == 7:      # frozen Phi(alpha), Phi(beta) of a truncated normal
+                rc = lib.bgx_cdf_col_set_truncation(C.byref(arr[i]), float(col[5]), float(col[6]))
             if rc != 0:
                 raise ValueError(f"invalid marginal for column {i}: kind={kind}, a={a}, b={b}, "
                                  f"lower={lower}, upper={upper}")
@@ -446,6 +541,7 @@ class CdfTable:
         return self._dev[key]
 
 
+@_device_guard
 def cdf_map(tensors, table, inverse=False, eps=1e-7, dlogp_in=None):
     """Map a list of ``[B, w_i]`` tensors through their per-column CDFs (``inverse``: icdfs) in one
     launch.  Returns (list of mapped tensors, dlogp ``[..., 1]``)."""
@@ -468,12 +564,7 @@ def cdf_map(tensors, table, inverse=False, eps=1e-7, dlogp_in=None):
         w = t.shape[1]
         segs_in[i].ptr, segs_in[i].width, segs_in[i].stride = t.data_ptr(), w, t.stride(0) if B > 1 else w
         segs_out[i].ptr, segs_out[i].width, segs_out[i].stride = o.data_ptr(), w, w
-    din = None
-    if dlogp_in is not None:
-        require_cuda_fp32(dlogp_in)
-        din = dlogp_in.reshape(-1).contiguous()
-        if din.shape[0] != B:
-            raise ValueError("dlogp accumulator has the wrong batch size")
+    din = _dlogp_arg(dlogp_in, B, rows[0].device)
     if B > 0:
         lo, hi, ldmin = _clamp_args(eps)
         cols = table.device(rows[0].device)
@@ -485,6 +576,7 @@ def cdf_map(tensors, table, inverse=False, eps=1e-7, dlogp_in=None):
     return outs, dlogp.reshape(*batch_shape, 1)
 
 
+@_device_guard
 def ic_to_xyz_mapped(plan, table, eps, bonds, angles, torsions, x0, R, dlogp_in=None):
     """icdf maps of (bonds | angles | torsions) + IC -> Cartesian in one kernel."""
     lib = _lib.load()
@@ -502,7 +594,7 @@ def ic_to_xyz_mapped(plan, table, eps, bonds, angles, torsions, x0, R, dlogp_in=
         raise ValueError("x0 must be [B,1,3] (or [1,3]) and R [B,3]")
     xyz = torch.empty(B, 3 * n, dtype=torch.float32, device=bonds.device)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
-    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    din = _dlogp_arg(dlogp_in, B, bonds.device)
     if B == 0:
         return xyz, dlogp
     lo, hi, ldmin = _clamp_args(eps)
@@ -516,6 +608,7 @@ def ic_to_xyz_mapped(plan, table, eps, bonds, angles, torsions, x0, R, dlogp_in=
     return xyz, dlogp
 
 
+@_device_guard
 def ic_from_xyz_mapped(plan, table, eps, xyz, dlogp_in=None):
     """Cartesian -> IC + cdf maps of every IC column in one kernel."""
     lib = _lib.load()
@@ -534,7 +627,7 @@ def ic_from_xyz_mapped(plan, table, eps, xyz, dlogp_in=None):
     x0 = torch.empty(B, 1, 3, dtype=torch.float32, device=dev)
     R = torch.empty(B, 3, dtype=torch.float32, device=dev)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
-    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    din = _dlogp_arg(dlogp_in, B, dev)
     if B == 0:
         return bonds, angles, torsions, x0, R, dlogp
     lo, hi, ldmin = _clamp_args(eps)
@@ -617,6 +710,7 @@ class RelPlan:
         return self._dev[key][0]
 
 
+@_device_guard
 def relic_to_xyz(plan, bonds, angles, torsions, fixed, dlogp_in=None):
     lib = _lib.load()
     require_cuda_fp32(bonds, angles, torsions, fixed)
@@ -630,7 +724,7 @@ def relic_to_xyz(plan, bonds, angles, torsions, fixed, dlogp_in=None):
     bonds, angles, torsions = bonds.contiguous(), angles.contiguous(), torsions.contiguous()
     xyz = torch.empty(B, 3 * plan.n_atoms, dtype=torch.float32, device=bonds.device)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=bonds.device)
-    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    din = _dlogp_arg(dlogp_in, B, bonds.device)
     if B == 0:
         return xyz, dlogp
     rc = lib.bgx_relic_to_xyz(C.byref(plan.device_plan(bonds.device)), B, bonds.data_ptr(), angles.data_ptr(),
@@ -640,6 +734,7 @@ def relic_to_xyz(plan, bonds, angles, torsions, fixed, dlogp_in=None):
     return xyz, dlogp
 
 
+@_device_guard
 def relic_from_xyz(plan, xyz, dlogp_in=None):
     lib = _lib.load()
     require_cuda_fp32(xyz)
@@ -653,7 +748,7 @@ def relic_from_xyz(plan, xyz, dlogp_in=None):
     torsions = torch.empty(B, n_rel, dtype=torch.float32, device=dev)
     fixed = torch.empty(B, plan.fixed_width, dtype=torch.float32, device=dev)
     dlogp = torch.empty(B, 1, dtype=torch.float32, device=dev)
-    din = dlogp_in.reshape(-1).contiguous() if dlogp_in is not None else None
+    din = _dlogp_arg(dlogp_in, B, dev)
     if B == 0:
         return bonds, angles, torsions, fixed, dlogp
     rc = lib.bgx_relic_from_xyz(C.byref(plan.device_plan(dev)), B, x.data_ptr(), bonds.data_ptr(), angles.data_ptr(),
@@ -673,6 +768,7 @@ def _seg(t, B):
     return s
 
 
+@_device_guard
 def split_cols(x, sizes):
     """``x [.., W]`` -> dense tensors of the given last-dim sizes, one launch."""
     lib = _lib.load()
@@ -690,6 +786,7 @@ def split_cols(x, sizes):
     return [p.reshape(*lead, p.shape[1]) if len(lead) != 1 else p for p in parts]
 
 
+@_device_guard
 def merge_cols(parts):
     """Concatenate tensors along the last dim, one launch."""
     lib = _lib.load()

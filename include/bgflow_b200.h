@@ -226,6 +226,11 @@ typedef struct bgx_cdf_col {
  * Returns BGX_ERR_INVALID for scale <= 0, upper <= lower or an unknown kind. */
 int bgx_cdf_col_init(int32_t kind, double a, double b, double lower, double upper, bgx_cdf_col* out);
 
+/* TruncatedNormalDistribution freezes Phi(alpha), Phi(beta) in registered buffers at construction
+ * (normal.py:148-151) and evaluates cdf / icdf / log_prob with THOSE, even after mu / sigma were trained or
+ * loaded from a checkpoint: override the constants bgx_cdf_col_init derived from mu / sigma. */
+int bgx_cdf_col_set_truncation(bgx_cdf_col* col, double cdf_lower, double cdf_upper);
+
 /* Map `n_seg` tensors of one flow state in ONE launch.  Segment i has in[i].width columns whose
  * bgx_cdf_col entries follow each other in `cols` (device array, sum of widths entries);
  * out[i] has the same width (out[i].ptr is written; may alias in[i].ptr).

@@ -60,6 +60,45 @@ def test_input_and_parameter_gradients(kind, inverse):
         np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=3e-3 * s, rtol=3e-3)
 
 
+@pytest.mark.parametrize("variant", ["shift_only", "scale_only", "preserve_volume", "shift_only_circular"])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_affine_variants_backward(variant, inverse):
+    """affine.py:41-47: NICE (no scale net: dlogp is a constant zero without a graph), scale-only,
+    volume-preserving and circular shift-only transformers must all train (the recompute
+    backward used to hand a graph-less dlogp to autograd.grad and raise)."""
+    gen = torch.Generator().manual_seed(3)
+    dim, split = 8, 4
+    blocks, blocks64 = [], []
+    for dt in (torch.float32, torch.float64):
+        g2 = torch.Generator().manual_seed(11)
+        out = blocks if dt == torch.float32 else blocks64
+        for _ in range(2):
+            b = {"kind": "affine", "log_alpha": -0.5,
+                 "shift": of.make_mlp([4, 24, 4], "relu", g2, dt) if variant != "scale_only" else None,
+                 "scale": of.make_mlp([4, 24, 4], "tanh", g2, dt) if variant in ("scale_only", "preserve_volume") else None,
+                 "preserve_volume": variant == "preserve_volume", "is_circular": variant == "shift_only_circular"}
+            out.append(b)
+    flow = stack_from(blocks, split, DEV)
+    z = torch.rand(37, dim, generator=gen)
+    wx, wd = torch.randn(37, dim, generator=gen), torch.randn(37, 1, generator=gen)
+    x_ref, d_ref, gz_ref, gp_ref = _oracle_grads("affine", blocks64, split, z, wx, wd, inverse)
+    zc = z.to(DEV).requires_grad_(True)
+    x, d = flow(zc, inverse=inverse)
+    np.testing.assert_allclose(x.detach().cpu().double().numpy(), x_ref.numpy(), atol=2e-5, rtol=1e-4)
+    ((x * wx.to(DEV)).sum() + (d * wd.to(DEV)).sum()).backward()
+    s = max(gz_ref.abs().max().item(), 1e-6)
+    np.testing.assert_allclose(zc.grad.cpu().double().numpy(), gz_ref.numpy(), atol=2e-3 * s, rtol=2e-3)
+    ours = []
+    for m in flow.modules():
+        if isinstance(m, bg.DenseNet):
+            lin = [l for l in m._layers if isinstance(l, torch.nn.Linear)]
+            ours += [l.weight.grad for l in lin] + [l.bias.grad for l in lin]
+    assert len(ours) == len(gp_ref)
+    for a, b in zip(ours, gp_ref):
+        sc = max(b.abs().max().item(), 1e-6)
+        np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=3e-3 * sc, rtol=3e-3)
+
+
 def test_kl_training_step_reduces_loss():
     """A few reverse-KL steps (bg.py:13-17) on a Gaussian target through kernel-forward blocks."""
     from bgflow_b200.distributed import kl_train_step

@@ -89,9 +89,10 @@ def test_reference_golden_on_the_pair_kernel(mode):
     np.testing.assert_allclose(dlogpi.cpu().double().numpy(), g["dlogpi_f64"], atol=1e-3, rtol=1e-4)
 
 
-def test_pair_kernel_matches_two_cta_kernel_bitwise():
+def test_pair_kernel_matches_two_cta_kernel():
     """Same operand splits, same MMA order, same epilogue arithmetic: the pair kernel (both modes) and the
-    two-CTAs-per-SM kernel must agree bit for bit, over many tiles per CTA (B = 2^17 + 4: 1025 tiles)."""
+    two-CTAs-per-SM kernel must produce the same transformed values bit for bit, over many tiles per CTA
+    (B = 2^17 + 4: 1025 tiles); the log-det is summed over four dim shares instead of two (rounding only)."""
     blocks, split = of.make_stack("spline", 66, 2, seed=0)
     flow = stack_from(blocks, split, DEV)
     g = torch.Generator().manual_seed(9)
@@ -102,8 +103,11 @@ def test_pair_kernel_matches_two_cta_kernel_bitwise():
             engine.config["spline_kernel"] = mode
             out[mode] = flow(z) + flow(z, inverse=True)
     for mode in ("auto", "pair_wide"):
-        for a, b in zip(out["tc2"], out[mode]):
-            assert torch.equal(a, b), (mode, float((a - b).abs().max()))
+        for k, (a, b) in enumerate(zip(out["tc2"], out[mode])):
+            if k % 2 == 0:
+                assert torch.equal(a, b), (mode, k, float((a - b).abs().max()))
+            else:
+                torch.testing.assert_close(a, b, atol=2e-5, rtol=0)
 
 
 def test_out_of_domain_inputs_are_clamped_and_counted():
