@@ -27,11 +27,30 @@ sys.path.insert(0, ROOT)
 
 DRYRUN = os.environ.get("BGX_BENCH_DRYRUN") == "1"
 
+def flops_bytes(kind, dim, hidden):
+    """Algorithmic GEMM FLOPs and HBM bytes per sample per coupling block: FLOPs = 2 * sum(in * out)
+    over the conditioner layers (x2 nets for affine), bytes = 4 * (D_c + 2 D_t + 2)."""
+    d_c, d_t = dim // 2, dim - dim // 2
+    dims = [d_c, *hidden, d_t * 25 if kind == "spline" else d_t]
+    fl = 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * (1 if kind == "spline" else 2)
+    return fl, 4 * (d_c + 2 * d_t + 2)
+
+
+def _wl(kind, dim, n_blocks, hidden):
+    return (kind, dim, n_blocks, hidden, *flops_bytes(kind, dim, hidden))
+
+
 WORKLOADS = {
     # name: (kind, dim, n_blocks, hidden, flops/sample/block, algorithmic bytes/sample/block)
-    "ala2_spline_d66_8blk": ("spline", 66, 8, (128, 128), 252416, 404),
-    "ala2_affine_d66_8blk": ("affine", 66, 8, (128, 128, 128), 164864, 404),
+    "ala2_spline_d66_8blk": _wl("spline", 66, 8, (128, 128)),
+    "ala2_affine_d66_8blk": _wl("affine", 66, 8, (128, 128, 128)),
+    # BASELINE config 5 roofline sweep
+    "spline_d384_8blk": _wl("spline", 384, 8, (128, 128)),
+    "spline_d3072_8blk": _wl("spline", 3072, 8, (128, 128)),
+    "affine_d384_8blk": _wl("affine", 384, 8, (128, 128, 128)),
+    "affine_d3072_8blk": _wl("affine", 3072, 8, (128, 128, 128)),
 }
+assert WORKLOADS["ala2_spline_d66_8blk"][4:] == (252416, 404) and WORKLOADS["ala2_affine_d66_8blk"][4:] == (164864, 404)
 
 
 def peaks():
@@ -200,6 +219,49 @@ def time_gpu_torch_port(blocks, kind, dim, rows, dev):
         e1.record()
         torch.cuda.synchronize()
     return rows * 3 / (e0.elapsed_time(e1) * 1e-3)
+
+
+def bench_sweep(args, dev, run_timed, world):
+    """BASELINE config 5: fwd + inv (+ log|det J|) roofline sweep over dim in {66, 384, 3072}, spline and affine
+    8-block stacks at batch 2^20 per GPU, every block on a tcgen05 kernel (asserted through bgx_kernel_count).
+    One entry per (kind, dim, direction): samples/s, ms per block launch, algorithmic TFLOP/s and GB/s with their
+    fractions of the measured peaks."""
+    import gc
+    import bgflow_b200 as bg
+    from bgflow_b200 import _lib
+    pk = peaks()
+    out = []
+    for name in ("ala2_spline_d66_8blk", "spline_d384_8blk", "spline_d3072_8blk", "ala2_affine_d66_8blk",
+                 "affine_d384_8blk", "affine_d3072_8blk"):
+        kind, dim, n_blocks, hidden, flops_sb, bytes_sb = WORKLOADS[name]
+        B = args.sweep_batch if dim <= 1024 else min(args.sweep_batch, args.sweep_batch_wide)
+        flow = build_flow(kind, dim, n_blocks, hidden, dev)
+        gen = torch.Generator(device=dev).manual_seed(1)
+        z = (torch.rand(B, dim, generator=gen, device=dev) if kind == "spline"
+             else torch.randn(B, dim, generator=gen, device=dev))
+        with torch.no_grad():
+            for direction in ("forward", "inverse"):
+                inv = direction == "inverse"
+                fn = (lambda: flow(z, inverse=True)) if inv else (lambda: flow(z))
+                before = _lib.kernel_counts()
+                for _ in range(2):
+                    fn()
+                steps = 3 if dim > 1024 else 5
+                ms = run_timed(fn, steps) / steps
+                used = {k: v - before[k] for k, v in _lib.kernel_counts().items() if v != before[k]}
+                t_blk = ms * 1e-3 / n_blocks          # whole pass / blocks (split + merge copies included)
+                out.append({"workload": name, "kind": kind, "dim": dim, "direction": direction, "batch_per_gpu": B,
+                            "samples_per_s": B * world / (ms * 1e-3), "ms_per_pass": ms,
+                            "tflops_algorithmic": flops_sb * B / t_blk / 1e12,
+                            "tensor_frac": flops_sb * B / t_blk / 1e12 / pk["tf_sustained"],
+                            "hbm_gbs_algorithmic": bytes_sb * B / t_blk / 1e9,
+                            "hbm_frac": bytes_sb * B / t_blk / 1e9 / pk["hbm_gbs"],
+                            "kernels": sorted(used)})
+        del flow, z
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
 
 
 def bench_ic(args, dev):
@@ -399,7 +461,12 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample-rows", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-full-pass", action="store_true",
+                    help="reference arm: skip the single pass over the full per-GPU batch (about 20 s)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep-batch", type=int, default=1 << 20)
+    ap.add_argument("--sweep-batch-wide", type=int, default=1 << 20, help="rows per GPU for the D = 3072 sweep points")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--extras", action="store_true",
                     help="also time the IC kernels, the restated single-GPU PyTorch path and a KL training step "
                          "(adds to the JSON line)")
@@ -430,11 +497,19 @@ def main():
         total = sum(times)
         value = rows * len(times) / total
         sample = f"{rows} rows of the {args.workload} workload per step (chunk of the 2^20 batch)"
+        # one pass over the FULL per-GPU batch of the b200 arm (2^20 rows as 16 chunks of 65536, what SURVEY 8d
+        # prescribes when one call does not fit), so the two arms can be compared on the same configuration
+        full = None
+        if not args.no_cpu_full_pass:
+            nchunk = max(1, args.batch_per_gpu // rows)
+            t_full = sum(time_cpu_port(blocks, kind, dim, rows, nchunk, threads))
+            full = {"rows": nchunk * rows, "chunks": nchunk, "seconds": t_full, "value": nchunk * rows / t_full,
+                    "unit": "samples/s"}
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config, cpu_rows_per_step=rows),
+            "data": "synthetic", "config": dict(config, cpu_rows_per_step=rows), "full_batch_pass": full,
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "host_cpus": os.cpu_count(),
                              "kind": "port", "sample": sample,
                              "note": "oracle/flows.py = op-for-op restatement of the reference's CPU PyTorch path "
@@ -489,6 +564,9 @@ def main():
                         f"tcgen05 kind::f16, operands split into bf16 terms ({engine.config['precision']})")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    from bgflow_b200.host import HostPipeline, bind_to_gpu_numa, copy_ceiling
+    numa = bind_to_gpu_numa(local_rank)      # before the pinned buffers exist: first touch lands on the GPU's node
+    config["numa"] = numa
     flow = build_flow(kind, dim, n_blocks, hidden, dev)
     g = torch.Generator(device="cpu").manual_seed(1 + rank)
     z_host = (torch.rand(B, dim, generator=g) if kind == "spline" else torch.randn(B, dim, generator=g)).pin_memory()
@@ -543,14 +621,36 @@ def main():
         # ---- end to end: pinned host input -> device -> flow -> host result, every step
         e2e = None
         if not args.no_e2e:
-            from bgflow_b200.host import HostPipeline
-            pipe = HostPipeline(flow, dim_in=dim, dim_out=dim, max_rows=B, device=dev)
+            prior = (bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)) if kind == "spline"
+                     else bg.NormalDistribution(dim)).to(dev)
+            pipe = HostPipeline(flow, dim_in=dim, dim_out=dim, max_rows=B, device=dev, prior=prior)
             for _ in range(args.warmup):
                 pipe.run(z_host)
             ms_e2e = run_timed(lambda: pipe.run(z_host), args.steps)
+            h2d, d2h = B * dim * 4, B * dim * 4 + B * 4            # per GPU per step
             e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
-                   "h2d_bytes_per_step": world * B * dim * 4, "d2h_bytes_per_step": world * (B * dim * 4 + B * 4),
+                   "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
                    "ms_per_step": ms_e2e / args.steps, "api": "bgflow_b200.host.HostPipeline.run (pinned host in/out)"}
+            # what the host <-> device link gives THIS rank while every rank copies both ways at once
+            barrier()
+            cc = copy_ceiling(dev)
+            barrier()
+            t_copy = max(h2d / (cc["h2d_gbs_concurrent"] * 1e9), d2h / (cc["d2h_gbs_concurrent"] * 1e9))
+            t_copy = max_over_ranks(t_copy)
+            e2e["copy_ceiling"] = dict({k: round(v, 2) for k, v in cc.items()},
+                                       note="pinned cudaMemcpyAsync, H2D and D2H concurrently, all ranks at once; GB/s of this rank",
+                                       min_ms_per_step_from_copies=1e3 * t_copy,
+                                       e2e_frac_of_copy_ceiling=1e3 * t_copy / (ms_e2e / args.steps))
+            # the generator's sampling call: prior drawn on the device, nothing crosses PCIe host -> device
+            for _ in range(args.warmup):
+                pipe.sample(B)
+            ms_s = run_timed(lambda: pipe.sample(B), args.steps)
+            e2e["sample_call"] = {"value": B * world * args.steps / (ms_s * 1e-3), "unit": "samples/s",
+                                  "h2d_bytes_per_step": 0, "d2h_bytes_per_step": world * d2h,
+                                  "ms_per_step": ms_s / args.steps,
+                                  "api": "HostPipeline.sample = BoltzmannGenerator.sample(n, with_dlogp=True): prior on the "
+                                         "device (bg.py:115, normal.py:75-92), pinned host out",
+                                  "frac_of_d2h_ceiling": (d2h / (cc["d2h_gbs"] * 1e9)) / (ms_s * 1e-3 / args.steps)}
 
     pk = peaks()
     traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
@@ -586,6 +686,19 @@ def main():
         out["cpu_baseline"] = {"value": rows / best, "unit": "samples/s", "cores": threads,
                                "host_cpus": os.cpu_count(), "kind": "port",
                                "sample": f"{rows} rows of the same workload, best of 2 after 1 warm-up"}
+    if not args.no_sweep:
+        sw = bench_sweep(args, dev, run_timed, world)
+        if rank == 0:
+            out["sweep"] = sw
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.extras:
+        # cheap secondary lines every driver run carries (65536 rows): the restated single-GPU PyTorch path (the
+        # north star's ">= 10x" denominator), the IC kernels and BASELINE config 4 end to end
+        blocks = oracle_blocks_from(flow)
+        out["secondary"] = {
+            "gpu_pytorch_port": {"value": time_gpu_torch_port(blocks, kind, dim, 65536, dev), "unit": "samples/s",
+                                 "sample": "65536 rows; oracle/flows.py op sequence on CUDA tensors"},
+            "ic_ala2": bench_ic(args, dev), "config4_pipeline": bench_config4(args, dev)}
+        out["secondary"]["speedup_vs_gpu_pytorch_port"] = value / out["secondary"]["gpu_pytorch_port"]["value"]
     if rank == 0 and world == 1 and args.extras:
         blocks = oracle_blocks_from(flow)
         out["extras"] = {

@@ -21,7 +21,7 @@ ERRORS = {-1: "BGX_ERR_INVALID (bad argument / inconsistent shapes)",
 
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3
 FLAG_INVERSE, FLAG_PRESERVE_VOLUME, FLAG_CIRCULAR, FLAG_BF16X6, FLAG_FORCE_SIMT = 1, 2, 4, 8, 16
-FLAG_NO_PAIR, FLAG_FORCE_WIDE = 32, 64
+FLAG_NO_PAIR, FLAG_FORCE_WIDE, FLAG_PREFER_PAIR = 32, 64, 128
 KERNEL_IDS = {"spline_pair": 0, "spline_pair_wide": 1, "spline_tc2": 2, "spline_tc": 3, "spline_simt": 4,
               "affine_tc2": 5, "affine_tc": 6, "affine_simt": 7, "affine_pair": 8, "affine_pair_wide": 9}
 

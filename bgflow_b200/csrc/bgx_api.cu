@@ -11,6 +11,8 @@ bool spline_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bg
 int spline_coupling_tc2(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int*, cudaStream_t);
 int spline_pair_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int);
 int spline_coupling_pair(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_spline_cfg*, int, int, int*, cudaStream_t);
+bool affine_pair_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, int);
+int affine_coupling_pair(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, float, int, int*, cudaStream_t);
 void tc_set_trace(unsigned long long*, int);
 bool affine_tc_eligible(const bgx_packed_mlp*, const bgx_packed_mlp*, int);
 bool affine_tc2_eligible(const bgx_coupling_io*, const bgx_packed_mlp*, const bgx_packed_mlp*, int);
@@ -35,9 +37,14 @@ extern "C" int bgx_set_status_buffer(int32_t* device_int) {
 extern "C" int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
                                    const bgx_packed_mlp* scale, float log_alpha, int flags, void* stream) {
   if (!io) return BGX_ERR_INVALID;
-  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc2_eligible(io, shift, scale, flags)) {
+  if (!(flags & (BGX_FLAG_FORCE_SIMT | BGX_FLAG_PREFER_PAIR)) && bgx::affine_tc2_eligible(io, shift, scale, flags)) {
     ++g_kernel_count[BGX_KERNEL_AFFINE_TC2];
     return bgx::affine_coupling_tc2(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
+  }
+  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_pair_eligible(io, shift, scale, flags) &&
+      (!bgx::affine_tc_eligible(shift, scale, flags) || (flags & BGX_FLAG_PREFER_PAIR))) {
+    ++g_kernel_count[BGX_KERNEL_AFFINE_PAIR_WIDE];
+    return bgx::affine_coupling_pair(io, shift, scale, log_alpha, flags, g_status, (cudaStream_t)stream);
   }
   if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::affine_tc_eligible(shift, scale, flags)) {
     ++g_kernel_count[BGX_KERNEL_AFFINE_TC];
@@ -50,18 +57,17 @@ extern "C" int bgx_affine_coupling(const bgx_coupling_io* io, const bgx_packed_m
 extern "C" int bgx_spline_coupling(const bgx_coupling_io* io, const bgx_packed_mlp* params_net,
                                    const bgx_spline_cfg* cfg, int flags, void* stream) {
   if (!io || !params_net || !cfg) return BGX_ERR_INVALID;
-  if (!(flags & (BGX_FLAG_FORCE_SIMT | BGX_FLAG_NO_PAIR))) {
-    const int mode = bgx::spline_pair_eligible(io, params_net, cfg, flags);
-    if (mode) {
-      ++g_kernel_count[mode == 2 ? BGX_KERNEL_SPLINE_PAIR_WIDE : BGX_KERNEL_SPLINE_PAIR];
-      return bgx::spline_coupling_pair(io, params_net, cfg, flags, mode, cfg->status ? cfg->status : g_status,
-                                       (cudaStream_t)stream);
-    }
+  int* status = cfg->status ? cfg->status : g_status;
+  const bool tc_ok = !(flags & BGX_FLAG_FORCE_SIMT);
+  const int pair_mode = (tc_ok && !(flags & BGX_FLAG_NO_PAIR)) ? bgx::spline_pair_eligible(io, params_net, cfg, flags) : 0;
+  const bool tc2_ok = tc_ok && !(flags & BGX_FLAG_FORCE_WIDE) && bgx::spline_tc2_eligible(io, params_net, cfg, flags);
+  if (pair_mode && (!tc2_ok || (flags & BGX_FLAG_PREFER_PAIR))) {
+    ++g_kernel_count[pair_mode == 2 ? BGX_KERNEL_SPLINE_PAIR_WIDE : BGX_KERNEL_SPLINE_PAIR];
+    return bgx::spline_coupling_pair(io, params_net, cfg, flags, pair_mode, status, (cudaStream_t)stream);
   }
-  if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc2_eligible(io, params_net, cfg, flags)) {
+  if (tc2_ok) {
     ++g_kernel_count[BGX_KERNEL_SPLINE_TC2];
-    return bgx::spline_coupling_tc2(io, params_net, cfg, flags, cfg->status ? cfg->status : g_status,
-                                    (cudaStream_t)stream);
+    return bgx::spline_coupling_tc2(io, params_net, cfg, flags, status, (cudaStream_t)stream);
   }
   if (!(flags & BGX_FLAG_FORCE_SIMT) && bgx::spline_tc_eligible(params_net, cfg, 0)) {
     ++g_kernel_count[BGX_KERNEL_SPLINE_TC];

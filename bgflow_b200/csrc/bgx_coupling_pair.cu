@@ -34,19 +34,10 @@
 #include "bgx_tc.cuh"
 #include "bgx_tc_epi.cuh"
 #include "bgx_spline_reg.cuh"
+#include "bgx_pair.cuh"
 
 namespace bgx {
 using namespace tc;
-
-constexpr int P_EPI_WARPS = 16;
-constexpr int P_THREADS = (P_EPI_WARPS + 4) * 32;     // 640
-constexpr int P_TM = 128;
-constexpr int P_STAGES = 2;
-constexpr uint32_t P_TILE_BYTES = 16384;              // one [128 x 64] bf16 k-tile of one term
-constexpr uint32_t P_KT_BYTES = 2 * P_TILE_BYTES;     // both terms
-constexpr uint32_t P_STAGE_BYTES = 2 * P_KT_BYTES;    // a unit has at most two k-tiles
-constexpr int P_SLOT = 256, P_ACC = 0, P_A = 128, P_A_STRIDE = 64;
-constexpr int P_NB = 8, P_PS = 3 * P_NB + 1, P_DPP = 5, P_BPAD = 28;
 
 struct PArgs {
   long long B;
@@ -81,51 +72,6 @@ struct alignas(16) PSmem {
   uint32_t tmem_base, pad[3];
   float dl_part[2][4][P_TM];       // [slot][dim share][row]
 };
-
-// Layer-0 operand of one slot: inputs 128 g + [32 j, 32 j + 32) of this thread's row -> two exact bf16 terms in
-// tensor memory.  Out of line on purpose: three call sites, and the epilogue's hot loop has to stay inside
-// the instruction cache (the first version of this kernel inlined it everywhere and lost 27 % of its warp
-// samples to instruction fetch).  WrapPeriodic (periodic.py:30-37) through sinpi / cospi: no slow path.
-__device__ __noinline__ void pair_stage_x(const PArgs& a, const float* crow, bool live, int g, int j, uint32_t a_col) {
-  const int K0 = a.net.K[0];
-  const int kg = 128 * g;                 // first input of the group
-  const int kend = min(K0, kg + 128);     // one past the last real input of the group
-  const float inv_pi_scale = a.net.pscale * 0.3183098861837907f;
-  // this warp's 32 inputs as two 16-input halves (8 packed columns each); a half is written iff the MMAs of
-  // the group read it (their k-steps cover inputs [kg, round_up(kend, 16)))
-  for (int h = 0; h < 2; ++h) {
-    const int b0 = kg + j * 32 + h * 16;
-    if (b0 >= kend) break;
-    float xv[16];
-    if (a.plain_cond) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) xv[i] = (live && b0 + i < kend) ? crow[b0 + i] : 0.f;
-    } else {
-#pragma unroll 1
-      for (int i = 0; i < 16; ++i) {
-        float v = 0.f;
-        if (live && b0 + i < kend) {
-          const int code = a.net.in_map[b0 + i];
-          v = crow[code & 0xffffff];
-          const int kind = code >> 24;
-          if (kind) {
-            const float t = (v - a.net.pleft) * inv_pi_scale;
-            v = kind == 1 ? cospif(t) : sinpif(t);
-          }
-        }
-        xv[i] = v;
-      }
-    }
-    uint32_t t1[8], t2[8], t3[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(xv[2 * i], xv[2 * i + 1], 2, t1[i], t2[i], t3[i]);
-    const uint32_t col = a_col + (uint32_t)((b0 - kg) / 2);
-    tmem_st8(col, t1);
-    tmem_st8(col + P_A_STRIDE, t2);
-  }
-  tmem_st_wait();
-  tc_fence_before();
-}
 
 template <bool INVERSE, int ACT, bool WIDE>
 __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(const __grid_constant__ PArgs a) {
@@ -349,7 +295,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
         ph_c[s] ^= 1;
       }
       const float* crow = WIDE ? a.cond + row * (long long)a.K0raw : cbuf + (s * P_TM + r_in_tile) * a.K0raw;
-      pair_stage_x(a, crow, !WIDE || row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
+      pair_stage_x(a.net, a.plain_cond, crow, !WIDE || row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&S->a_ready[s]);

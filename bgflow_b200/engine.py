@@ -89,9 +89,13 @@ config = {"precision": "bf16x3", "force_simt": False,
           # the batch is large, so that the two-CTAs-per-SM kernels (dense single tensors only) apply;
           # the copies cost ~5 % of a block, the one-CTA kernel ~25 %
           "gather_segments": True, "gather_min_rows": 4096,
-          # spline blocks: "auto" (pair kernel where eligible), "pair_wide" (pair kernel, tiles accessed in
-          # place in global memory even where they fit shared memory), "tc2" (skip the pair kernel; A/B)
-          "spline_kernel": "auto"}
+          # spline blocks: "auto" (two-CTAs-per-SM kernel for narrow dense blocks, pair kernel for every other
+          # tensor-core shape), "pair" (pair kernel wherever eligible), "pair_wide" (pair kernel with tiles accessed
+          # in place in global memory even where they fit shared memory), "tc2" (never the pair kernel)
+          "spline_kernel": "auto",
+          # affine blocks: "auto" (two-CTAs-per-SM / one-CTA kernels for narrow blocks, the pair kernel for wide
+          # ones), "pair" (the pair kernel wherever eligible), "no_pair"
+          "affine_kernel": "auto"}
 
 _status = {}
 
@@ -149,10 +153,12 @@ def _mode_flags():
     sk = config.get("spline_kernel", "auto")
     if sk == "tc2":
         f |= _lib.FLAG_NO_PAIR
+    elif sk == "pair":
+        f |= _lib.FLAG_PREFER_PAIR
     elif sk == "pair_wide":
-        f |= _lib.FLAG_FORCE_WIDE
+        f |= _lib.FLAG_FORCE_WIDE | _lib.FLAG_PREFER_PAIR
     elif sk != "auto":
-        raise ValueError("engine.config['spline_kernel'] must be 'auto', 'pair_wide' or 'tc2'")
+        raise ValueError("engine.config['spline_kernel'] must be 'auto', 'pair', 'pair_wide' or 'tc2'")
     return f
 
 
@@ -322,8 +328,16 @@ def affine_coupling(cond, tr, shift, scale, log_alpha, inverse=False, preserve_v
         return outs, dlogp
     # (the affine entry point has no per-call status argument: point the library at THIS device's flag)
     lib.bgx_set_status_buffer(C.c_void_p(pipeline_status(tr[0].device).data_ptr()))
-    f = flags | _mode_flags() | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
+    f = flags | (_mode_flags() & ~(_lib.FLAG_NO_PAIR | _lib.FLAG_FORCE_WIDE | _lib.FLAG_PREFER_PAIR)) \
+        | (_lib.FLAG_INVERSE if inverse else 0) | (_lib.FLAG_PRESERVE_VOLUME if preserve_volume else 0) \
         | (_lib.FLAG_CIRCULAR if is_circular else 0)
+    ak = config.get("affine_kernel", "auto")
+    if ak == "pair":
+        f |= _lib.FLAG_PREFER_PAIR
+    elif ak == "no_pair":
+        f |= _lib.FLAG_NO_PAIR
+    elif ak != "auto":
+        raise ValueError("engine.config['affine_kernel'] must be 'auto', 'pair' or 'no_pair'")
     rc = lib.bgx_affine_coupling(C.byref(io), C.byref(shift) if shift is not None else None,
                                  C.byref(scale) if scale is not None else None, float(log_alpha), f, _stream())
     _lib.check(rc, "bgx_affine_coupling")

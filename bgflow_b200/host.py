@@ -1,28 +1,124 @@
-"""Host-buffer entry point: run a flow on data that lives in (pinned) host memory.
+"""Host-buffer entry points: run a flow on data that lives in (pinned) host memory.
 
 ``HostPipeline.run(z_host)`` is the call ``bench.py`` times for its end-to-end number: the
 batch is cut into chunks that are copied host->device, pushed through the flow and copied back
 device->host on a small ring of CUDA streams, so the PCIe transfers of neighbouring chunks
 overlap the kernels of the current one (the reference does ``x.to(device)`` / ``.cpu()`` around a
 monolithic call, bgflow/bg.py:115-117).
+
+``HostPipeline.sample(n)`` is the sampling call of a generator (bgflow/bg.py:105-135): the prior is
+drawn ON THE DEVICE chunk by chunk (``prior.sample`` — bgflow/distribution/normal.py:75-92 draws on the
+parameter's device too), so nothing crosses PCIe host->device; only samples, ``dlogp`` and (optionally) the
+generator energy ``prior.energy(z) + dlogp`` (bg.py:124-126) come back.
+
+``bind_to_gpu_numa`` pins the calling process to the CPUs of the GPU's NUMA node BEFORE pinned buffers are
+allocated (first-touch places them on that node); ``copy_ceiling`` measures what the host<->device link
+gives this process for concurrent H2D + D2H copies — the denominator of the end-to-end number.
 """
+
+import os
 
 import torch
 
-__all__ = ["HostPipeline"]
+__all__ = ["HostPipeline", "bind_to_gpu_numa", "copy_ceiling"]
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index):
+    """Restrict this process to the CPUs local to GPU ``device_index`` (sysfs ``local_cpulist`` of its PCI
+    function).  Returns ``{"numa_node", "cpus", "bound"}``; a no-op (bound False) where sysfs does not say."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        with open(os.path.join(path, "numa_node")) as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(os.path.join(path, "local_cpulist")) as f:
+            text = f.read().strip()
+        cpus = _parse_cpulist(text) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(cpus=text, bound=True)
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return info
+
+
+def copy_ceiling(device, nbytes=256 << 20, reps=4):
+    """Concurrent pinned H2D + D2H ``cudaMemcpyAsync`` on two streams: GB/s per direction for this
+    process (call it on every rank at once to see what the box gives N GPUs together)."""
+    device = torch.device(device)
+    n = nbytes // 4
+    h_in = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_in.zero_()
+    h_out.zero_()
+    d_in = torch.empty(n, dtype=torch.float32, device=device)
+    d_out = torch.zeros(n, dtype=torch.float32, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    out = {}
+    for mode in ("h2d", "d2h", "both"):
+        ms = {}
+        for _ in range(2):       # first pass = warm-up
+            torch.cuda.synchronize(device)
+            ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in ("h2d", "d2h")}
+            if mode in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    ev["h2d"][0].record()
+                    for _ in range(reps):
+                        d_in.copy_(h_in, non_blocking=True)
+                    ev["h2d"][1].record()
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    ev["d2h"][0].record()
+                    for _ in range(reps):
+                        h_out.copy_(d_out, non_blocking=True)
+                    ev["d2h"][1].record()
+            torch.cuda.synchronize(device)
+            for k in ("h2d", "d2h"):
+                if mode in (k, "both"):
+                    ms[k] = ev[k][0].elapsed_time(ev[k][1])
+        for k, v in ms.items():
+            out[f"{k}_gbs" + ("_concurrent" if mode == "both" else "")] = reps * nbytes / (v * 1e-3) / 1e9
+    return out
 
 
 class HostPipeline:
     def __init__(self, flow, dim_in, dim_out, max_rows, device, chunk_rows=1 << 17, n_streams=3,
-                 inverse=False):
+                 inverse=False, prior=None, with_energy=False):
         self.flow = flow
         self.device = torch.device(device)
         self.chunk = int(chunk_rows)
         self.inverse = inverse
+        self.prior = prior
+        self.with_energy = with_energy
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         self.out = torch.empty(max_rows, dim_out, dtype=torch.float32).pin_memory()
         self.dlogp = torch.empty(max_rows, 1, dtype=torch.float32).pin_memory()
+        self.energy = torch.empty(max_rows, 1, dtype=torch.float32).pin_memory() if with_energy else None
         self.dim_in = dim_in
+
+    def _fan_out(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        return cur
+
+    def _fan_in(self, cur):
+        for s in self.streams:
+            cur.wait_stream(s)
+        cur.synchronize()          # the results are host memory: the call returns them complete
 
     @torch.no_grad()
     def run(self, z_host):
@@ -31,9 +127,7 @@ class HostPipeline:
         B = z_host.shape[0]
         if B > self.out.shape[0] or z_host.shape[1] != self.dim_in:
             raise ValueError("input does not fit the pipeline's buffers")
-        cur = torch.cuda.current_stream(self.device)
-        for s in self.streams:
-            s.wait_stream(cur)
+        cur = self._fan_out()
         for n, lo in enumerate(range(0, B, self.chunk)):
             hi = min(B, lo + self.chunk)
             s = self.streams[n % len(self.streams)]
@@ -42,7 +136,31 @@ class HostPipeline:
                 y, d = self.flow(x, inverse=self.inverse)
                 self.out[lo:hi].copy_(y, non_blocking=True)
                 self.dlogp[lo:hi].copy_(d, non_blocking=True)
-        for s in self.streams:
-            cur.wait_stream(s)
-        cur.synchronize()          # the results are host memory: the call returns them complete
+        self._fan_in(cur)
+        return self.out[:B], self.dlogp[:B]
+
+    @torch.no_grad()
+    def sample(self, n_samples, temperature=1.0):
+        """``BoltzmannGenerator.sample(n, with_dlogp=True[, with_energy=True])`` (bg.py:105-135) into pinned host
+        buffers: prior drawn on the device, flow, device->host copies of ``x``, ``dlogp`` (and the generator
+        energy ``prior.energy(z) + dlogp``) — no host->device traffic.  Returns host views."""
+        if self.prior is None:
+            raise ValueError("HostPipeline.sample needs a prior (a module with .sample(n) on the device)")
+        B = int(n_samples)
+        if B > self.out.shape[0]:
+            raise ValueError("n_samples does not fit the pipeline's buffers")
+        cur = self._fan_out()
+        for n, lo in enumerate(range(0, B, self.chunk)):
+            hi = min(B, lo + self.chunk)
+            s = self.streams[n % len(self.streams)]
+            with torch.cuda.stream(s):
+                z = self.prior.sample(hi - lo, temperature=temperature)
+                y, d = self.flow(z, temperature=temperature)
+                self.out[lo:hi].copy_(y, non_blocking=True)
+                self.dlogp[lo:hi].copy_(d, non_blocking=True)
+                if self.with_energy:
+                    self.energy[lo:hi].copy_(self.prior.energy(z, temperature=temperature) + d, non_blocking=True)
+        self._fan_in(cur)
+        if self.with_energy:
+            return self.out[:B], self.dlogp[:B], self.energy[:B]
         return self.out[:B], self.dlogp[:B]

@@ -134,8 +134,10 @@ typedef struct bgx_coupling_io {
 #define BGX_FLAG_CIRCULAR 4         /* affine.py:56-57: y %= 1 (shift-only) */
 #define BGX_FLAG_BF16X6 8           /* tensor-core path: 6 bf16 products (fp32-equivalent); default 3 (~2^-16) */
 #define BGX_FLAG_FORCE_SIMT 16      /* always use the generic fp32 SIMT kernel */
-#define BGX_FLAG_NO_PAIR 32         /* spline: skip the pair kernel (A/B against the two-CTAs-per-SM kernel) */
+#define BGX_FLAG_NO_PAIR 32         /* spline: never the pair kernel */
 #define BGX_FLAG_FORCE_WIDE 64      /* spline pair kernel: in-place global tile access even where the tile fits shared memory */
+#define BGX_FLAG_PREFER_PAIR 128    /* spline: the pair kernel even where the two-CTAs-per-SM kernel applies (default: the
+                                       latter for narrow dense blocks — measured faster at D = 66 — the pair kernel elsewhere) */
 
 /* y' = y * exp(ls) + mu   (forward)   |   y' = (y - mu) * exp(-ls)   (inverse)
  * mu = shift(cond), ls = tanh(scale(cond)) * exp(log_alpha);  dlogp = +-sum(ls).

@@ -32,12 +32,12 @@ def _delta(before, after):
     return {k: after[k] - before[k] for k in after if after[k] != before[k]}
 
 
-def _run_vs_oracle(dim, n_blocks, batch, seed, ytol, dtol):
-    blocks, split = of.make_stack("spline", dim, n_blocks, seed=seed)
-    blocks64, _ = of.make_stack("spline", dim, n_blocks, seed=seed, dtype=torch.float64)
+def _run_vs_oracle(dim, n_blocks, batch, seed, ytol, dtol, kind="spline", hidden=(128, 128)):
+    blocks, split = of.make_stack(kind, dim, n_blocks, seed=seed, hidden=hidden)
+    blocks64, _ = of.make_stack(kind, dim, n_blocks, seed=seed, hidden=hidden, dtype=torch.float64)
     flow = stack_from(blocks, split, DEV)
     g = torch.Generator().manual_seed(seed + batch)
-    z = torch.rand(batch, dim, generator=g)
+    z = torch.rand(batch, dim, generator=g) if kind == "spline" else torch.randn(batch, dim, generator=g)
     x_ref, d_ref = of.coupling_stack(blocks64, z.double(), split)
     zi_ref, di_ref = of.coupling_stack(blocks64, z.double(), split, inverse=True)
     with torch.no_grad():
@@ -60,16 +60,30 @@ def test_wide_mode_against_fp64_oracle(dim, batch):
     assert got == {"spline_pair_wide": 4}, got      # 2 blocks x 2 directions, all on the tensor-core kernel
 
 
+@pytest.mark.parametrize("dim,batch,hidden", [(384, 300, (128, 128, 128)), (384, 1, (128, 128)), (3072, 131, (128, 128, 128)),
+                                              (130, 1000, (128,)), (70, 515, (128, 128))])
+def test_affine_wide_against_fp64_oracle(dim, batch, hidden):
+    """RealNVP blocks of BASELINE config 5 on the affine pair kernel: shift and scale nets in the two
+    tensor-memory slots of one tile, layer 0 k-tiled, last layer 2 / 12 passes; ragged batches, D_t not a multiple
+    of 4 (scalar tile access) or of 32 (partial column groups)."""
+    engine.config["affine_kernel"] = "pair"
+    before = _lib.kernel_counts()
+    _run_vs_oracle(dim, 2, batch, seed=7, ytol=5e-5, dtol=1e-3, kind="affine", hidden=hidden)
+    got = _delta(before, _lib.kernel_counts())
+    assert got == {"affine_pair_wide": 4}, got
+
+
 @pytest.mark.parametrize("batch", [4, 128, 132, 256 + 128 + 8, 4096 + 4])
 def test_narrow_mode_against_fp64_oracle(batch):
     """D = 66 (33 | 33): tiles staged in shared memory by bulk TMA; one / two / odd numbers of tiles."""
+    engine.config["spline_kernel"] = "pair"
     before = _lib.kernel_counts()
     _run_vs_oracle(66, 3, batch, seed=5, ytol=2e-5, dtol=1e-3)
     got = _delta(before, _lib.kernel_counts())
     assert got == {"spline_pair": 6}, got
 
 
-@pytest.mark.parametrize("mode", ["auto", "pair_wide"])
+@pytest.mark.parametrize("mode", ["pair", "pair_wide"])
 def test_reference_golden_on_the_pair_kernel(mode):
     engine.config["spline_kernel"] = mode
     g = load_golden("spline_d66_8blk")
@@ -99,10 +113,10 @@ def test_pair_kernel_matches_two_cta_kernel():
     z = torch.rand((1 << 17) + 4, 66, generator=g).to(DEV)
     out = {}
     with torch.no_grad():
-        for mode in ("tc2", "auto", "pair_wide"):
+        for mode in ("tc2", "pair", "pair_wide"):
             engine.config["spline_kernel"] = mode
             out[mode] = flow(z) + flow(z, inverse=True)
-    for mode in ("auto", "pair_wide"):
+    for mode in ("pair", "pair_wide"):
         for k, (a, b) in enumerate(zip(out["tc2"], out[mode])):
             if k % 2 == 0:
                 assert torch.equal(a, b), (mode, k, float((a - b).abs().max()))
