@@ -425,30 +425,49 @@ def bench_config4(args, dev, rows=262144):
 
 
 def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
-    """Secondary measurement (BASELINE config 5, "KL-train grad allreduce"): reverse-KL steps on a
-    Gaussian target — kernel forward, recompute backward, ONE flat gradient all-reduce (NCCL when
-    world > 1), Adam.  ``rows`` samples per rank per step."""
-    from bgflow_b200.distributed import allreduce_gradients
+    """BASELINE config 5, "KL-train grad allreduce": reverse-KL steps on a Gaussian target — kernel forward,
+    recompute backward, per-coupling-block gradient buckets all-reduced over NCCL WHILE the backward of the earlier
+    blocks still runs (``BucketedGradReducer``), Adam.  ``rows`` samples per rank per step.  The same step is also
+    timed with the all-reduce after the backward and without any, which gives the exposed share of the collective."""
+    from bgflow_b200.distributed import BucketedGradReducer
+    red = BucketedGradReducer(flow)
     opt = torch.optim.Adam(flow.parameters(), lr=1e-5)
-    n_elems = [0]
 
-    def train_step():
-        opt.zero_grad(set_to_none=True)
+    def train_step(reduce=True):
+        red.zero_grad()
         z = torch.rand(rows, dim, device=dev) if kind == "spline" else torch.randn(rows, dim, device=dev)
         x, dlogp = flow(z)
         loss = (0.5 * ((x - 0.5) / 0.25).square().sum(-1, keepdim=True) - dlogp).mean()
         loss.backward()
-        n_elems[0] = allreduce_gradients(flow.parameters())
+        if reduce:
+            red.finish()
         opt.step()
 
-    for _ in range(3):
-        train_step()
     steps = max(3, args.steps // 2)
-    ms = run_timed(train_step, steps)
-    return {"samples_per_s": rows * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "rows_per_gpu": rows,
-            "allreduce_fp32_elems": n_elems[0], "n_gpus": world,
-            "what": "fused-kernel forward; backward = conditioner re-run + its GEMM backward (torch/cuBLAS fp32) + "
-                    "bgx_spline_backward kernel (affine: device-side torch); flat grad all-reduce; Adam"}
+    res = {}
+    for mode in ("overlap", "after_backward", "no_allreduce"):
+        red.overlap = mode == "overlap"
+        fn = (lambda: train_step(False)) if mode == "no_allreduce" else train_step
+        if mode == "no_allreduce":
+            red.overlap = False
+        for _ in range(3):
+            fn()
+        res[mode] = run_timed(fn, steps) / steps
+    red.remove()
+    out = {"samples_per_s": rows * world / (res["overlap"] * 1e-3), "ms_per_step": res["overlap"], "rows_per_gpu": rows,
+           "n_gpus": world, "allreduce_fp32_elems": red.n_elements, "allreduce_bytes": 4 * red.n_elements,
+           "buckets": len(red.buckets), "ms_per_step_allreduce_after_backward": res["after_backward"],
+           "ms_per_step_no_allreduce": res["no_allreduce"],
+           "what": "fused-kernel forward; backward = conditioner re-run + its GEMM backward (torch/cuBLAS fp32) + "
+                   "bgx_spline_backward kernel; one NCCL all-reduce per coupling block launched from a gradient hook "
+                   "as soon as that block's backward is done (overlaps the remaining backward); Adam"}
+    if world > 1:
+        alone = res["after_backward"] - res["no_allreduce"]
+        exposed = res["overlap"] - res["no_allreduce"]
+        out["allreduce_ms_alone"] = alone
+        out["allreduce_ms_exposed"] = exposed
+        out["overlap_fraction"] = (1.0 - exposed / alone) if alone > 1e-6 else None
+    return out
 
 
 def main():
@@ -467,6 +486,7 @@ def main():
     ap.add_argument("--sweep-batch", type=int, default=1 << 20)
     ap.add_argument("--sweep-batch-wide", type=int, default=1 << 20, help="rows per GPU for the D = 3072 sweep points")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the KL training step (gradient all-reduce) measurement")
     ap.add_argument("--extras", action="store_true",
                     help="also time the IC kernels, the restated single-GPU PyTorch path and a KL training step "
                          "(adds to the JSON line)")
@@ -707,10 +727,10 @@ def main():
                                            "single-GPU PyTorch path, restated)"},
             "ic_ala2": bench_ic(args, dev), "ic_tail": bench_tail(args, dev),
             "config4_pipeline": bench_config4(args, dev)}
-    if args.extras:
+    if not args.no_train:
         tr = bench_train(args, flow, kind, dim, dev, run_timed, world)
         if rank == 0:
-            out.setdefault("extras", {})["kl_train"] = tr
+            out["kl_train"] = tr
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

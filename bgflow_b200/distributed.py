@@ -10,7 +10,7 @@ reference's single-device ``KLTrainer.train`` (bgflow/nn/training/trainers.py:14
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_rows", "allreduce_gradients", "kl_train_step"]
+__all__ = ["shard_rows", "allreduce_gradients", "kl_train_step", "BucketedGradReducer"]
 
 
 def shard_rows(n_total, rank=None, world=None):
@@ -45,13 +45,107 @@ def allreduce_gradients(parameters, average=True, group=None):
     return int(flat.numel())
 
 
-def kl_train_step(generator, optimizer, n_samples_per_rank, temperature=1.0):
+class BucketedGradReducer:
+    """Gradient all-reduce overlapped with the backward pass.
+
+    The parameters of every bucket module (by default: every coupling block, i.e. every module with a
+    ``transformer`` attribute, plus one bucket for whatever is left) share ONE flat fp32 buffer; their
+    ``.grad`` tensors are views into it, so autograd accumulates in place and nothing is packed or copied.
+    A post-accumulate hook counts a bucket's parameters; when the last one has its gradient — a block's
+    backward is complete — the bucket's ``all_reduce(SUM, async_op=True)`` is launched.  NCCL runs it on its own
+    stream (ordered after the work already queued), while the main stream goes on with the backward of the
+    blocks earlier in the flow: the collectives of blocks N-1 .. 1 hide behind compute, only block 0's is exposed.
+    ``finish()`` (before ``optimizer.step()``) waits for the handles and divides by the world size.
+
+    Works on any backend / device (gloo on CPU in the tests); without a process group it only zeroes / averages."""
+
+    def __init__(self, module, bucket_modules=None, group=None, average=True):
+        self.group, self.average = group, average
+        if bucket_modules is None:
+            bucket_modules = [m for m in module.modules() if hasattr(m, "transformer")]
+        seen, groups = set(), []
+        for m in bucket_modules:
+            ps = [p for p in m.parameters() if p.requires_grad and id(p) not in seen]
+            seen.update(id(p) for p in ps)
+            if ps:
+                groups.append(ps)
+        rest = [p for p in module.parameters() if p.requires_grad and id(p) not in seen]
+        if rest:
+            groups.append(rest)
+        self.buckets, self._handles, self._hooks = [], [], []
+        for ps in groups:
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+            off = 0
+            for p in ps:
+                if p.dtype != torch.float32 or p.device != flat.device:
+                    raise NotImplementedError("BucketedGradReducer: fp32 parameters on one device per bucket")
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            b = {"flat": flat, "n": len(ps), "ready": 0}
+            self.buckets.append(b)
+            for p in ps:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+        self.launched = 0
+        self.overlap = True      # False: nothing is launched from the hooks; ``finish`` reduces after the backward
+
+    @property
+    def n_elements(self):
+        return sum(int(b["flat"].numel()) for b in self.buckets)
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, bucket):
+        def hook(param):
+            bucket["ready"] += 1
+            if bucket["ready"] == bucket["n"]:
+                bucket["ready"] = 0
+                if self.overlap and self._active():
+                    self._handles.append(dist.all_reduce(bucket["flat"], op=dist.ReduceOp.SUM, group=self.group,
+                                                         async_op=True))
+                    self.launched += 1
+        return hook
+
+    def zero_grad(self):
+        """Use instead of ``optimizer.zero_grad()``: the gradients must stay views of the buckets."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["ready"] = 0
+
+    def finish(self):
+        """Wait for the collectives launched during backward and average.  Returns the number of elements reduced."""
+        if not self.overlap and self._active():
+            for b in self.buckets:
+                dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group)
+        for h in self._handles:
+            h.wait()
+        self._handles.clear()
+        if self.average and self._active():
+            w = dist.get_world_size(self.group)
+            for b in self.buckets:
+                b["flat"].div_(w)
+        return self.n_elements
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()
+
+
+def kl_train_step(generator, optimizer, n_samples_per_rank, temperature=1.0, reducer=None):
     """One reverse-KL step of a data-parallel run: every rank draws its own samples
     (bg.py:13-17 ``kldiv``), gradients are all-reduced, all ranks take the same optimiser step.
-    Returns the rank-local loss value (a tensor)."""
-    optimizer.zero_grad(set_to_none=True)
+    With a ``BucketedGradReducer`` the all-reduce of every coupling block overlaps the rest of the backward;
+    without one a single flat all-reduce follows it.  Returns the rank-local loss value (a tensor)."""
+    if reducer is not None:
+        reducer.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=True)
     loss = generator.kldiv(n_samples_per_rank, temperature=temperature).mean()
     loss.backward()
-    allreduce_gradients(generator.parameters())
+    if reducer is not None:
+        reducer.finish()
+    else:
+        allreduce_gradients(generator.parameters())
     optimizer.step()
     return loss.detach()

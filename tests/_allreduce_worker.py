@@ -24,6 +24,19 @@ ref.load_state_dict(net.state_dict())
 err = max((p.grad - q.grad).abs().max().item() for p, q in zip(net.parameters(), ref.parameters()))
 assert n == sum(p.numel() for p in net.parameters()), n
 assert err < 1e-6, err
+
+# the overlapped path: per-"block" buckets all-reduced from post-accumulate hooks while backward continues
+net2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+net2.load_state_dict(net.state_dict())
+red = bd.BucketedGradReducer(net2, bucket_modules=[net2[2], net2[0]], average=False)
+for step in range(2):                      # twice: the buckets are reused, gradients must not pile up
+    red.zero_grad()
+    (net2(full[lo:hi]).pow(2).sum() / 16).backward()
+    n2 = red.finish()
+    err2 = max((p.grad - q.grad).abs().max().item() for p, q in zip(net2.parameters(), ref.parameters()))
+    assert n2 == n and err2 < 1e-6, (step, n2, err2)
+assert red.launched == 4, red.launched     # 2 buckets x 2 steps, each launched from a hook during backward
+assert all(p.grad.data_ptr() >= b["flat"].data_ptr() for b in red.buckets[:1] for p in net2[2].parameters())
 if rank == 0:
-    print(f"ALLREDUCE_OK world={world} elements={n} err={err:.2e}")
+    print(f"ALLREDUCE_OK world={world} elements={n} err={err:.2e} bucketed_err={err2:.2e}")
 dist.destroy_process_group()
