@@ -73,20 +73,6 @@ def build(force=False, verbose=False):
             if verbose:
                 print(log)
     for stale in set(glob.glob(os.path.join(OBJ, "*.o"))) - set(objs):
-        if not os.path.basename(stale).startswith("experimental_"):
-            os.remove(stale)
+        os.remove(stale)
     _run([nvcc, "-shared", "-o", LIB_PATH, *objs])
     return LIB_PATH
-
-
-def compile_check_experimental():
-    """``nvcc -c`` of ``csrc/experimental/*.cu`` (drafts that are NOT linked into the library): keeps
-    them compiling.  Objects go to ``csrc/_obj/experimental_*.o``."""
-    os.makedirs(OBJ, exist_ok=True)
-    nvcc = _nvcc()
-    out = []
-    for src in sorted(glob.glob(os.path.join(CSRC, "experimental", "*.cu"))):
-        obj = os.path.join(OBJ, "experimental_" + os.path.basename(src)[:-3] + ".o")
-        _run([nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
-        out.append(obj)
-    return out

@@ -34,6 +34,7 @@
 #include "bgx_tc.cuh"
 #include "bgx_tc_epi.cuh"
 #include "bgx_spline_reg.cuh"
+#include "bgx_spline_reg2.cuh"
 #include "bgx_pair.cuh"
 
 namespace bgx {
@@ -331,17 +332,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
             tmem_ld_wait();
-            uint32_t t1[16], t2[16], t3[16];
+            uint32_t t1[16], t2[16];
             const float4* b4 = reinterpret_cast<const float4*>(bias_h + l * 128 + j * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 bb = b4[i];
-              const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
-              const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
-              const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
-              const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
-              split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
-              split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
+              hidden_pair2<ACT>(v[4 * i], v[4 * i + 1], bb.x, bb.y, t1[2 * i], t2[2 * i]);
+              hidden_pair2<ACT>(v[4 * i + 2], v[4 * i + 3], bb.z, bb.w, t1[2 * i + 1], t2[2 * i + 1]);
             }
             const uint32_t acol = tmem + lane_base + s * P_SLOT + P_A + j * 16;
             tmem_st16(acol, t1);
@@ -351,73 +348,91 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&S->a_ready[s]);
           } else {
-            // ---- last layer: pass c holds dims 5c .. 5c+4; this warp takes the dims i with (i + c) % 4 == j
+            // ---- last layer: pass c holds dims 5c .. 5c+4.  Per (pass, slot) the four warps of a quadrant take the
+            // roles {dims 0,1 packed | dims 2,3 packed | dim 4 | nothing}, rotating with c + s so the load evens out;
+            // a pair of dims is evaluated in packed fp32 lanes (bgx_spline_reg2.cuh)
             const int c = u - (G + L - 2);
-            const int i0 = (j - c) & 3;
+            const int role = (j + c + s) & 3;
             const long long row = tile_of(it, s) * P_TM + r_in_tile;
             const bool live = row < a.B;
             if (!WIDE && c == 0) {
               ok = ok && mbar_wait_sleep(&S->y_full[s], ph_y[s], a.status);
               ph_y[s] ^= 1;
             }
-            const int d0 = P_DPP * c + i0;               // first dim of this warp in the pass (second: d0 + 4, only if i0 == 0)
-            const int n_mine = (d0 < a.D_t ? 1 : 0) + ((i0 == 0 && d0 + 4 < a.D_t) ? 1 : 0);
+            const int iA = role == 2 ? 4 : 2 * role;                 // first dim of this warp inside the pass
+            const int dA = P_DPP * c + iA;
+            const bool hasA = role < 3 && dA < a.D_t, hasB = role < 2 && dA + 1 < a.D_t;
             float* yrow = WIDE ? a.tout + row * (long long)a.D_t : ybuf + (s * P_TM + r_in_tile) * a.D_t;
-            // operands that do not depend on the accumulator first: the transformed inputs and the bias
-            float xin[2] = {0.f, 0.f};
+            // the transformed inputs do not depend on the accumulator: fetch them before waiting for it
+            float xA = 0.f, xB = 0.f;
             if (WIDE) {
-              if (live && n_mine > 0) xin[0] = a.tin[row * (long long)a.D_t + d0];
-              if (live && n_mine > 1) xin[1] = a.tin[row * (long long)a.D_t + d0 + 4];
+              if (live && hasA) xA = a.tin[row * (long long)a.D_t + dA];
+              if (live && hasB) xB = a.tin[row * (long long)a.D_t + dA + 1];
             } else {
-              if (n_mine > 0) xin[0] = yrow[d0];
-              if (n_mine > 1) xin[1] = yrow[d0 + 4];
+              if (hasA) xA = yrow[dA];
+              if (hasB) xB = yrow[dA + 1];
             }
-            const float* bsrc = (WIDE ? a.bias_last : bias_l) + ((size_t)c * P_DPP + i0) * P_BPAD;
-            float p[P_BPAD];
-            if (n_mine > 0) {
-              const float4* b4 = reinterpret_cast<const float4*>(bsrc);
-#pragma unroll
-              for (int qq = 0; qq < 7; ++qq) {
-                const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
-                p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
-              }
-            }
+            const float* bsrc = (WIDE ? a.bias_last : bias_l) + ((size_t)c * P_DPP + iA) * P_BPAD;
             wait_acc(s);
-            const uint32_t acc_addr = tmem + lane_base + s * P_SLOT + P_ACC;
-#pragma unroll 1
-            for (int m = 0; m < n_mine; ++m) {
-              const int i = i0 + 4 * m;
-              uint32_t v[32];
-              tmem_ld32(acc_addr + i * P_PS, v);
-              tmem_ld_wait();
-              if (m == n_mine - 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S->acc_empty[s]);
-              }
-              if (m == 1) {
-                const float4* b4 = reinterpret_cast<const float4*>(bsrc + 4 * P_BPAD);
-#pragma unroll
-                for (int qq = 0; qq < 7; ++qq) {
-                  const float4 bb = WIDE ? __ldg(b4 + qq) : b4[qq];
-                  p[4 * qq] = bb.x; p[4 * qq + 1] = bb.y; p[4 * qq + 2] = bb.z; p[4 * qq + 3] = bb.w;
-                }
-              }
-              float pp[P_PS];
-#pragma unroll
-              for (int k = 0; k < P_PS; ++k) pp[k] = __uint_as_float(v[k]) + p[k];
-              float x = xin[m];
-              n_oob += (live && (x < a.ck.left || x > a.ck.right)) ? 1 : 0;
-              x = fminf(fmaxf(x, a.ck.left), a.ck.right);
-              float y, lad;
-              rqs_eval_reg<!INVERSE, true>(pp, a.ck, x, y, lad);
-              if (!WIDE || live) yrow[P_DPP * c + i] = y;
-              ld[s] += lad;
-            }
-            if (n_mine == 0) {
+            const uint32_t acc_addr = tmem + lane_base + s * P_SLOT + P_ACC + iA * P_PS;
+            auto release = [&]() {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&S->acc_empty[s]);
+            };
+            n_oob += (live && hasA && (xA < a.ck.left || xA > a.ck.right)) ? 1 : 0;
+            n_oob += (live && hasB && (xB < a.ck.left || xB > a.ck.right)) ? 1 : 0;
+            xA = fminf(fmaxf(xA, a.ck.left), a.ck.right);
+            xB = fminf(fmaxf(xB, a.ck.left), a.ck.right);
+            if (hasB) {
+              uint32_t va[25], vb[25];
+              tmem_ld25(acc_addr, va);
+              tmem_ld25(acc_addr + P_PS, vb);
+              tmem_ld_wait();
+              release();
+              F2 p2[P_PS];
+              const float4* bA = reinterpret_cast<const float4*>(bsrc);
+              const float4* bB = reinterpret_cast<const float4*>(bsrc + P_BPAD);
+#pragma unroll
+              for (int qq = 0; qq < 6; ++qq) {
+                const float4 x4 = WIDE ? __ldg(bA + qq) : bA[qq], y4 = WIDE ? __ldg(bB + qq) : bB[qq];
+                p2[4 * qq] = f2(__uint_as_float(va[4 * qq]) + x4.x, __uint_as_float(vb[4 * qq]) + y4.x);
+                p2[4 * qq + 1] = f2(__uint_as_float(va[4 * qq + 1]) + x4.y, __uint_as_float(vb[4 * qq + 1]) + y4.y);
+                p2[4 * qq + 2] = f2(__uint_as_float(va[4 * qq + 2]) + x4.z, __uint_as_float(vb[4 * qq + 2]) + y4.z);
+                p2[4 * qq + 3] = f2(__uint_as_float(va[4 * qq + 3]) + x4.w, __uint_as_float(vb[4 * qq + 3]) + y4.w);
+              }
+              p2[24] = f2(__uint_as_float(va[24]) + (WIDE ? __ldg(bsrc + 24) : bsrc[24]),
+                          __uint_as_float(vb[24]) + (WIDE ? __ldg(bsrc + P_BPAD + 24) : bsrc[P_BPAD + 24]));
+              F2 y2, l2;
+              rqs_eval_reg2<!INVERSE>(p2, a.ck, f2(xA, xB), y2, l2);
+              if (!WIDE || live) {
+                yrow[dA] = lo(y2);
+                yrow[dA + 1] = hi(y2);
+              }
+              ld[s] += lo(l2);
+              ld[s] += hi(l2);
+            } else if (hasA) {
+              uint32_t va[25];
+              tmem_ld25(acc_addr, va);
+              tmem_ld_wait();
+              release();
+              float pp[P_PS];
+              const float4* bA = reinterpret_cast<const float4*>(bsrc);
+#pragma unroll
+              for (int qq = 0; qq < 6; ++qq) {
+                const float4 x4 = WIDE ? __ldg(bA + qq) : bA[qq];
+                pp[4 * qq] = __uint_as_float(va[4 * qq]) + x4.x;
+                pp[4 * qq + 1] = __uint_as_float(va[4 * qq + 1]) + x4.y;
+                pp[4 * qq + 2] = __uint_as_float(va[4 * qq + 2]) + x4.z;
+                pp[4 * qq + 3] = __uint_as_float(va[4 * qq + 3]) + x4.w;
+              }
+              pp[24] = __uint_as_float(va[24]) + (WIDE ? __ldg(bsrc + 24) : bsrc[24]);
+              float y, lad;
+              rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
+              if (!WIDE || live) yrow[dA] = y;
+              ld[s] += lad;
+            } else {
+              release();
             }
             if (c == P - 1) {
               // ---- end of this slot's tile: hand the output tile to the I/O thread and the log-det shares to the

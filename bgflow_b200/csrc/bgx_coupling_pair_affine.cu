@@ -230,17 +230,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
             tmem_ld_wait();
-            uint32_t t1[16], t2[16], t3[16];
+            uint32_t t1[16], t2[16];
             const float4* b4 = reinterpret_cast<const float4*>(bias_h + s * a.hid_bias_floats + l * 128 + j * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 bb = b4[i];
-              const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
-              const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
-              const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
-              const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
-              split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
-              split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
+              hidden_pair2<ACT>(v[4 * i], v[4 * i + 1], bb.x, bb.y, t1[2 * i], t2[2 * i]);
+              hidden_pair2<ACT>(v[4 * i + 2], v[4 * i + 3], bb.z, bb.w, t1[2 * i + 1], t2[2 * i + 1]);
             }
             const uint32_t acol = tmem + lane_base + s * P_SLOT + P_A + j * 16;
             tmem_st16(acol, t1);

@@ -22,6 +22,7 @@
 #include "bgx_tc.cuh"
 #include "bgx_tc_epi.cuh"
 #include "bgx_spline_reg.cuh"
+#include "bgx_spline_reg2.cuh"
 
 namespace bgx {
 using namespace tc;
@@ -75,7 +76,9 @@ struct alignas(16) T2Smem {
 // loads per dim) and MUFU lg2 for the log-det.  (Tried and measured slower on the B200: evaluating two
 // dims in one basic block for ILP; handing the accumulator back before evaluating — both cost more in
 // registers, extra tcgen05.ld and instruction-cache misses than the shorter wait gains.)
-template <bool INVERSE, int ACT, bool FAST>
+// PACKED: the dims of a pass are evaluated two at a time in packed fp32 pairs (bgx_spline_reg2.cuh: FADD2 / FMUL2 /
+// FFMA2, one issue slot for two dims) — the epilogue is issue-bound, so this is where the time goes.
+template <bool INVERSE, int ACT, bool FAST, bool PACKED = false>
 __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(const T2Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the address space: LDS/STS instead of generic LD/ST)
@@ -357,12 +360,17 @@ __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(cons
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bb = b4[i];
-            const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
-            const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
-            const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
-            const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
-            split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
-            split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
+            if (PACKED) {
+              hidden_pair2<ACT>(v[4 * i], v[4 * i + 1], bb.x, bb.y, t1[2 * i], t2[2 * i]);
+              hidden_pair2<ACT>(v[4 * i + 2], v[4 * i + 3], bb.z, bb.w, t1[2 * i + 1], t2[2 * i + 1]);
+            } else {
+              const float h0 = act_fast<ACT>(__uint_as_float(v[4 * i]) + bb.x);
+              const float h1 = act_fast<ACT>(__uint_as_float(v[4 * i + 1]) + bb.y);
+              const float h2 = act_fast<ACT>(__uint_as_float(v[4 * i + 2]) + bb.z);
+              const float h3 = act_fast<ACT>(__uint_as_float(v[4 * i + 3]) + bb.w);
+              split_bf16(h0, h1, 2, t1[2 * i], t2[2 * i], t3[2 * i]);
+              split_bf16(h2, h3, 2, t1[2 * i + 1], t2[2 * i + 1], t3[2 * i + 1]);
+            }
           }
           const uint32_t acol = tmem + lane_base + T2_A + col / 2;
           tmem_st16(acol, t1);
@@ -390,7 +398,48 @@ __global__ void __launch_bounds__(T2_THREADS, 2) spline_coupling_tc2_kernel(cons
         for (int i = i0; i < T2_DPP; i += 2) n_mine += (5 * c + i < a.D_t) ? 1 : 0;
         const float* bv = bias_s + last_off + c * (T2_DPP * T2_BPAD);
         bool released = false;
-        for (int m = 0; m < n_mine; ++m) {
+        int m_first = 0;
+        if (PACKED && FAST && n_mine >= 2) {
+          // ---- dims i0 and i0 + 2 of this pass together, one per fp32 lane
+          const int iA = i0, iB = i0 + 2;
+          uint32_t va[25], vb[25];
+          tmem_ld25(acc_addr + iA * T2_PS, va);
+          tmem_ld25(acc_addr + iB * T2_PS, vb);
+          tmem_ld_wait();
+          if (n_mine == 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S->acc_empty);
+            released = true;
+          }
+          F2 p2[T2_PS];
+          {
+            const float4* bA = reinterpret_cast<const float4*>(bv + iA * T2_BPAD);
+            const float4* bB = reinterpret_cast<const float4*>(bv + iB * T2_BPAD);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const float4 x4 = bA[q], y4 = bB[q];
+              p2[4 * q] = f2(__uint_as_float(va[4 * q]) + x4.x, __uint_as_float(vb[4 * q]) + y4.x);
+              p2[4 * q + 1] = f2(__uint_as_float(va[4 * q + 1]) + x4.y, __uint_as_float(vb[4 * q + 1]) + y4.y);
+              p2[4 * q + 2] = f2(__uint_as_float(va[4 * q + 2]) + x4.z, __uint_as_float(vb[4 * q + 2]) + y4.z);
+              p2[4 * q + 3] = f2(__uint_as_float(va[4 * q + 3]) + x4.w, __uint_as_float(vb[4 * q + 3]) + y4.w);
+            }
+            p2[24] = f2(__uint_as_float(va[24]) + bv[iA * T2_BPAD + 24], __uint_as_float(vb[24]) + bv[iB * T2_BPAD + 24]);
+          }
+          float* ysA = yrow + 5 * c + iA;
+          float xA = ysA[0], xB = ysA[2];
+          n_oob += ((xA < a.ck.left || xA > a.ck.right) ? 1 : 0) + ((xB < a.ck.left || xB > a.ck.right) ? 1 : 0);
+          xA = fminf(fmaxf(xA, a.ck.left), a.ck.right);
+          xB = fminf(fmaxf(xB, a.ck.left), a.ck.right);
+          F2 y2, l2;
+          rqs_eval_reg2<!INVERSE>(p2, a.ck, f2(xA, xB), y2, l2);
+          ysA[0] = lo(y2);
+          ysA[2] = hi(y2);
+          ld += lo(l2);
+          ld += hi(l2);
+          m_first = 2;
+        }
+        for (int m = m_first; m < n_mine; ++m) {
           const int i = i0 + 2 * m;
           uint32_t v[32];
           tmem_ld32(acc_addr + i * T2_PS, v);
@@ -531,16 +580,24 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
     if (rc) return rc;
   }
   using KernT = void (*)(const T2Args);
-#define BGX_T2_ROW(INV, FAST) \
-  {spline_coupling_tc2_kernel<INV, 0, FAST>, spline_coupling_tc2_kernel<INV, 1, FAST>, \
-   spline_coupling_tc2_kernel<INV, 2, FAST>, spline_coupling_tc2_kernel<INV, 3, FAST>}
-  static const KernT kerns[2][2][4] = {{BGX_T2_ROW(false, false), BGX_T2_ROW(true, false)},
-                                       {BGX_T2_ROW(false, true), BGX_T2_ROW(true, true)}};
+#define BGX_T2_ROW(INV, FAST, PK) \
+  {spline_coupling_tc2_kernel<INV, 0, FAST, PK>, spline_coupling_tc2_kernel<INV, 1, FAST, PK>, \
+   spline_coupling_tc2_kernel<INV, 2, FAST, PK>, spline_coupling_tc2_kernel<INV, 3, FAST, PK>}
+  static const KernT kerns[3][2][4] = {{BGX_T2_ROW(false, false, false), BGX_T2_ROW(true, false, false)},
+                                       {BGX_T2_ROW(false, true, false), BGX_T2_ROW(true, true, false)},
+                                       {BGX_T2_ROW(false, true, true), BGX_T2_ROW(true, true, true)}};
 #undef BGX_T2_ROW
   if (net->act < 0 || net->act > 3) return BGX_ERR_INVALID;
-  static const int pair = [] { const char* e = getenv("BGX_T2_FAST"); return e ? (atoi(e) ? 1 : 0) : T2_FAST_DEFAULT; }();
+  // BGX_T2_FAST=0: first epilogue (A/B switch); BGX_T2_PACKED=0: scalar spline evaluation (A/B switch)
+  static const int pair = [] {
+    const char* e = getenv("BGX_T2_FAST");
+    const int fast = e ? (atoi(e) ? 1 : 0) : T2_FAST_DEFAULT;
+    const char* pk = getenv("BGX_T2_PACKED");
+    const int packed = pk ? (atoi(pk) ? 1 : 0) : 1;
+    return fast ? (packed ? 2 : 1) : 0;
+  }();
   KernT kern = kerns[pair][a.inverse][net->act];
-  static size_t configured[2][2][4] = {};
+  static size_t configured[3][2][4] = {};
   if (smem > configured[pair][a.inverse][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

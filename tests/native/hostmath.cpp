@@ -47,3 +47,29 @@ extern "C" int hm_rqs_eval(int root, int fast, float left, float right, float bo
   }
   return 0;
 }
+
+// ---- the packed two-dims-per-thread evaluation (bgx_spline_reg2.cuh), host build: pairs (2i, 2i+1)
+#include "bgx_spline_reg2.cuh"
+
+extern "C" int hm_rqs_eval2(int root, float left, float right, float bottom, float top, float min_w, float min_h,
+                            float min_d, int identity_init, int n, const float* params, const float* x, float* y,
+                            float* lad) {
+  bgx::SplineK c;
+  const float wx = right - left, hy = top - bottom;
+  const float beta = identity_init ? (float)(0.6931471805599453 / (1.0 - (double)min_d)) : 1.f;
+  c.left = left; c.right = right; c.bottom = bottom; c.top = top;
+  c.wscale = wx * (1.f - min_w * bgx::NB); c.hscale = hy * (1.f - min_h * bgx::NB);
+  c.wstep = wx * min_w; c.hstep = hy * min_h;
+  c.min_d = min_d; c.beta = beta; c.beta_l2e = beta * bgx::LOG2E; c.ln2_over_beta = bgx::LN2 / beta;
+  for (int i = 0; i + 1 < n; i += 2) {
+    bgx::F2 p[bgx::PS];
+    for (int k = 0; k < bgx::PS; ++k) p[k] = bgx::f2(params[i * bgx::PS + k], params[(i + 1) * bgx::PS + k]);
+    const bgx::F2 xi = bgx::f2(fminf(fmaxf(x[i], left), right), fminf(fmaxf(x[i + 1], left), right));
+    bgx::F2 yy, ll;
+    if (root) bgx::rqs_eval_reg2<true>(p, c, xi, yy, ll);
+    else bgx::rqs_eval_reg2<false>(p, c, xi, yy, ll);
+    y[i] = bgx::lo(yy); y[i + 1] = bgx::hi(yy);
+    lad[i] = bgx::lo(ll); lad[i + 1] = bgx::hi(ll);
+  }
+  return 0;
+}

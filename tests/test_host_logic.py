@@ -361,17 +361,3 @@ def test_fuse_domain_maps_rewrites_builder_tail():
     # nothing to fuse: unchanged block list
     plain = bg.SequentialFlow([bg.SwapFlow(), bg.SwapFlow()])
     assert len(bg.fuse_domain_maps(plain)) == 2
-
-
-def test_experimental_tc3_protocol_model():
-    """The barrier protocol of the drafted (not built) half-chunk kernel, csrc/experimental/: abstract
-    model under random schedules — no deadlock, no parity aliasing, no overwrite of a busy buffer."""
-    import importlib.util
-    path = os.path.join(ROOT, "bgflow_b200", "csrc", "experimental", "sim_tc3_protocol.py")
-    spec = importlib.util.spec_from_file_location("sim_tc3_protocol", path)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    for kt, nhalf in (((1, 2), 17), ((1, 2), 1), ((2, 2, 2), 5)):
-        for n_tiles in (1, 3):
-            for seed in range(4):
-                assert mod.Sim(n_tiles, kt, nhalf, seed).run()

@@ -195,3 +195,27 @@ def test_register_spline_fast_and_reference_paths_agree(hm):
     y, lad = _rqs(hm, True, True, np.zeros((100, 25), np.float32), np.linspace(0.01, 0.99, 100))
     np.testing.assert_allclose(y, np.linspace(0.01, 0.99, 100), atol=2e-6)
     np.testing.assert_allclose(lad, 0.0, atol=2e-6)
+
+
+@pytest.mark.parametrize("root", [True, False])
+@pytest.mark.parametrize("dom", [(0.0, 1.0, 0.0, 1.0), (-2.0, 3.0, -1.0, 5.0)])
+def test_packed_two_dim_evaluation_equals_scalar_evaluation(hm, root, dom):
+    """``rqs_eval_reg2`` (two transformed dims per thread in packed fp32 pairs, bgx_spline_reg2.cuh) performs
+    the scalar evaluation's operations in the same order for each lane: on the host build both agree to the last
+    bit, on every input including the domain edges."""
+    rng = np.random.default_rng(11)
+    n = 20000
+    params = (rng.standard_normal((n, 25)) * rng.choice([0.3, 1.0, 3.0], size=(n, 1))).astype(np.float32)
+    left, right, bottom, top = dom
+    lo, hi = (bottom, top) if root else (left, right)
+    x = (lo + (hi - lo) * rng.random(n)).astype(np.float32)
+    x[:4] = [lo, hi, lo + 1e-7 * (hi - lo), hi - 1e-6 * (hi - lo)]
+    y1, l1 = _rqs(hm, root, True, params, x, dom)
+    hm.hm_rqs_eval2.restype = C.c_int
+    hm.hm_rqs_eval2.argtypes = [C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_int] + [C.c_void_p] * 4
+    y2, l2 = np.empty_like(x), np.empty_like(x)
+    rc = hm.hm_rqs_eval2(int(root), *dom, 1e-3, 1e-3, 1e-3, 1, n, params.ctypes.data, x.ctypes.data, y2.ctypes.data,
+                         l2.ctypes.data)
+    assert rc == 0
+    np.testing.assert_array_equal(y1, y2)
+    np.testing.assert_array_equal(l1, l2)
