@@ -578,7 +578,7 @@ def main():
         engine.config["precision"] = os.environ["BGX_PRECISION"]
     if os.environ.get("BGX_FORCE_SIMT"):
         engine.config["force_simt"] = True
-    if os.environ.get("BGX_SPLINE_KERNEL"):
+    if os.environ.get("BGX_SPLINE_KERNEL"):  # A/B switch
         engine.config["spline_kernel"] = os.environ["BGX_SPLINE_KERNEL"]
     config["kernel"] = ("fp32 SIMT" if engine.config["force_simt"] else
                         f"tcgen05 kind::f16, operands split into bf16 terms ({engine.config['precision']})")

@@ -71,11 +71,18 @@ struct alignas(16) PSmem {
   uint64_t dl_ready[2];    // 16: the four dim shares of every row's log-det are written
   uint64_t dl_free[2];     // 1: ... and summed (the buffer may be rewritten)
   uint32_t tmem_base, pad[3];
-  float dl_part[2][4][P_TM];       // [slot][dim share][row]
+  float dl_part[2][6][P_TM];       // [slot][dim share (epilogue warp of the quadrant)][row]
 };
 
-template <bool INVERSE, int ACT, bool WIDE>
-__global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(const __grid_constant__ PArgs a) {
+// EPW = epilogue warps per TMEM lane quadrant.  4: 16 epilogue warps at <= 96 registers, a quadrant's five dims of a pass
+// go to its warps as {2 packed, 2 packed, 1, -}.  6: 24 epilogue warps at <= 72 registers, one dim per warp per pass
+// {1, 1, 1, 1, 1, -}: a shorter critical path per pass and more warps per scheduler to hide the evaluation's latencies
+// (the epilogue is bound by per-warp instruction latency, not by issue slots: profiles/README.md).
+template <bool INVERSE, int ACT, bool WIDE, int EPW>
+__global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_kernel(const __grid_constant__ PArgs a) {
+  constexpr int NW = 4 * EPW;                  // epilogue warps
+  constexpr int NTHREADS = (NW + 4) * 32;
+  constexpr int W_PROD = NW, W_IO = NW + 1, W_MMA = NW + 2, W_RED = NW + 3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = base;
@@ -95,14 +102,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       mbar_init(&S->w_empty[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&S->a_ready[s], P_EPI_WARPS);
+      mbar_init(&S->a_ready[s], NW);
       mbar_init(&S->acc_full[s], 1);
-      mbar_init(&S->acc_empty[s], P_EPI_WARPS);
+      mbar_init(&S->acc_empty[s], NW);
       mbar_init(&S->y_full[s], 1);
       mbar_init(&S->c_full[s], 1);
-      mbar_init(&S->y_done[s], P_EPI_WARPS);
-      mbar_init(&S->c_free[s], P_EPI_WARPS);
-      mbar_init(&S->dl_ready[s], P_EPI_WARPS);
+      mbar_init(&S->y_done[s], NW);
+      mbar_init(&S->c_free[s], NW);
+      mbar_init(&S->dl_ready[s], NW);
       mbar_init(&S->dl_free[s], 1);
     }
     fence_mbar_init();
@@ -110,13 +117,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
   {
     int off = 0;
     for (int l = 0; l < L - 1; ++l) {
-      for (int i = threadIdx.x; i < a.net.Np[l]; i += P_THREADS) bias_h[off + i] = a.net.bias[l][i];
+      for (int i = threadIdx.x; i < a.net.Np[l]; i += NTHREADS) bias_h[off + i] = a.net.bias[l][i];
       off += a.net.Np[l];
     }
     if (!WIDE)
-      for (int i = threadIdx.x; i < a.last_bias_floats; i += P_THREADS) bias_l[i] = a.bias_last[i];
+      for (int i = threadIdx.x; i < a.last_bias_floats; i += NTHREADS) bias_l[i] = a.bias_last[i];
   }
-  if (warp == 18) tmem_alloc<512>(&S->tmem_base);
+  if (warp == W_MMA) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
   auto tile_of = [&](long long it, int s) { return 2 * (blockIdx.x + it * (long long)gridDim.x) + s; };
   auto rows_of = [&](long long tile) { return (int)min((long long)P_TM, a.B - tile * P_TM); };
 
-  if (warp == 16) {
+  if (warp == W_PROD) {
     // ------------------------------------------------------------------ weight producer (one thread)
     if (lane == 0) {
       uint32_t ph_e[P_STAGES] = {0, 0};
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       }
     }
     __syncwarp();
-  } else if (warp == 17) {
+  } else if (warp == W_IO) {
     // ------------------------------------------------------------------ tile I/O, narrow mode (one thread)
     if (!WIDE && lane == 0) {
       const uint32_t ystride = (uint32_t)(P_TM * a.D_t), cstride = (uint32_t)(P_TM * a.K0raw);
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
-  } else if (warp == 19) {
+  } else if (warp == W_RED) {
     // ------------------------------------------------------------------ log-det reducer: sums the four dim shares
     // of every row in a fixed order (deterministic) and adds the running dlogp; keeps that wait off the epilogue warps
     uint32_t ph_r[2] = {0, 0};
@@ -219,13 +226,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
           const long long row = tile * P_TM + r;
           if (row < a.B) {
             const float base_dl = a.dlogp_in ? a.dlogp_in[row] : 0.f;
-            a.dlogp_out[row] = base_dl + ((dl[r] + dl[P_TM + r]) + (dl[2 * P_TM + r] + dl[3 * P_TM + r]));
+            float sum = (dl[r] + dl[P_TM + r]) + (dl[2 * P_TM + r] + dl[3 * P_TM + r]);
+            if (EPW == 6) sum += dl[4 * P_TM + r] + dl[5 * P_TM + r];
+            a.dlogp_out[row] = base_dl + sum;
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->dl_free[s]);
       }
-  } else if (warp == 18) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
     const uint32_t idesc = idesc_bf16(128, 128);
     int stage = 0;
@@ -296,7 +305,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
         ph_c[s] ^= 1;
       }
       const float* crow = WIDE ? a.cond + row * (long long)a.K0raw : cbuf + (s * P_TM + r_in_tile) * a.K0raw;
-      pair_stage_x(a.net, a.plain_cond, crow, !WIDE || row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
+      if (j < 4) pair_stage_x(a.net, a.plain_cond, crow, !WIDE || row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&S->a_ready[s]);
@@ -329,6 +338,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
             // ---- hidden layer l: accumulator columns [32 j, 32 j + 32) -> bias, activation, exact bf16 split -> A
             const int l = u - (G - 1);
             wait_acc(s);
+            if (j >= 4) {            // (EPW = 6) the hidden layers' 128 columns go to four warps per quadrant
+              if (lane == 0) mbar_arrive(&S->a_ready[s]);
+              continue;
+            }
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
             tmem_ld_wait();
@@ -352,16 +365,17 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
             // roles {dims 0,1 packed | dims 2,3 packed | dim 4 | nothing}, rotating with c + s so the load evens out;
             // a pair of dims is evaluated in packed fp32 lanes (bgx_spline_reg2.cuh)
             const int c = u - (G + L - 2);
-            const int role = (j + c + s) & 3;
+            const int role = EPW == 4 ? ((j + c + s) & 3) : ((j + c + s) % 6);
             const long long row = tile_of(it, s) * P_TM + r_in_tile;
             const bool live = row < a.B;
             if (!WIDE && c == 0) {
               ok = ok && mbar_wait_sleep(&S->y_full[s], ph_y[s], a.status);
               ph_y[s] ^= 1;
             }
-            const int iA = role == 2 ? 4 : 2 * role;                 // first dim of this warp inside the pass
+            const int iA = EPW == 4 ? (role == 2 ? 4 : 2 * role) : role;   // first dim of this warp inside the pass
             const int dA = P_DPP * c + iA;
-            const bool hasA = role < 3 && dA < a.D_t, hasB = role < 2 && dA + 1 < a.D_t;
+            const bool hasA = (EPW == 4 ? role < 3 : role < 5) && dA < a.D_t;
+            const bool hasB = EPW == 4 && role < 2 && dA + 1 < a.D_t;
             float* yrow = WIDE ? a.tout + row * (long long)a.D_t : ybuf + (s * P_TM + r_in_tile) * a.D_t;
             // the transformed inputs do not depend on the accumulator: fetch them before waiting for it
             float xA = 0.f, xB = 0.f;
@@ -459,7 +473,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) spline_coupling_pair_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 18) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -558,22 +572,25 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
     if (rc) return rc;
   }
   using KernT = void (*)(const PArgs);
-#define BGX_P_ROW(INV, W) \
-  {spline_coupling_pair_kernel<INV, 0, W>, spline_coupling_pair_kernel<INV, 1, W>, \
-   spline_coupling_pair_kernel<INV, 2, W>, spline_coupling_pair_kernel<INV, 3, W>}
-  static const KernT kerns[2][2][4] = {{BGX_P_ROW(false, false), BGX_P_ROW(true, false)},
-                                       {BGX_P_ROW(false, true), BGX_P_ROW(true, true)}};
+#define BGX_P_ROW(INV, W, E) \
+  {spline_coupling_pair_kernel<INV, 0, W, E>, spline_coupling_pair_kernel<INV, 1, W, E>, \
+   spline_coupling_pair_kernel<INV, 2, W, E>, spline_coupling_pair_kernel<INV, 3, W, E>}
+  static const KernT kerns[2][2][2][4] = {
+      {{BGX_P_ROW(false, false, 4), BGX_P_ROW(true, false, 4)}, {BGX_P_ROW(false, true, 4), BGX_P_ROW(true, true, 4)}},
+      {{BGX_P_ROW(false, false, 6), BGX_P_ROW(true, false, 6)}, {BGX_P_ROW(false, true, 6), BGX_P_ROW(true, true, 6)}}};
 #undef BGX_P_ROW
+  // epilogue warps per quadrant: BGX_PAIR_EPW=4 (16 warps, packed pairs of dims) or 6 (24 warps, one dim per warp and pass)
+  static const int epw6 = [] { const char* e = getenv("BGX_PAIR_EPW"); return (e ? atoi(e) : P_EPW_DEFAULT) == 6 ? 1 : 0; }();
   const int inv = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
-  KernT kern = kerns[wide ? 1 : 0][inv][net->act];
-  static size_t configured[2][2][4] = {};
-  if (smem > configured[wide ? 1 : 0][inv][net->act]) {
+  KernT kern = kerns[epw6][wide ? 1 : 0][inv][net->act];
+  static size_t configured[2][2][2][4] = {};
+  if (smem > configured[epw6][wide ? 1 : 0][inv][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
-    configured[wide ? 1 : 0][inv][net->act] = smem;
+    configured[epw6][wide ? 1 : 0][inv][net->act] = smem;
   }
   const unsigned grid = (unsigned)std::min<long long>(a.npairs, (long long)sm_count);
-  kern<<<grid, P_THREADS, smem, st>>>(a);
+  kern<<<grid, (epw6 ? 28 : 20) * 32, smem, st>>>(a);
   return post_launch();
 }
 

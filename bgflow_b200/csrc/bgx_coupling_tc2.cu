@@ -593,7 +593,9 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
     const char* e = getenv("BGX_T2_FAST");
     const int fast = e ? (atoi(e) ? 1 : 0) : T2_FAST_DEFAULT;
     const char* pk = getenv("BGX_T2_PACKED");
-    const int packed = pk ? (atoi(pk) ? 1 : 0) : 1;
+    const int packed = pk ? (atoi(pk) ? 1 : 0) : 0;   // measured on the B200: 0.898 ms packed vs 0.859 ms scalar per launch here
+                                                      // (extra register moves + FFMA2 latency with only 8 warps per CTA); the
+                                                      // pair kernel, which releases its accumulators early, keeps the packed form
     return fast ? (packed ? 2 : 1) : 0;
   }();
   KernT kern = kerns[pair][a.inverse][net->act];

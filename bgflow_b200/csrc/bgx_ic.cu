@@ -20,12 +20,38 @@
 // Layout: the [tile x 3N] coordinate block of a CTA is contiguous in global memory; it is
 // staged through shared memory as P[c][t] (leading dim BT+1: conflict-free both for the
 // per-thread phase (fixed c, consecutive t) and for the coalesced copy phase).
+#include <cstdlib>
+#include <map>
+
 #include "bgx_ic.cuh"
 #include "bgx_cdf_math.cuh"
+#include "bgx_tc.cuh"
 
 namespace bgx {
 
 enum { IC_GLOBAL = 0, IC_RELATIVE = 1 };
+// Tile I/O of the kernels.  IO_GLOBAL: every thread works on its row in global memory (molecules whose tile does not
+// fit shared memory).  IO_STAGED: element-wise staging through a transposed shared-memory tile (any batch, any
+// alignment; the tail rows of a batch).  IO_BULK: whole row-major tiles move with ONE bulk-TMA copy per tensor
+// (cp.async.bulk, SASS UBLKCP) and the per-thread phase reads / writes its row of the tile in place — the staging
+// walks were 60 % of the instructions and two thirds of the time of these kernels (ncu source page, profiles/).
+enum { IO_GLOBAL = 0, IO_STAGED = 1, IO_BULK = 2 };
+
+using tc::bulk_g2s;
+using tc::fence_async_smem;
+using tc::fence_mbar_init;
+using tc::mbar_expect_tx;
+using tc::mbar_init;
+using tc::mbar_wait;
+
+__device__ __forceinline__ void ic_bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(tc::smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void ic_bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 
 struct IcArgs {
   long long B;
@@ -60,9 +86,11 @@ struct IcArgs {
 };
 
 // ---------------------------------------------------------------- IC -> Cartesian
-template <bool SMEM>
+template <int MODE>
 __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
-  extern __shared__ float sm[];
+  constexpr bool SMEM = MODE == IO_STAGED, BULK = MODE == IO_BULK;
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bulk_bar;
   const int t = threadIdx.x;
   const long long row0 = (long long)blockIdx.x * BT;
   const long long row = row0 + t;
@@ -107,14 +135,36 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
                       [&](int m, int c, float v) { sm[(3 * N + c) * LDT + m] = v; });
     }
     __syncthreads();
+  } else if (BULK) {
+    // row-major tiles [BT x width]: bonds | angles | torsions (| fixed block) | output coordinates
+    float* raw_b = sm;
+    float* raw_a = raw_b + BT * nb;
+    float* raw_t = raw_a + BT * na;
+    float* raw_f = raw_t + BT * nt;
+    float* out = raw_f + (global ? 0 : BT * a.fixed_w);
+    if (t == 0) {
+      mbar_init(&bulk_bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(&bulk_bar, (uint32_t)(BT * 4 * (nb + na + nt + (global ? 0 : a.fixed_w))));
+      bulk_g2s(raw_b, a.bonds + row0 * nb, (uint32_t)(BT * nb * 4), &bulk_bar);
+      bulk_g2s(raw_a, a.angles + row0 * na, (uint32_t)(BT * na * 4), &bulk_bar);
+      bulk_g2s(raw_t, a.torsions + row0 * nt, (uint32_t)(BT * nt * 4), &bulk_bar);
+      if (!global) bulk_g2s(raw_f, a.fixed_in + row0 * a.fixed_w, (uint32_t)(BT * a.fixed_w * 4), &bulk_bar);
+    }
+    mbar_wait(&bulk_bar, 0, nullptr);
+    pos.base = out + t * (3 * N); pos.stride_c = 1;
   } else {
     pos.base = a.xyz + row * (long long)(3 * N); pos.stride_c = 1;
   }
 
   if (live) {
-    const float* bo = a.bonds + row * nb;
-    const float* an = a.angles + row * na;
-    const float* to = a.torsions + row * nt;
+    const float* bo = BULK ? sm + t * nb : a.bonds + row * nb;
+    const float* an = BULK ? sm + BT * nb + t * na : a.angles + row * na;
+    const float* to = BULK ? sm + BT * (nb + na) + t * nt : a.torsions + row * nt;
+    const float* fx = BULK ? sm + BT * (nb + na + nt) + t * a.fixed_w : a.fixed_in + row * (long long)a.fixed_w;
     float dl = 0.f;
     if (global) {
     const float* x0p = a.x0 + row * a.x0_stride;
@@ -167,7 +217,7 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
       const int nf3 = 3 * a.n_fixed;
       if (a.keep > 0) {
         // x_fixed = z_fixed . Tblacken + mean   (pca.py:93-99), log-det -jacobian_xz
-        const float* zf = a.fixed_in + row * a.keep;
+        const float* zf = fx;
         for (int i = 0; i < a.n_fixed; ++i) {
           float acc[3];
 #pragma unroll
@@ -182,7 +232,7 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
         }
         dl -= a.ld_whiten;
       } else if (!SMEM) {
-        const float* xf = a.fixed_in + row * nf3;
+        const float* xf = fx;
         for (int i = 0; i < a.n_fixed; ++i) pos.set(a.fixed[i], {xf[3 * i], xf[3 * i + 1], xf[3 * i + 2]});
       }
     }
@@ -230,6 +280,15 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
     float* g = a.xyz + row0 * W;
     walk_block(t, W, nrow, [&](int m, int c) { g[m * W + c] = sm[c * LDT + m]; });
   }
+  if (BULK) {
+    fence_async_smem();          // the tile was written through the generic proxy, the bulk store reads it through the async one
+    __syncthreads();
+    if (t == 0) {
+      const int W = 3 * N;
+      ic_bulk_s2g(a.xyz + row0 * W, sm + BT * (nb + na + nt + (global ? 0 : a.fixed_w)), (uint32_t)(BT * W * 4));
+      ic_bulk_commit_wait_read();      // shared memory must outlive the copy's reads
+    }
+  }
 }
 
 // ---------------------------------------------------------------- Cartesian -> IC
@@ -239,16 +298,18 @@ __global__ void __launch_bounds__(BT) ic_to_xyz_kernel(const IcArgs a) {
 constexpr int FS = 32;        // samples per CTA (from_xyz)
 constexpr int LDF = FS + 1;
 
-template <bool SMEM>
+template <int MODE>
 __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
-  extern __shared__ float sm[];
+  constexpr bool SMEM = MODE == IO_STAGED, BULK = MODE == IO_BULK, QUAD = MODE != IO_GLOBAL;
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bulk_bar;
   const int t = threadIdx.x;
   const int N = a.n_atoms, nb = a.nb, na = a.na, nt = a.nt;
   const int W = 3 * N;
   const bool global = a.kind == IC_GLOBAL;
-  const int spb = SMEM ? FS : BT;                    // samples per CTA
+  const int spb = QUAD ? FS : BT;                    // samples per CTA
   const long long row0 = (long long)blockIdx.x * spb;
-  const int s_loc = SMEM ? (t >> 2) : t, g = SMEM ? (t & 3) : 0, ng = SMEM ? 4 : 1;
+  const int s_loc = QUAD ? (t >> 2) : t, g = QUAD ? (t & 3) : 0, ng = QUAD ? 4 : 1;
   const long long row = row0 + s_loc;
   const bool live = row < a.B;
   const int nrow = (int)min((long long)spb, a.B - row0);
@@ -261,15 +322,30 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
     __syncthreads();
     pos.base = sm + s_loc;
     pos.stride_c = LDF;
+  } else if (BULK) {
+    // row-major tiles [FS x width]: coordinates in | bonds | angles | torsions (| fixed block) out
+    if (t == 0) {
+      mbar_init(&bulk_bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(&bulk_bar, (uint32_t)(FS * W * 4));
+      bulk_g2s(sm, a.xyz_in + row0 * W, (uint32_t)(FS * W * 4), &bulk_bar);
+    }
+    mbar_wait(&bulk_bar, 0, nullptr);
+    pos.base = sm + s_loc * W;
+    pos.stride_c = 1;
   } else {
     pos.base = const_cast<float*>(a.xyz_in) + row * (long long)(3 * N);
     pos.stride_c = 1;
   }
   float dl = 0.f;
+  float* const qb = sm + FS * W;          // (BULK) output tiles
   if (live) {
-    float* bo = a.o_bonds + row * nb;
-    float* an = a.o_angles + row * na;
-    float* to = a.o_torsions + row * nt;
+    float* bo = BULK ? qb + s_loc * nb : a.o_bonds + row * nb;
+    float* an = BULK ? qb + FS * nb + s_loc * na : a.o_angles + row * na;
+    float* to = BULK ? qb + FS * (nb + na) + s_loc * nt : a.o_torsions + row * nt;
     for (int r = g; r < a.n_rel; r += ng) {
       const int4 z = *reinterpret_cast<const int4*>(a.rel + 4 * r);
       const V3 xi = pos.get(z.x), xj = pos.get(z.y), xk = pos.get(z.z), xl = pos.get(z.w);
@@ -309,7 +385,7 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
     if (!global) {
       // fixed block (ic.py:419) and, for the mixed transform, its whitening (pca.py:83-91): the
       // threads of a sample share the atoms / the whitened components
-      float* fo = a.fixed_out + row * a.fixed_w;
+      float* fo = BULK ? qb + FS * (nb + na + nt) + s_loc * a.fixed_w : a.fixed_out + row * a.fixed_w;
       float* Qf = Qs + (nb + na + nt) * LDF;
       if (a.keep == 0) {
         for (int i = g; i < a.n_fixed; i += ng) {
@@ -381,7 +457,7 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
       a.o_R[row * 3 + 2] = gamma;
     }
   }
-  if (SMEM) {   // the four threads of a sample are adjacent lanes
+  if (QUAD) {   // the four threads of a sample are adjacent lanes
     dl += __shfl_xor_sync(0xffffffffu, dl, 1);
     dl += __shfl_xor_sync(0xffffffffu, dl, 2);
   }
@@ -399,6 +475,17 @@ __global__ void __launch_bounds__(BT) ic_from_xyz_kernel(const IcArgs a) {
       const int wf = a.fixed_w;
       float* gf = a.fixed_out + row0 * wf;
       walk_block_f(t, wf, nrow, [&](int m, int c) { gf[m * wf + c] = Qb[(nb + na + nt + c) * LDF + m]; });
+    }
+  }
+  if (BULK) {
+    fence_async_smem();
+    __syncthreads();
+    if (t == 0) {
+      ic_bulk_s2g(a.o_bonds + row0 * nb, qb, (uint32_t)(FS * nb * 4));
+      ic_bulk_s2g(a.o_angles + row0 * na, qb + FS * nb, (uint32_t)(FS * na * 4));
+      ic_bulk_s2g(a.o_torsions + row0 * nt, qb + FS * (nb + na), (uint32_t)(FS * nt * 4));
+      if (!global) ic_bulk_s2g(a.fixed_out + row0 * a.fixed_w, qb + FS * (nb + na + nt), (uint32_t)(FS * a.fixed_w * 4));
+      ic_bulk_commit_wait_read();
     }
   }
 }
@@ -452,24 +539,89 @@ static int fill_relplan(const bgx_relplan* plan, long long batch, IcArgs& a) {
   return BGX_OK;
 }
 
-template <typename KS, typename KG>
-static int launch_ic(KS ksm, KG kgl, const IcArgs& a, int extra_cols, int samples_per_cta, cudaStream_t st) {
+static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// raise a kernel's dynamic shared-memory limit once per (kernel, size) instead of on every launch
+template <typename K>
+static int ensure_smem(K kern, size_t bytes) {
+  static std::map<const void*, size_t> seen;
+  if (bytes <= 48 * 1024) return BGX_OK;
+  size_t& cur = seen[(const void*)kern];
+  if (bytes <= cur) return BGX_OK;
+  int rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (!rc) cur = bytes;
+  return rc;
+}
+
+// advance every per-sample pointer of `a` by `rows` samples (the tail launch after the bulk-tile launch)
+static IcArgs skip_rows(const IcArgs& a, long long rows, bool to_xyz) {
+  IcArgs r = a;
+  r.B = a.B - rows;
+  const long long W = 3LL * a.n_atoms;
+  if (to_xyz) {
+    r.bonds += rows * a.nb; r.angles += rows * a.na; r.torsions += rows * a.nt;
+    if (r.x0) r.x0 += rows * a.x0_stride;
+    if (r.R) r.R += rows * a.r_stride;
+    if (r.fixed_in) r.fixed_in += rows * a.fixed_w;
+    r.xyz += rows * W;
+  } else {
+    r.xyz_in += rows * W;
+    r.o_bonds += rows * a.nb; r.o_angles += rows * a.na; r.o_torsions += rows * a.nt;
+    if (r.o_x0) r.o_x0 += rows * 3;
+    if (r.o_R) r.o_R += rows * 3;
+    if (r.fixed_out) r.fixed_out += rows * a.fixed_w;
+  }
+  if (r.dlogp_in) r.dlogp_in += rows;
+  r.dlogp_out += rows;
+  return r;
+}
+
+static int ic_io_mode() {   // BGX_IC_BULK=0: element-wise staging everywhere (A/B switch)
+  static const int m = [] { const char* e = getenv("BGX_IC_BULK"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
+// kb / ksm / kgl: the kernel with bulk-TMA tiles, with element-wise staging, on global memory
+template <typename K>
+static int launch_ic(K kb, K ksm, K kgl, const IcArgs& a, int extra_cols, int samples_per_cta, bool to_xyz,
+                     cudaStream_t st) {
   if (a.B == 0) return BGX_OK;
   long long grid = (a.B + BT - 1) / BT;
   if (grid > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
   size_t sb = sizeof(float) * (size_t)(3 * a.n_atoms + extra_cols) * (samples_per_cta + 1);
   if (a.kind == IC_GLOBAL && !a.slot_of_col) sb = (size_t)1 << 30;   // plans without a slot map: global-memory path
-  if (sb <= 200 * 1024) {
-    if (sb > 48 * 1024) {  // (both kernels share this instantiation: no static cache here)
-      int rc = check(cudaFuncSetAttribute(ksm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-      if (rc) return rc;
-    }
-    const long long grid_s = (a.B + samples_per_cta - 1) / samples_per_cta;
-    if (grid_s > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
-    ksm<<<(unsigned)grid_s, BT, sb, st>>>(a);
-  } else {
+  if (sb > 200 * 1024) {
     kgl<<<(unsigned)grid, BT, 0, st>>>(a);
+    return post_launch();
   }
+  // ---- full tiles through bulk-TMA copies (row-major tiles: inputs + outputs of a tile, no padding)
+  const int io_w = a.nb + a.na + a.nt + (a.kind == IC_GLOBAL ? 0 : a.fixed_w) + 3 * a.n_atoms;
+  const size_t sb_bulk = sizeof(float) * (size_t)io_w * samples_per_cta;
+  const bool aligned = to_xyz ? (al16(a.bonds) && al16(a.angles) && al16(a.torsions) && al16(a.xyz) &&
+                                 (a.kind == IC_GLOBAL || al16(a.fixed_in)))
+                              : (al16(a.xyz_in) && al16(a.o_bonds) && al16(a.o_angles) && al16(a.o_torsions) &&
+                                 (a.kind == IC_GLOBAL || al16(a.fixed_out)));
+  long long done = 0;
+  if (ic_io_mode() && aligned && sb_bulk <= 200 * 1024 && a.B >= samples_per_cta) {
+    const long long tiles = a.B / samples_per_cta;
+    if (tiles > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
+    int rc = ensure_smem(kb, sb_bulk);
+    if (rc) return rc;
+    IcArgs full = a;
+    full.B = tiles * samples_per_cta;
+    kb<<<(unsigned)tiles, BT, sb_bulk, st>>>(full);
+    rc = post_launch();
+    if (rc) return rc;
+    done = full.B;
+    if (done == a.B) return BGX_OK;
+  }
+  // ---- the remaining rows (or everything) through the element-wise staged kernel
+  const IcArgs rest = done ? skip_rows(a, done, to_xyz) : a;
+  int rc = ensure_smem(ksm, sb);
+  if (rc) return rc;
+  const long long grid_s = (rest.B + samples_per_cta - 1) / samples_per_cta;
+  if (grid_s > 0x7fffffffLL) return BGX_ERR_UNSUPPORTED;
+  ksm<<<(unsigned)grid_s, BT, sb, st>>>(rest);
   return post_launch();
 }
 
@@ -488,7 +640,8 @@ extern "C" int bgx_ic_to_xyz(const bgx_zplan* plan, int64_t batch, const float* 
   a.bonds = bonds; a.angles = angles; a.torsions = torsions;
   a.x0 = x0; a.R = R; a.x0_stride = x0_stride; a.r_stride = r_stride;
   a.xyz = xyz; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, 0, BT, (cudaStream_t)stream);
+  return launch_ic(ic_to_xyz_kernel<IO_BULK>, ic_to_xyz_kernel<IO_STAGED>, ic_to_xyz_kernel<IO_GLOBAL>, a, 0, BT, true,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int bgx_ic_to_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* marginals, float clamp_lo,
@@ -505,7 +658,8 @@ extern "C" int bgx_ic_to_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* ma
   a.bonds = bonds; a.angles = angles; a.torsions = torsions;
   a.x0 = x0; a.R = R; a.x0_stride = x0_stride; a.r_stride = r_stride;
   a.xyz = xyz; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, 0, BT, (cudaStream_t)stream);
+  return launch_ic(ic_to_xyz_kernel<IO_BULK>, ic_to_xyz_kernel<IO_STAGED>, ic_to_xyz_kernel<IO_GLOBAL>, a, 0, BT, true,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int bgx_relic_to_xyz(const bgx_relplan* plan, int64_t batch, const float* bonds, const float* angles,
@@ -517,7 +671,8 @@ extern "C" int bgx_relic_to_xyz(const bgx_relplan* plan, int64_t batch, const fl
   if (!bonds || !angles || !torsions || !fixed || !xyz || !dlogp_out) return BGX_ERR_INVALID;
   a.bonds = bonds; a.angles = angles; a.torsions = torsions; a.fixed_in = fixed;
   a.xyz = xyz; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_to_xyz_kernel<true>, ic_to_xyz_kernel<false>, a, a.keep, BT, (cudaStream_t)stream);
+  return launch_ic(ic_to_xyz_kernel<IO_BULK>, ic_to_xyz_kernel<IO_STAGED>, ic_to_xyz_kernel<IO_GLOBAL>, a, a.keep, BT, true,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float* xyz, float* bonds,
@@ -529,7 +684,8 @@ extern "C" int bgx_ic_from_xyz(const bgx_zplan* plan, int64_t batch, const float
   if (!xyz || !bonds || !angles || !torsions || !x0 || !R || !dlogp_out) return BGX_ERR_INVALID;
   a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions;
   a.o_x0 = x0; a.o_R = R; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_atoms - 6, FS, (cudaStream_t)stream);
+  return launch_ic(ic_from_xyz_kernel<IO_BULK>, ic_from_xyz_kernel<IO_STAGED>, ic_from_xyz_kernel<IO_GLOBAL>, a,
+                   3 * a.n_atoms - 6, FS, false, (cudaStream_t)stream);
 }
 
 extern "C" int bgx_ic_from_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* marginals, float clamp_lo,
@@ -544,7 +700,8 @@ extern "C" int bgx_ic_from_xyz_mapped(const bgx_zplan* plan, const bgx_cdf_col* 
   a.clamp = {clamp_lo, clamp_hi, logdet_min};
   a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions;
   a.o_x0 = x0; a.o_R = R; a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_atoms - 6, FS, (cudaStream_t)stream);
+  return launch_ic(ic_from_xyz_kernel<IO_BULK>, ic_from_xyz_kernel<IO_STAGED>, ic_from_xyz_kernel<IO_GLOBAL>, a,
+                   3 * a.n_atoms - 6, FS, false, (cudaStream_t)stream);
 }
 
 extern "C" int bgx_relic_from_xyz(const bgx_relplan* plan, int64_t batch, const float* xyz, float* bonds,
@@ -556,6 +713,6 @@ extern "C" int bgx_relic_from_xyz(const bgx_relplan* plan, int64_t batch, const 
   if (!xyz || !bonds || !angles || !torsions || !fixed || !dlogp_out) return BGX_ERR_INVALID;
   a.xyz_in = xyz; a.o_bonds = bonds; a.o_angles = angles; a.o_torsions = torsions; a.fixed_out = fixed;
   a.dlogp_in = dlogp_in; a.dlogp_out = dlogp_out;
-  return launch_ic(ic_from_xyz_kernel<true>, ic_from_xyz_kernel<false>, a, 3 * a.n_rel + a.fixed_w, FS,
-                   (cudaStream_t)stream);
+  return launch_ic(ic_from_xyz_kernel<IO_BULK>, ic_from_xyz_kernel<IO_STAGED>, ic_from_xyz_kernel<IO_GLOBAL>, a,
+                   3 * a.n_rel + a.fixed_w, FS, false, (cudaStream_t)stream);
 }
