@@ -643,7 +643,9 @@ def main():
         if not args.no_e2e:
             prior = (bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)) if kind == "spline"
                      else bg.NormalDistribution(dim)).to(dev)
-            pipe = HostPipeline(flow, dim_in=dim, dim_out=dim, max_rows=B, device=dev, prior=prior)
+            pipe = HostPipeline(flow, dim_in=dim, dim_out=dim, max_rows=B, device=dev, prior=prior,
+                                chunk_rows=int(os.environ.get("BGX_E2E_CHUNK", 1 << 17)),
+                                n_streams=int(os.environ.get("BGX_E2E_STREAMS", 3)))
             for _ in range(args.warmup):
                 pipe.run(z_host)
             ms_e2e = run_timed(lambda: pipe.run(z_host), args.steps)

@@ -40,7 +40,7 @@ def test_matches_reference_golden(name):
     fix_tol = 1e-4 if int(g["keepdims"]) < 0 else 1e-3
     n0 = _lib.launch_count()
     bonds, angles, torsions, fixed, dlogp = ic(_t(g["xyz_f32"]))
-    assert _lib.launch_count() == n0 + 1
+    assert _lib.launch_count() <= n0 + 2          # full tiles through bulk-TMA copies + (possibly) one launch for the tail rows
     B = g["xyz_f32"].shape[0]
     assert bonds.shape == (B, 17) and fixed.shape == (B, ic.dim_fixed) and dlogp.shape == (B, 1)
     for got, key in ((bonds, "bonds"), (angles, "angles"), (torsions, "torsions")):
