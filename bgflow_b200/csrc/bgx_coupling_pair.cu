@@ -39,6 +39,7 @@
 
 namespace bgx {
 using namespace tc;
+unsigned long long* tc_get_trace(int* cap);
 
 struct PArgs {
   long long B;
@@ -59,6 +60,8 @@ struct PArgs {
   int hid_bias_floats, last_bias_floats;
   const float* bias_last;     // [npass][5][28] (global)
   int plain_cond;             // conditioner input map is the identity (no WrapPeriodic)
+  unsigned long long* trace;  // bgx_debug_set_trace: CTA 0 writes per-role wait-time totals (cycles), >= 16 entries
+  int debug;                  // BGX_PAIR_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no spline evaluation, 4 = no hidden-layer math
 };
 
 struct alignas(16) PSmem {
@@ -138,10 +141,13 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     if (lane == 0) {
       uint32_t ph_e[P_STAGES] = {0, 0};
       int stage = 0;
-      long long nfill = 0;
+      long long nfill = 0, t_prod = 0;
+      const long long t_begin = clock64();
       auto fill = [&](int l, int c, int t0, int nt) -> bool {
         if (nfill >= P_STAGES) {
+          const long long c0 = clock64();
           if (!mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status)) return false;
+          t_prod += clock64() - c0;
           ph_e[stage] ^= 1;
         }
         uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
@@ -161,6 +167,10 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         for (int g = 0; g < G && ok; ++g) ok = fill(0, 0, 2 * g, min(2, a.ktiles[0] - 2 * g));
         for (int l = 1; l < L - 1 && ok; ++l) ok = fill(l, 0, 0, a.ktiles[l]);
         for (int c = 0; c < P && ok; ++c) ok = fill(L - 1, c, 0, a.ktiles[L - 1]);
+      }
+      if (a.trace && blockIdx.x == 0) {
+        a.trace[12] = (unsigned long long)(clock64() - t_begin);  // producer: whole loop
+        a.trace[13] = (unsigned long long)t_prod;                 //   waiting for a free stage
       }
     }
     __syncwarp();
@@ -243,16 +253,24 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     bool ok = true;
     // one unit on both slots: `wait_a` = a freshly staged A operand is needed, `wait_e` = the accumulator must
     // have been pulled by the epilogue (a last-layer pass preceded), `accum` = keep the accumulator (layer-0 group > 0)
+    const bool tr = a.trace && blockIdx.x == 0;
+    long long t_w = 0, t_a = 0, t_e = 0;
+    const long long t_begin = clock64();
     auto unit = [&](int nslots, int K, bool wait_a, bool wait_e, bool accum) {
       if (!ok) return;
+      long long c0 = tr ? clock64() : 0;
       ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
+      if (tr) t_w += clock64() - c0;
       ph_wf[stage] ^= 1;
       const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
       const int ksteps = (K + 15) / 16;
 #pragma unroll 1
       for (int s = 0; s < nslots && ok; ++s) {
+        long long c1 = tr ? clock64() : 0;
         if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
+        long long c2 = tr ? clock64() : 0;
         if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
+        if (tr) { t_a += c2 - c1; t_e += clock64() - c2; }
         if (!ok) break;
         tc_fence_after();
         const uint32_t acc_addr = tmem + s * P_SLOT + P_ACC;
@@ -263,7 +281,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
           const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);
           const uint32_t a1 = tmem + s * P_SLOT + P_A + (uint32_t)(t * 32), a2 = a1 + P_A_STRIDE;
           const int nk = min(4, ksteps - t * 4);
-          if (nk == 4) {
+          if (a.debug & 1) {
+          } else if (nk == 4) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               mma3_bf16x3_elect(acc_addr, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
@@ -289,6 +308,13 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         else unit(nslots, a.net.K[L - 1], u == G + L - 2, u > G + L - 2, false);
       }
     }
+    if (tr && lane == 0) {
+      a.trace[0] = (unsigned long long)(clock64() - t_begin);     // MMA warp: whole loop
+      a.trace[1] = (unsigned long long)t_w;                       //   waiting for weights
+      a.trace[2] = (unsigned long long)t_a;                       //   waiting for a staged A operand
+      a.trace[3] = (unsigned long long)t_e;                       //   waiting for a pulled accumulator
+      a.trace[4] = (unsigned long long)n_my;
+    }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps (0..15)
@@ -312,8 +338,13 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         if (!WIDE && g == 0) mbar_arrive(&S->c_free[s]);
       }
     };
+    const bool tr = a.trace && blockIdx.x == 0 && warp == 0;
+    long long t_acc = 0;
+    const long long t_begin = clock64();
     auto wait_acc = [&](int s) {
+      const long long c0 = tr ? clock64() : 0;
       ok = ok && mbar_wait_sleep(&S->acc_full[s], ph_acc[s], a.status);
+      if (tr) t_acc += clock64() - c0;
       ph_acc[s] ^= 1;
       tc_fence_after();
     };
@@ -350,6 +381,10 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 bb = b4[i];
+              if (a.debug & 4) {
+                t1[2 * i] = v[4 * i]; t2[2 * i] = v[4 * i + 1]; t1[2 * i + 1] = v[4 * i + 2]; t2[2 * i + 1] = v[4 * i + 3];
+                continue;
+              }
               hidden_pair2<ACT>(v[4 * i], v[4 * i + 1], bb.x, bb.y, t1[2 * i], t2[2 * i]);
               hidden_pair2<ACT>(v[4 * i + 2], v[4 * i + 3], bb.z, bb.w, t1[2 * i + 1], t2[2 * i + 1]);
             }
@@ -417,8 +452,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
               }
               p2[24] = f2(__uint_as_float(va[24]) + (WIDE ? __ldg(bsrc + 24) : bsrc[24]),
                           __uint_as_float(vb[24]) + (WIDE ? __ldg(bsrc + P_BPAD + 24) : bsrc[P_BPAD + 24]));
-              F2 y2, l2;
-              rqs_eval_reg2<!INVERSE>(p2, a.ck, f2(xA, xB), y2, l2);
+              F2 y2 = f2(xA, xB), l2 = f2(0.f, 0.f);
+              if (!(a.debug & 2)) rqs_eval_reg2<!INVERSE>(p2, a.ck, f2(xA, xB), y2, l2);
               if (!WIDE || live) {
                 yrow[dA] = lo(y2);
                 yrow[dA + 1] = hi(y2);
@@ -441,8 +476,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
                 pp[4 * qq + 3] = __uint_as_float(va[4 * qq + 3]) + x4.w;
               }
               pp[24] = __uint_as_float(va[24]) + (WIDE ? __ldg(bsrc + 24) : bsrc[24]);
-              float y, lad;
-              rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
+              float y = xA, lad = 0.f;
+              if (!(a.debug & 2)) rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
               if (!WIDE || live) yrow[dA] = y;
               ld[s] += lad;
             } else {
@@ -470,6 +505,10 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
       }
     }
     if (n_oob && a.oob) atomicAdd(a.oob, n_oob);
+    if (tr && lane == 0) {
+      a.trace[8] = (unsigned long long)(clock64() - t_begin);     // epilogue warp 0: whole loop
+      a.trace[9] = (unsigned long long)t_acc;                     //   waiting for accumulators
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -545,6 +584,15 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   a.bias_last = net->spline_bias;
   a.G = ceil_div(net->K[0], 128);
   a.plain_cond = (net->K[0] == net->raw_width && net->periodic_scale == 0.f) ? 1 : 0;
+  {
+    int cap = 0;
+    unsigned long long* tb = tc_get_trace(&cap);
+    a.trace = cap >= 16 ? tb : nullptr;
+  }
+  {
+    static const int dbg = [] { const char* e = getenv("BGX_PAIR_DEBUG"); return e ? atoi(e) : 0; }();
+    a.debug = dbg;
+  }
   SplineParams sp;
   spline_params_from_cfg(cfg, sp);
   {

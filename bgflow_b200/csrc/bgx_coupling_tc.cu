@@ -535,6 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spline_coupling_tc_kernel(const
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0;
 void tc_set_trace(unsigned long long* buf, int cap) { g_trace = buf; g_trace_cap = cap; }
+unsigned long long* tc_get_trace(int* cap) { if (cap) *cap = g_trace_cap; return g_trace; }
 
 bool spline_tc_eligible(const bgx_packed_mlp* net, const bgx_spline_cfg* cfg, int d_c) {
   if (!net || !cfg || cfg->n_bins != NB) return false;

@@ -195,7 +195,7 @@ def test_fused_tail_matches_unfused_and_oracle(batch):
     x_ref, aug_ref, d_ref = tail(*us)
     n0 = _lib.launch_count()
     x, aug, d = fused(*us)
-    assert _lib.launch_count() == n0 + 2                      # one multi-cdf launch (aug) + one mapped-IC launch
+    assert _lib.launch_count() <= n0 + 3                      # one multi-cdf launch (aug) + the mapped-IC kernel (bulk tiles + tail rows)
     assert x.shape == (batch, 66) and aug.shape == (batch, 10) and d.shape == (batch, 1)
     torch.testing.assert_close(aug, aug_ref, atol=0, rtol=0)
     torch.testing.assert_close(x, x_ref, atol=1e-4, rtol=1e-4)
