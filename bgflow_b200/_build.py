@@ -16,10 +16,12 @@ OBJ = os.path.join(CSRC, "_obj")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libbgflow_b200.so")
 
+# BGX_PAIR_INSTRUMENT=1 in the environment compiles the pair kernel's timing experiments / wait accounting in
+# (tools/trace_pair.py); the shipped library is built without them
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + (["-DBGX_PAIR_INSTRUMENT=1"] if os.environ.get("BGX_PAIR_INSTRUMENT") == "1" else [])
 
 
 def _nvcc():

@@ -41,6 +41,13 @@ namespace bgx {
 using namespace tc;
 unsigned long long* tc_get_trace(int* cap);
 
+// Timing experiments (BGX_PAIR_DEBUG) and per-role wait accounting (bgx_debug_set_trace) are compiled in only with
+// -DBGX_PAIR_INSTRUMENT=1: the extra predicates and clock reads cost 10 % of the kernel's time (measured).
+#ifndef BGX_PAIR_INSTRUMENT
+#define BGX_PAIR_INSTRUMENT 0
+#endif
+constexpr bool P_INSTR = BGX_PAIR_INSTRUMENT != 0;
+
 struct PArgs {
   long long B;
   const float* cond;    // [B][K0raw] dense
@@ -60,6 +67,7 @@ struct PArgs {
   int hid_bias_floats, last_bias_floats;
   const float* bias_last;     // [npass][5][28] (global)
   int plain_cond;             // conditioner input map is the identity (no WrapPeriodic)
+  int cs;                     // CTAs per cluster (1, 2 or 4): every weight stage is fetched once per cluster (TMA multicast)
   unsigned long long* trace;  // bgx_debug_set_trace: CTA 0 writes per-role wait-time totals (cycles), >= 16 entries
   int debug;                  // BGX_PAIR_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no spline evaluation, 4 = no hidden-layer math
 };
@@ -97,12 +105,19 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.net.n_layers;
   const int G = a.G, P = a.npass;
-  const long long n_my = (a.npairs > blockIdx.x) ? (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // Work distribution: cluster `cid` takes `cs` consecutive tile pairs per iteration, one per CTA; every CTA of a cluster
+  // runs the same number of iterations (a CTA whose pair does not exist still takes part in the weight traffic)
+  const int cs = a.cs;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0;
+  const long long ncl = gridDim.x / cs, cid = blockIdx.x / cs;
+  const long long per_it = ncl * cs;
+  const long long n_my = (a.npairs + per_it - 1) / per_it;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P_STAGES; ++i) {
       mbar_init(&S->w_full[i], 1);
-      mbar_init(&S->w_empty[i], 1);
+      mbar_init(&S->w_empty[i], (uint32_t)cs);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&S->a_ready[s], NW);
@@ -128,12 +143,14 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
   }
   if (warp == W_MMA) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
-  __syncthreads();
+  if (cs > 1) cluster_sync_all();     // every CTA's barriers exist before a peer arrives on them / multicasts into them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S->tmem_base;
 
   // tile of slot s in CTA-local iteration `it`; a slot is active iff its tile exists
-  auto tile_of = [&](long long it, int s) { return 2 * (blockIdx.x + it * (long long)gridDim.x) + s; };
+  auto tile_of = [&](long long it, int s) { return 2 * ((cid + it * ncl) * cs + crank) + s; };
+  auto slots_of = [&](long long it) { return tile_of(it, 0) >= a.ntiles ? 0 : (tile_of(it, 1) < a.ntiles ? 2 : 1); };
   auto rows_of = [&](long long tile) { return (int)min((long long)P_TM, a.B - tile * P_TM); };
 
   if (warp == W_PROD) {
@@ -142,12 +159,12 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
       uint32_t ph_e[P_STAGES] = {0, 0};
       int stage = 0;
       long long nfill = 0, t_prod = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = P_INSTR ? clock64() : 0;
       auto fill = [&](int l, int c, int t0, int nt) -> bool {
         if (nfill >= P_STAGES) {
-          const long long c0 = clock64();
+          const long long c0 = P_INSTR ? clock64() : 0;
           if (!mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status)) return false;
-          t_prod += clock64() - c0;
+          if (P_INSTR) t_prod += clock64() - c0;
           ph_e[stage] ^= 1;
         }
         uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
@@ -155,8 +172,12 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         const int kt = a.ktiles[l];
         for (int t = 0; t < nt; ++t) {
           const long long src = ((long long)c * kt + t0 + t) * 8192;
-          bulk_g2s(dst + (size_t)t * P_KT_BYTES, a.wb[0][l] + src, P_TILE_BYTES, &S->w_full[stage]);
-          bulk_g2s(dst + (size_t)t * P_KT_BYTES + P_TILE_BYTES, a.wb[1][l] + src, P_TILE_BYTES, &S->w_full[stage]);
+          for (int term = 0; term < 2; ++term) {
+            uint8_t* d = dst + (size_t)t * P_KT_BYTES + (size_t)term * P_TILE_BYTES;
+            if (cs == 1) bulk_g2s(d, a.wb[term][l] + src, P_TILE_BYTES, &S->w_full[stage]);
+            else if ((uint32_t)((2 * t + term) % cs) == crank)     // this CTA's share, delivered to the whole cluster
+              bulk_g2s_multicast(d, a.wb[term][l] + src, P_TILE_BYTES, &S->w_full[stage], cmask);
+          }
         }
         ++nfill;
         stage ^= 1;
@@ -168,7 +189,13 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         for (int l = 1; l < L - 1 && ok; ++l) ok = fill(l, 0, 0, a.ktiles[l]);
         for (int c = 0; c < P && ok; ++c) ok = fill(L - 1, c, 0, a.ktiles[L - 1]);
       }
-      if (a.trace && blockIdx.x == 0) {
+      // drain: the last stages' release arrivals (from every CTA of the cluster) have landed before this CTA may leave
+      for (int k = 0; k < P_STAGES && k < nfill && ok; ++k) {
+        ok = mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status);
+        ph_e[stage] ^= 1;
+        stage ^= 1;
+      }
+      if (P_INSTR && a.trace && blockIdx.x == 0) {
         a.trace[12] = (unsigned long long)(clock64() - t_begin);  // producer: whole loop
         a.trace[13] = (unsigned long long)t_prod;                 //   waiting for a free stage
       }
@@ -253,9 +280,9 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     bool ok = true;
     // one unit on both slots: `wait_a` = a freshly staged A operand is needed, `wait_e` = the accumulator must
     // have been pulled by the epilogue (a last-layer pass preceded), `accum` = keep the accumulator (layer-0 group > 0)
-    const bool tr = a.trace && blockIdx.x == 0;
+    const bool tr = P_INSTR && a.trace && blockIdx.x == 0;
     long long t_w = 0, t_a = 0, t_e = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = P_INSTR ? clock64() : 0;
     auto unit = [&](int nslots, int K, bool wait_a, bool wait_e, bool accum) {
       if (!ok) return;
       long long c0 = tr ? clock64() : 0;
@@ -281,7 +308,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
           const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);
           const uint32_t a1 = tmem + s * P_SLOT + P_A + (uint32_t)(t * 32), a2 = a1 + P_A_STRIDE;
           const int nk = min(4, ksteps - t * 4);
-          if (a.debug & 1) {
+          if (P_INSTR && (a.debug & 1)) {
           } else if (nk == 4) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
@@ -295,12 +322,14 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         }
         mma_commit_elect(&S->acc_full[s]);
       }
-      mma_commit_elect(&S->w_empty[stage]);     // both slots' MMAs on this stage are issued: release it when they finish
+      // both slots' MMAs on this stage are issued: release it (in every CTA of the cluster) when they finish
+      if (cs == 1) mma_commit_elect(&S->w_empty[stage]);
+      else mma_commit_elect_multicast(&S->w_empty[stage], cmask);
       stage ^= 1;
     };
     const int U = G + (L - 2) + P;
     for (long long it = 0; it < n_my && ok; ++it) {
-      const int nslots = (tile_of(it, 1) < a.ntiles) ? 2 : 1;
+      const int nslots = slots_of(it);
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         if (u < G) unit(nslots, min(128, a.net.K[0] - 128 * u), true, u == 0 && it > 0, u > 0);
@@ -338,9 +367,9 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         if (!WIDE && g == 0) mbar_arrive(&S->c_free[s]);
       }
     };
-    const bool tr = a.trace && blockIdx.x == 0 && warp == 0;
+    const bool tr = P_INSTR && a.trace && blockIdx.x == 0 && warp == 0;
     long long t_acc = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = P_INSTR ? clock64() : 0;
     auto wait_acc = [&](int s) {
       const long long c0 = tr ? clock64() : 0;
       ok = ok && mbar_wait_sleep(&S->acc_full[s], ph_acc[s], a.status);
@@ -353,7 +382,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     int n_oob = 0;
     const int U = (G - 1) + (L - 1) + P;      // staging events of layer-0 groups 1.., hidden layers, last-layer passes
     for (long long it = 0; it < n_my; ++it) {
-      const int nslots = (tile_of(it, 1) < a.ntiles) ? 2 : 1;
+      const int nslots = slots_of(it);
       if (it == 0)
         for (int s = 0; s < nslots; ++s) stage_x(0, s, 0);
       ld[0] = ld[1] = 0.f;
@@ -381,7 +410,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 bb = b4[i];
-              if (a.debug & 4) {
+              if (P_INSTR && (a.debug & 4)) {
                 t1[2 * i] = v[4 * i]; t2[2 * i] = v[4 * i + 1]; t1[2 * i + 1] = v[4 * i + 2]; t2[2 * i + 1] = v[4 * i + 3];
                 continue;
               }
@@ -453,7 +482,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
               p2[24] = f2(__uint_as_float(va[24]) + (WIDE ? __ldg(bsrc + 24) : bsrc[24]),
                           __uint_as_float(vb[24]) + (WIDE ? __ldg(bsrc + P_BPAD + 24) : bsrc[P_BPAD + 24]));
               F2 y2 = f2(xA, xB), l2 = f2(0.f, 0.f);
-              if (!(a.debug & 2)) rqs_eval_reg2<!INVERSE>(p2, a.ck, f2(xA, xB), y2, l2);
+              if (!(P_INSTR && (a.debug & 2))) rqs_eval_reg2<!INVERSE>(p2, a.ck, f2(xA, xB), y2, l2);
               if (!WIDE || live) {
                 yrow[dA] = lo(y2);
                 yrow[dA + 1] = hi(y2);
@@ -477,7 +506,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
               }
               pp[24] = __uint_as_float(va[24]) + (WIDE ? __ldg(bsrc + 24) : bsrc[24]);
               float y = xA, lad = 0.f;
-              if (!(a.debug & 2)) rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
+              if (!(P_INSTR && (a.debug & 2))) rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
               if (!WIDE || live) yrow[dA] = y;
               ld[s] += lad;
             } else {
@@ -511,7 +540,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (cs > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -637,8 +667,38 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
     if (rc) return rc;
     configured[epw6][wide ? 1 : 0][inv][net->act] = smem;
   }
-  const unsigned grid = (unsigned)std::min<long long>(a.npairs, (long long)sm_count);
-  kern<<<grid, (epw6 ? 28 : 20) * 32, smem, st>>>(a);
+  // CTAs per cluster (BGX_PAIR_CLUSTER = 1, 2 or 4): the CTAs of a cluster fetch every weight stage ONCE (each issues its
+  // share of the bulk copies with .multicast::cluster), which divides the L2 -> SM weight traffic by the cluster size
+  static const int cs_env = [] { const char* e = getenv("BGX_PAIR_CLUSTER"); return e ? atoi(e) : P_CLUSTER_DEFAULT; }();
+  const int cs = (cs_env == 2 || cs_env == 4) ? cs_env : 1;
+  a.cs = cs;
+  cudaLaunchConfig_t lc = {};
+  lc.blockDim = dim3((epw6 ? 28 : 20) * 32, 1, 1);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = cs > 1 ? 1 : 0;
+  long long ncl = sm_count / cs;
+  if (cs > 1) {
+    static int max_clusters[2][2][2][2][4] = {};     // [cs == 4][epw6][wide][inv][act]: co-resident clusters of this kernel
+    int& mc = max_clusters[cs == 4][epw6][wide ? 1 : 0][inv][net->act];
+    if (!mc) {
+      lc.gridDim = dim3((unsigned)(ncl * cs), 1, 1);
+      rc = check(cudaOccupancyMaxActiveClusters(&mc, kern, &lc));
+      if (rc) return rc;
+      if (mc < 1) return BGX_ERR_UNSUPPORTED;
+    }
+    ncl = std::min<long long>(ncl, mc);
+  }
+  ncl = std::min<long long>(ncl, (a.npairs + cs - 1) / cs);
+  lc.gridDim = dim3((unsigned)(ncl * cs), 1, 1);
+  rc = check(cudaLaunchKernelEx(&lc, kern, a));
+  if (rc) return rc;
   return post_launch();
 }
 

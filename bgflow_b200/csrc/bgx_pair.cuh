@@ -17,6 +17,7 @@ constexpr uint32_t P_KT_BYTES = 2 * P_TILE_BYTES;     // both terms
 constexpr uint32_t P_STAGE_BYTES = 2 * P_KT_BYTES;    // a unit has at most two k-tiles
 constexpr int P_SLOT = 256, P_ACC = 0, P_A = 128, P_A_STRIDE = 64;
 constexpr int P_NB = 8, P_PS = 3 * P_NB + 1, P_DPP = 5, P_BPAD = 28;
+constexpr int P_CLUSTER_DEFAULT = 2; // CTAs per cluster sharing each weight stage by TMA multicast (1, 2 or 4)
 constexpr int P_EPW_DEFAULT = 4;     // epilogue warps per quadrant of the spline pair kernel (4 or 6)
 
 // Layer-0 operand of one slot: inputs 128 g + [32 j, 32 j + 32) of this thread's row -> two exact bf16 terms in

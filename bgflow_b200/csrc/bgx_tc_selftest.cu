@@ -176,13 +176,18 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
     if (lane == 0) mbar_arrive(a_ready);
     if (v_ld) {          // concurrent TMEM reads of the accumulator while the MMAs run
       uint32_t sink = 0;
-      while (!*done_flag) {
-        uint32_t r[32];
+      int n_ld = 0;
+      while (!*done_flag) {      // two 32-column loads (8 KB per warp) in flight per wait
+        uint32_t r[32], r2[32];
         tmem_ld32(tmem + lane_base + ST_ACC_COL + 64, r);
+        tmem_ld32(tmem + lane_base + ST_ACC_COL + 32, r2);
         tmem_ld_wait();
-        sink ^= r[lane & 31];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sink ^= r[i] ^ r2[i];     // (static indices: no local-memory spill in the loop)
+        n_ld += 2;
       }
       if (sink == 0x12345678u) out[0] = 1.f;
+      if (warp == 0 && lane == 0) status[3] = n_ld;      // x 4 warps x 4 KB = bytes read through tcgen05.ld meanwhile
     }
     mbar_wait(acc_full, 0, status);
     tc_fence_after();

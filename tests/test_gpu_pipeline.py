@@ -76,7 +76,7 @@ def test_config4_pipeline_matches_oracle(batch, fuse):
     assert np.median(derr) < 2e-4 and np.quantile(derr, 0.99) < 1e-2, (np.median(derr), derr.max())
     if fuse:
         # 14 couplings (+ segment gathers are torch copies) + one cdf launch (augmented) + one mapped-IC launch
-        assert n_launch == 16, n_launch
+        assert n_launch in (16, 17), n_launch      # 17: the IC kernel ran its full tiles through bulk copies + one tail launch
 
 
 def test_config4_energy_direction_round_trip():

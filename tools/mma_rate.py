@@ -50,3 +50,16 @@ for mode, name, cols in ((4, "bf16x3 TS N=128", 128), (5, "bf16x3 TS N=256", 256
         n = reps * 12
         cyc = int(st[1]) / n
         print(f"{name:18s} {label:22s}: {cyc:6.1f} cycles/MMA = {cyc * 128 / cols:6.1f} per 128x128x16 (rc={rc}, timeout={int(st[0])})")
+
+print("--- does tcgen05.ld share the TMEM read port with the A-operand fetch of TS-mode MMAs?  (4 warps loop on tcgen05.ld.x32 of the accumulator)")
+for mode, name, cols in ((4, "bf16x3 TS N=128", 128), (5, "bf16x3 TS N=256", 256)):
+    for label, bits in (("alone", 0), ("+ concurrent tcgen05.ld", 1 << 30)):
+        st = torch.zeros(4, dtype=torch.int32, device=dev)
+        reps = 512
+        word = mode | (reps << 4) | bits
+        rc = lib.bgx_tc_selftest(word, A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(), st.data_ptr(), None)
+        torch.cuda.synchronize()
+        n = reps * 12
+        cyc = int(st[1]) / n
+        extra = f"; tcgen05.ld moved {int(st[3]) * 4 * 4096 / max(int(st[1]), 1):5.1f} B/cycle meanwhile" if bits else ""
+        print(f"{name:18s} {label:26s}: {cyc:6.1f} cycles/MMA = {cyc * 128 / cols:6.1f} per 128x128x16 (rc={rc}, timeout={int(st[0])}){extra}")
