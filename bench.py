@@ -445,6 +445,19 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
 
     steps = max(3, args.steps // 2)
     res = {}
+    from bgflow_b200 import engine as _engine
+    gemm_modes = {}
+    for gm in ("tf32", "bf16x3"):          # the conditioner backward's GEMM variants (engine.config["backward_gemm"])
+        old_gm = _engine.config["backward_gemm"]
+        _engine.config["backward_gemm"] = gm
+        red.overlap = True
+        try:
+            for _ in range(2):
+                train_step()
+            gemm_modes[gm] = run_timed(train_step, steps) / steps
+        except Exception as exc:  # noqa: BLE001  (a torch build without mm(out_dtype=...) must not kill the bench)
+            gemm_modes[gm] = f"unavailable: {type(exc).__name__}"
+        _engine.config["backward_gemm"] = old_gm
     for mode in ("overlap", "after_backward", "no_allreduce"):
         red.overlap = mode == "overlap"
         fn = (lambda: train_step(False)) if mode == "no_allreduce" else train_step
@@ -457,7 +470,8 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     out = {"samples_per_s": rows * world / (res["overlap"] * 1e-3), "ms_per_step": res["overlap"], "rows_per_gpu": rows,
            "n_gpus": world, "allreduce_fp32_elems": red.n_elements, "allreduce_bytes": 4 * red.n_elements,
            "buckets": len(red.buckets), "ms_per_step_allreduce_after_backward": res["after_backward"],
-           "ms_per_step_no_allreduce": res["no_allreduce"],
+           "ms_per_step_no_allreduce": res["no_allreduce"], "backward_gemm": "fp32 (cuBLAS)",
+           "ms_per_step_other_backward_gemm_modes": gemm_modes,
            "what": "fused-kernel forward; backward = conditioner re-run + its GEMM backward (torch/cuBLAS fp32) + "
                    "bgx_spline_backward kernel; one NCCL all-reduce per coupling block launched from a gradient hook "
                    "as soon as that block's backward is done (overlaps the remaining backward); Adam"}

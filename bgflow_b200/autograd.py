@@ -44,18 +44,22 @@ class _FusedCoupling(torch.autograd.Function):
             cond = [x.detach().requires_grad_(True) for x in saved[:ctx.n_cond]]
             if ctx.kind == "spline":
                 gin, g_tr = _spline_backward(t, cond, saved[ctx.n_cond:], params, grads, ctx.inverse)
+            elif _affine_explicit_ok(t, params):
+                gin, g_tr = _affine_backward(t, cond, saved[ctx.n_cond:], grads, ctx.inverse)
             else:
+                from . import engine
                 tr = [x.detach().requires_grad_(True) for x in saved[ctx.n_cond:]]
-                out, dlogp = _torch_math.affine(t, torch.cat(cond, dim=-1), torch.cat(tr, dim=-1), ctx.inverse)
-                outs = torch.split(out, [x.shape[-1] for x in tr], dim=-1)
-                # only outputs that carry a graph and an upstream gradient: for a shift-only (NICE) or
-                # identity transformer dlogp is a constant zero without a grad_fn (affine.py:41-47)
-                pairs = [(o, g) for o, g in zip([*outs, dlogp], grads) if g is not None and o.requires_grad]
-                if pairs:
-                    g_all = torch.autograd.grad([o for o, _ in pairs], [*cond, *tr, *params],
-                                                grad_outputs=[g for _, g in pairs], allow_unused=True)
-                else:
-                    g_all = (None,) * (ctx.n_cond + ctx.n_tr + len(params))
+                with _matmul_mode(engine.config.get("backward_gemm")):
+                    out, dlogp = _torch_math.affine(t, torch.cat(cond, dim=-1), torch.cat(tr, dim=-1), ctx.inverse)
+                    outs = torch.split(out, [x.shape[-1] for x in tr], dim=-1)
+                    # only outputs that carry a graph and an upstream gradient: for a shift-only (NICE) or
+                    # identity transformer dlogp is a constant zero without a grad_fn (affine.py:41-47)
+                    pairs = [(o, g) for o, g in zip([*outs, dlogp], grads) if g is not None and o.requires_grad]
+                    if pairs:
+                        g_all = torch.autograd.grad([o for o, _ in pairs], [*cond, *tr, *params],
+                                                    grad_outputs=[g for _, g in pairs], allow_unused=True)
+                    else:
+                        g_all = (None,) * (ctx.n_cond + ctx.n_tr + len(params))
                 g_tr = g_all[ctx.n_cond:ctx.n_cond + ctx.n_tr]
                 gin = (*g_all[:ctx.n_cond], *g_all[ctx.n_cond + ctx.n_tr:])
         g_cond = gin[:ctx.n_cond]
@@ -64,27 +68,128 @@ class _FusedCoupling(torch.autograd.Function):
         return (None, None, None, None, None, *g_cond, *g_tr, *full)
 
 
+class _matmul_mode:
+    """``backward_gemm == "tf32"``: cuBLAS TF32 tensor-core GEMMs inside the block (restored on exit)."""
+
+    def __init__(self, mode):
+        self.tf32 = mode == "tf32"
+
+    def __enter__(self):
+        if self.tf32:
+            self.old = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        if self.tf32:
+            torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
+def _affine_explicit_ok(t, params):
+    """Plain RealNVP block (shift and scale DenseNets, no volume preservation / circular wrap), every parameter
+    trainable: the backward below applies; anything else re-evaluates the torch definition under autograd."""
+    from . import engine, _mlp_grad
+    if engine.config.get("backward_gemm") != "bf16x3" or t._preserve_volume or t._is_circular:
+        return False
+    sh, sc = t._shift_transformation, t._scale_transformation
+    if sh is None or sc is None or not _mlp_grad.supported(sh) or not _mlp_grad.supported(sc):
+        return False
+    allp = list(t.parameters())
+    return len(params) == len(allp) and len(allp) == 1 + len(list(sh.parameters())) + len(list(sc.parameters()))
+
+
+@torch.no_grad()
+def _affine_backward(t, cond, tr, grads, inverse):
+    """Backward of ``y' = y exp(ls) + mu`` / ``y' = (y - mu) exp(-ls)`` with ``ls = tanh(s) exp(log_alpha)``
+    (affine.py:35-70) written out by hand; both conditioners are re-run and differentiated on tensor cores
+    (``_mlp_grad``).  Returns (grads of cond + parameters in ``t.parameters()`` order, grads of tr)."""
+    from . import _mlp_grad
+    widths = [x.shape[-1] for x in tr]
+    y = torch.cat([x.detach() for x in tr], dim=-1) if len(tr) > 1 else tr[0].detach()
+    x = torch.cat([c.detach() for c in cond], dim=-1) if len(cond) > 1 else cond[0].detach()
+    lead, d_t = y.shape[:-1], y.shape[-1]
+    y2, x2 = y.reshape(-1, d_t), x.reshape(-1, x.shape[-1])
+    g_out = torch.cat([g if g is not None else torch.zeros_like(v) for g, v in zip(grads[:-1], tr)], dim=-1).reshape(-1, d_t)
+    g_dl = grads[-1].reshape(-1, 1) if grads[-1] is not None else None
+    st_mu = _mlp_grad.forward(t._shift_transformation, x2)
+    st_s = _mlp_grad.forward(t._scale_transformation, x2)
+    alpha = torch.exp(t._log_alpha.detach())
+    th = torch.tanh(st_s["out"])
+    ls = th * alpha
+    if not inverse:
+        e = torch.exp(ls)
+        d_y = g_out * e
+        d_mu = g_out
+        d_ls = d_y * y2
+        if g_dl is not None:
+            d_ls = d_ls + g_dl
+    else:
+        e = torch.exp(-ls)
+        d_y = g_out * e
+        d_mu = -d_y
+        d_ls = -d_y * (y2 - st_mu["out"])
+        if g_dl is not None:
+            d_ls = d_ls - g_dl
+    d_log_alpha = (d_ls * ls).sum().reshape(t._log_alpha.shape)       # d ls / d log_alpha = ls
+    d_s = d_ls * alpha * (1 - th * th)
+    dx_mu, g_mu = _mlp_grad.backward(st_mu, d_mu.contiguous())
+    dx_s, g_s = _mlp_grad.backward(st_s, d_s)
+    d_x = (dx_mu + dx_s).reshape(*lead, x.shape[-1])
+    g_cond = torch.split(d_x, [c.shape[-1] for c in cond], dim=-1)
+    # parameter order of AffineTransformer.parameters(): registration order of the module's members
+    named = dict(shift=g_mu, scale=g_s)
+    order = []
+    for name, _ in t.named_parameters():
+        if name == "_log_alpha":
+            order.append(d_log_alpha)
+        elif name.startswith("_shift_transformation"):
+            order.append(named["shift"].pop(0))
+        elif name.startswith("_scale_transformation"):
+            order.append(named["scale"].pop(0))
+        else:
+            raise RuntimeError(f"unexpected parameter {name} in an AffineTransformer")
+    return (*g_cond, *order), torch.split(d_y.reshape(*lead, d_t), widths, dim=-1)
+
+
 def _spline_backward(t, cond, tr, params, grads, inverse):
-    """Spline block backward: conditioner forward/backward with torch (dense GEMMs), the transform's
-    chain rule in ONE kernel (``bgx_spline_backward``).  Returns (grads of cond + params, grads of tr)."""
-    from . import engine
+    """Spline block backward: conditioner recompute + its backward, the transform's chain rule in ONE kernel
+    (``bgx_spline_backward``).  The conditioner GEMMs run on tensor cores (``_mlp_grad``: exact bf16 splits, three
+    products, fp32 accumulation) for plain DenseNets, through torch autograd (fp32 cuBLAS) otherwise.
+    Returns (grads of cond + params, grads of tr)."""
+    from . import engine, _mlp_grad
     widths = [x.shape[-1] for x in tr]
     y = torch.cat([x.detach() for x in tr], dim=-1) if len(tr) > 1 else tr[0].detach()
     d_t = y.shape[-1]
-    p = t._params_net(torch.cat(cond, dim=-1) if len(cond) > 1 else cond[0])
     lead = y.shape[:-1]
-    p2, y2 = p.reshape(-1, p.shape[-1]), y.reshape(-1, d_t)
-    k = p2.shape[-1] // (3 * d_t)
+    y2 = y.reshape(-1, d_t)
     g_out = torch.cat([g if g is not None else torch.zeros_like(x) for g, x in zip(grads[:-1], tr)], dim=-1)
     g_dl = grads[-1]
     st = t._default_settings
-    d_p, d_y = engine.spline_backward(
-        p2.detach(), y2, g_out.reshape(-1, d_t), g_dl.reshape(-1) if g_dl is not None else None,
-        t._end_slope_cols(d_t, k, y.device), k, inverse=inverse, left=t._left, right=t._right, bottom=t._bottom,
-        top=t._top, min_bin_width=st["min_bin_width"], min_bin_height=st["min_bin_height"],
-        min_derivative=st["min_derivative"], identity_init=st["enable_identity_init"])
-    gin = torch.autograd.grad(p, [*cond, *params], grad_outputs=d_p.reshape(p.shape), allow_unused=True)
-    return gin, torch.split(d_y.reshape(*lead, d_t), widths, dim=-1)
+    out = {}
+
+    def transform_backward(p2):
+        k = p2.shape[-1] // (3 * d_t)
+        d_p, out["d_y"] = engine.spline_backward(
+            p2, y2, g_out.reshape(-1, d_t), g_dl.reshape(-1) if g_dl is not None else None,
+            t._end_slope_cols(d_t, k, y.device), k, inverse=inverse, left=t._left, right=t._right, bottom=t._bottom,
+            top=t._top, min_bin_width=st["min_bin_width"], min_bin_height=st["min_bin_height"],
+            min_derivative=st["min_derivative"], identity_init=st["enable_identity_init"])
+        return d_p
+
+    net = t._params_net
+    all_params = list(t.parameters())
+    if (engine.config.get("backward_gemm") == "bf16x3" and _mlp_grad.supported(net)
+            and len(params) == len(all_params) and len(all_params) == len(list(net.parameters()))):
+        x = torch.cat([c.detach() for c in cond], dim=-1) if len(cond) > 1 else cond[0].detach()
+        d_x, g_params = _mlp_grad.forward_backward(net, x.reshape(-1, x.shape[-1]), transform_backward)
+        g_cond = torch.split(d_x.reshape(*lead, x.shape[-1]), [c.shape[-1] for c in cond], dim=-1)
+        gin = (*g_cond, *g_params)
+    else:
+        with _matmul_mode(engine.config.get("backward_gemm")):
+            p = net(torch.cat(cond, dim=-1) if len(cond) > 1 else cond[0])
+            d_p = transform_backward(p.detach().reshape(-1, p.shape[-1]))
+            gin = torch.autograd.grad(p, [*cond, *params], grad_outputs=d_p.reshape(p.shape), allow_unused=True)
+    return gin, torch.split(out["d_y"].reshape(*lead, d_t), widths, dim=-1)
 
 
 def fused_coupling_with_grad(transformer, kind, cond, tr, inverse):

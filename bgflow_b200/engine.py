@@ -95,7 +95,13 @@ config = {"precision": "bf16x3", "force_simt": False,
           "spline_kernel": "auto",
           # affine blocks: "auto" (two-CTAs-per-SM / one-CTA kernels for narrow blocks, the pair kernel for wide
           # ones), "pair" (the pair kernel wherever eligible), "no_pair"
-          "affine_kernel": "auto"}
+          "affine_kernel": "auto",
+          # conditioner GEMMs of the recompute backward (training path): "fp32" (default: torch autograd on cuBLAS fp32
+          # GEMMs, the reference's semantics), "tf32" (the same with cuBLAS TF32 tensor-core GEMMs: 2^-11 per product)
+          # or "bf16x3" (explicit backward, three bf16 products of exact two-term splits with fp32 accumulation:
+          # fp32-class accuracy, but cuBLAS serves bf16 -> fp32-out GEMMs of these shapes with pre-Hopper kernels and the
+          # step gets SLOWER, 27 ms vs 20 ms — measured, profiles/r2_train_profile_bf16x3.txt)
+          "backward_gemm": "fp32"}
 
 _status = {}
 
@@ -393,6 +399,22 @@ def spline_backward(params, y, g_out, g_dlogp, end_slope_col, n_bins, inverse=Fa
                                  d_y.data_ptr(), _stream())
     _lib.check(rc, "bgx_spline_backward")
     return d_params, d_y
+
+
+@_device_guard
+def split_bf16(x):
+    """Exact two-term bf16 split ``x = hi + lo`` of an fp32 CUDA tensor (``bgx_split_bf16``).  Returns two
+    contiguous bf16 tensors of ``x``'s shape."""
+    lib = _lib.load()
+    require_cuda_fp32(x)
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        rc = lib.bgx_split_bf16(C.c_void_p(x.data_ptr()), x.numel(), C.c_void_p(hi.data_ptr()), C.c_void_p(lo.data_ptr()),
+                                _stream())
+        _lib.check(rc, "bgx_split_bf16")
+    return hi, lo
 
 
 class ZPlan:

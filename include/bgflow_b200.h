@@ -300,6 +300,12 @@ int bgx_relic_from_xyz(const bgx_relplan* plan, int64_t batch, const float* xyz,
 int bgx_split_merge(int64_t batch, const bgx_seg* whole, int32_t n_parts, const bgx_seg* parts, int merge,
                     void* stream);
 
+/* Training path: exact two-term bf16 split of an fp32 tensor, hi = rn(x), lo = rn(x - hi) (x = hi + lo to 2^-17 |x|).
+ * The backward GEMMs of the conditioner (bgflow_b200/_mlp_grad.py; the reference differentiates dense.py:47-48 with
+ * autograd) run as three bf16 tensor-core products hi.hi + hi.lo + lo.hi with fp32 accumulation, like the forward
+ * kernels.  x: n floats, 16-byte aligned; hi / lo: n bf16 values each, 8-byte aligned. */
+int bgx_split_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T

@@ -99,6 +99,48 @@ def test_affine_variants_backward(variant, inverse):
         np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=3e-3 * sc, rtol=3e-3)
 
 
+@pytest.mark.parametrize("kind", ["spline", "affine"])
+@pytest.mark.parametrize("mode,tol", [("tf32", 1e-2), ("bf16x3", 3e-3)])
+def test_backward_gemm_modes(kind, mode, tol):
+    """engine.config["backward_gemm"]: the conditioner backward on cuBLAS TF32 GEMMs, or written out explicitly with
+    three bf16 tensor-core products of exact operand splits (``_mlp_grad`` + ``bgx_split_bf16``; also the hand-written
+    affine backward) — both against the fp64 oracle (fp32 cuBLAS is the default the other tests cover)."""
+    from bgflow_b200 import engine
+    old = engine.config["backward_gemm"]
+    engine.config["backward_gemm"] = mode
+    try:
+        dim, nblk = 10, 2
+        hidden = (128, 128) if kind == "spline" else (24, 24)
+        blocks, split = of.make_stack(kind, dim, nblk, hidden=hidden, seed=2)
+        blocks64, _ = of.make_stack(kind, dim, nblk, hidden=hidden, seed=2, dtype=torch.float64)
+        flow = stack_from(blocks, split, DEV)
+        g = torch.Generator().manual_seed(4)
+        z = torch.rand(300, dim, generator=g) if kind == "spline" else torch.randn(300, dim, generator=g)
+        wx, wd = torch.randn(300, dim, generator=g), torch.randn(300, 1, generator=g)
+        for inverse in (False, True):
+            x_ref, d_ref, gz_ref, gp_ref = _oracle_grads(kind, blocks64, split, z, wx, wd, inverse)
+            flow.zero_grad()
+            zc = z.to(DEV).requires_grad_(True)
+            x, d = flow(zc, inverse=inverse)
+            ((x * wx.to(DEV)).sum() + (d * wd.to(DEV)).sum()).backward()
+            s = gz_ref.abs().max().item()
+            np.testing.assert_allclose(zc.grad.cpu().double().numpy(), gz_ref.numpy(), atol=tol * s, rtol=tol)
+            ours = []
+            for m in flow.modules():
+                if isinstance(m, bg.DenseNet):
+                    lin = [l for l in m._layers if isinstance(l, torch.nn.Linear)]
+                    ours += [l.weight.grad for l in lin] + [l.bias.grad for l in lin]
+            assert len(ours) == len(gp_ref)
+            for a, b in zip(ours, gp_ref):
+                sc = max(b.abs().max().item(), 1e-6)
+                np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=1.5 * tol * sc, rtol=1.5 * tol)
+            if kind == "affine":
+                la = [m for m in flow.modules() if isinstance(m, bg.AffineTransformer)]
+                assert all(t._log_alpha.grad is not None and torch.isfinite(t._log_alpha.grad).all() for t in la)
+    finally:
+        engine.config["backward_gemm"] = old
+
+
 def test_kl_training_step_reduces_loss():
     """A few reverse-KL steps (bg.py:13-17) on a Gaussian target through kernel-forward blocks."""
     from bgflow_b200.distributed import kl_train_step
