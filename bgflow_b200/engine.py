@@ -89,9 +89,9 @@ config = {"precision": "bf16x3", "force_simt": False,
           # the batch is large, so that the two-CTAs-per-SM kernels (dense single tensors only) apply;
           # the copies cost ~5 % of a block, the one-CTA kernel ~25 %
           "gather_segments": True, "gather_min_rows": 4096,
-          # spline blocks: "auto" (two-CTAs-per-SM kernel for narrow dense blocks, pair kernel for every other
-          # tensor-core shape), "pair" (pair kernel wherever eligible), "pair_wide" (pair kernel with tiles accessed
-          # in place in global memory even where they fit shared memory), "tc2" (never the pair kernel)
+          # spline blocks: "auto" / "pair" (the pair kernel wherever eligible: tiles in shared memory for narrow dense
+          # blocks, in place in global memory otherwise), "pair_wide" (in-place tiles even where they fit shared
+          # memory), "tc2" (never the pair kernel: two-CTAs-per-SM / one-CTA / SIMT kernels; A/B)
           "spline_kernel": "auto",
           # affine blocks: "auto" (two-CTAs-per-SM / one-CTA kernels for narrow blocks, the pair kernel for wide
           # ones), "pair" (the pair kernel wherever eligible), "no_pair"

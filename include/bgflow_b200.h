@@ -136,8 +136,9 @@ typedef struct bgx_coupling_io {
 #define BGX_FLAG_FORCE_SIMT 16      /* always use the generic fp32 SIMT kernel */
 #define BGX_FLAG_NO_PAIR 32         /* spline: never the pair kernel */
 #define BGX_FLAG_FORCE_WIDE 64      /* spline pair kernel: in-place global tile access even where the tile fits shared memory */
-#define BGX_FLAG_PREFER_PAIR 128    /* spline: the pair kernel even where the two-CTAs-per-SM kernel applies (default: the
-                                       latter for narrow dense blocks — measured faster at D = 66 — the pair kernel elsewhere) */
+#define BGX_FLAG_PREFER_PAIR 128    /* affine: the pair kernel even where the two-CTAs-per-SM kernel applies (default: the
+                                       latter for narrow dense blocks, the pair kernel for wide ones).  Spline blocks use
+                                       the pair kernel wherever it is eligible unless BGX_FLAG_NO_PAIR is set. */
 
 /* y' = y * exp(ls) + mu   (forward)   |   y' = (y - mu) * exp(-ls)   (inverse)
  * mu = shift(cond), ls = tanh(scale(cond)) * exp(log_alpha);  dlogp = +-sum(ls).

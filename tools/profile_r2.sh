@@ -1,0 +1,32 @@
+#!/bin/bash
+# Round-2 evidence capture (run under gpurun, 1 GPU).  Writes everything to gpurun_out/r2_*.
+set -u
+O=gpurun_out
+mkdir -p $O
+B=${1:-1048576}
+NCU="ncu --clock-control none"
+# the numbers themselves first (never taken under the profiler)
+timeout 1200 python bench.py --steps 10 --warmup 3 > $O/r2_bench.json 2> $O/r2_bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference.json 2> $O/r2_bench_reference.err
+timeout 300 python bench.py --workload ala2_affine_d66_8blk --steps 10 --warmup 3 --no-cpu-baseline --no-sweep --no-train > $O/r2_bench_affine.json 2> $O/r2_bench_affine.err
+BGX_SPLINE_KERNEL=tc2 timeout 300 python bench.py --steps 10 --no-cpu-baseline --no-e2e --no-sweep --no-train > $O/r2_bench_spline_tc2.json 2>/dev/null
+timeout 300 python tools/bench_ic.py > $O/r2_bench_ic.json 2> $O/r2_bench_ic.err
+BGX_IC_BULK=0 timeout 300 python tools/bench_ic.py > $O/r2_bench_ic_staged.json 2>/dev/null
+timeout 120 python tools/mma_rate.py > $O/r2_mma_rate_probe.txt 2>&1
+# full captures of the dominant kernels at the bench batch size (one launch each)
+timeout 400 $NCU --set full --import-source on -k regex:spline_coupling_pair -s 10 -c 1 -o $O/r2_spline_pair \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-train --batch-per-gpu $B > $O/r2_spline_pair.log 2>&1
+timeout 400 $NCU --set full --import-source on -k regex:spline_coupling_pair -s 10 -c 1 -o $O/r2_spline_pair_d384 \
+  python bench.py --workload spline_d384_8blk --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-train --batch-per-gpu 262144 > $O/r2_spline_pair_d384.log 2>&1
+timeout 400 $NCU --set full --import-source on -k regex:affine_coupling_pair -s 10 -c 1 -o $O/r2_affine_pair_d384 \
+  python bench.py --workload affine_d384_8blk --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-train --batch-per-gpu 262144 > $O/r2_affine_pair_d384.log 2>&1
+timeout 300 $NCU --set full --import-source on -k regex:ic_ -s 4 -c 2 -o $O/r2_ic python tools/run_ic.py > $O/r2_ic.log 2>&1
+# launch list of the bench command (shares of the step)
+timeout 300 $NCU --metrics gpu__time_duration.sum -s 60 -c 60 --csv --log-file $O/r2_launches_spline.csv \
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-train > /dev/null 2>&1
+# sanitizers on the new kernels (small batches)
+timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_pair.py tests/test_gpu_ic.py tests/test_gpu_relic.py -x -q > $O/r2_memcheck.log 2>&1
+timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_pair.py -x -q -k "narrow or affine_wide" > $O/r2_racecheck.log 2>&1
+timeout 200 python -c 'import __graft_entry__ as g; g.smoke()' > $O/r2_smoke.log 2>&1; tail -2 $O/r2_smoke.log
+timeout 1200 python -m pytest tests -m gpu -q > $O/r2_gpu_tests.log 2>&1; tail -2 $O/r2_gpu_tests.log
+ls -la $O | grep r2_ | tail -30
