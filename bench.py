@@ -690,17 +690,19 @@ def main():
 
     pk = peaks()
     traffic = None      # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and B == (1 << 20) and not engine.config["force_simt"]:
-        tj = json.load(open(tpath)).get("spline_coupling_tc_kernel" if kind == "spline" else "affine_coupling_tc_kernel")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    traffic_kernel = None
+    if os.path.exists(tpath) and B == (1 << 20) and not engine.config["force_simt"] and dim == 66:
+        tj = json.load(open(tpath)).get("spline_coupling_pair_kernel" if kind == "spline" else "affine_coupling_tc_kernel")
         if tj:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_kernel = tj["kernel"]
     avg_kern_s = 1e-3 * sum(kern_ms) / max(len(kern_ms), 1)
     roofline = {
         "bound": "tensor", "kernel": f"fused {kind} coupling block (conditioner GEMMs + transform + log-det)",
         "achieved": flops_sb * B / avg_kern_s / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
         "frac": flops_sb * B / avg_kern_s / 1e12 / pk["tf_sustained"], "traffic": traffic,
-        "traffic_source": "profiles/r1_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+        "traffic_source": f"profiles/r2_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch of {traffic_kernel})",
         "peak_source": pk["source"] + " (dense bf16 cuBLAS, sustained); fp32-accurate math in the kernel",
         "avg_launch_ms": 1e3 * avg_kern_s, "launches_timed": len(kern_ms),
         "algorithmic_flops_per_launch": flops_sb * B, "algorithmic_bytes_per_launch": bytes_sb * B,

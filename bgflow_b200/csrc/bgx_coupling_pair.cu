@@ -426,10 +426,12 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
             if (lane == 0) mbar_arrive(&S->a_ready[s]);
           } else {
             // ---- last layer: pass c holds dims 5c .. 5c+4.  Per (pass, slot) the four warps of a quadrant take the
-            // roles {dims 0,1 packed | dims 2,3 packed | dim 4 | nothing}, rotating with c + s so the load evens out;
+            // roles {dims 0,1 packed | dims 2,3 packed | dim 4 | nothing}, rotating with c so the load evens out;
             // a pair of dims is evaluated in packed fp32 lanes (bgx_spline_reg2.cuh)
             const int c = u - (G + L - 2);
-            const int role = EPW == 4 ? ((j + c + s) & 3) : ((j + c + s) % 6);
+            // (independent of the slot: a row's dims are grouped into the same log-det shares wherever the row sits
+            // in the batch, so its dlogp does not depend on the batch it travels in, bit for bit)
+            const int role = EPW == 4 ? ((j + c) & 3) : ((j + c) % 6);
             const long long row = tile_of(it, s) * P_TM + r_in_tile;
             const bool live = row < a.B;
             if (!WIDE && c == 0) {

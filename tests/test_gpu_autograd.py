@@ -100,7 +100,7 @@ def test_affine_variants_backward(variant, inverse):
 
 
 @pytest.mark.parametrize("kind", ["spline", "affine"])
-@pytest.mark.parametrize("mode,tol", [("tf32", 1e-2), ("bf16x3", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("tf32", 3e-2), ("bf16x3", 3e-3)])   # (TF32: 2^-11 per product, ReLU kinks flip)
 def test_backward_gemm_modes(kind, mode, tol):
     """engine.config["backward_gemm"]: the conditioner backward on cuBLAS TF32 GEMMs, or written out explicitly with
     three bf16 tensor-core products of exact operand splits (``_mlp_grad`` + ``bgx_split_bf16``; also the hand-written
