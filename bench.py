@@ -447,7 +447,7 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     res = {}
     from bgflow_b200 import engine as _engine
     gemm_modes = {}
-    for gm in ("tf32", "bf16x3"):          # the conditioner backward's GEMM variants (engine.config["backward_gemm"])
+    for gm in ("tcgen05", "tf32", "bf16x3"):          # the conditioner backward's GEMM variants (engine.config["backward_gemm"])
         old_gm = _engine.config["backward_gemm"]
         _engine.config["backward_gemm"] = gm
         red.overlap = True

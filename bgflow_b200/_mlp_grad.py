@@ -12,7 +12,7 @@ import torch
 
 from . import engine
 
-__all__ = ["supported", "forward", "backward", "forward_backward"]
+__all__ = ["supported", "forward", "backward", "forward_backward", "forward_tc", "backward_tc", "tc_supported"]
 
 _ACTS = (torch.nn.SiLU, torch.nn.ReLU, torch.nn.Tanh)
 
@@ -47,6 +47,11 @@ def supported(net):
     return la is not None and all(l.weight.is_cuda and l.weight.dtype == torch.float32 for l in la[0])
 
 
+def tc_supported(net):
+    """``supported`` and every layer has at most 128 inputs or at most 128 outputs (what ``bgx_linear`` covers)."""
+    return supported(net) and _tc_ok(_layers(net)[0])
+
+
 def _mm3(a, b):
     """a = (a_hi, a_lo) [M, K], b = (b_hi, b_lo) [K, N] (bf16, any strides) -> fp32 [M, N] ~= a @ b."""
     f32 = torch.float32
@@ -75,6 +80,87 @@ def _act_grad(mod, z, g):
     if isinstance(mod, torch.nn.Tanh):
         return g * (1 - torch.tanh(z) ** 2)
     return g
+
+
+def _linear_cache(net):
+    c = net.__dict__.get("_bgx_linear_tc")
+    if c is None:
+        c = net.__dict__["_bgx_linear_tc"] = {}
+    return c
+
+
+def _tc_ok(lin):
+    return all(engine.LinearTC.supports(*l.weight.shape) for l in lin)
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _versioned(cache, key, params, make):
+    """``make()`` once per version of ``params`` (cached under ``key``)."""
+    ver = tuple((p.data_ptr(), p._version) for p in params)
+    ent = cache.get(key)
+    if ent is None or ent[0] != ver:
+        ent = cache[key] = (ver, make())
+    return ent[1]
+
+
+@torch.no_grad()
+def forward_tc(net, x):
+    """``forward`` with every layer GEMM on ``bgx_linear`` (tcgen05, exact bf16 splits).  The last layer's output is
+    padded with zero columns to a multiple of 4 floats (``state["out"]`` is ``[B, pad4(N)]``, row stride = width) so
+    that the backward's operand rows are 16-byte aligned; ``state["n_out"]`` is the true width."""
+    lin, acts = _layers(net)
+    cache = _linear_cache(net)
+    hs, zs = [x], []
+    for i, (l, a) in enumerate(zip(lin, acts)):
+        f = cache.setdefault(("fwd", i), engine.LinearTC())
+        n = l.weight.shape[0]
+        if i + 1 == len(lin) and n % 4:
+            def padded(l=l, n=n):
+                w = torch.zeros(_pad4(n), l.weight.shape[1], dtype=torch.float32, device=l.weight.device)
+                w[:n] = l.weight.detach()
+                b = torch.zeros(_pad4(n), dtype=torch.float32, device=l.weight.device)
+                b[:n] = l.bias.detach()
+                return w, b
+            w, b = _versioned(cache, ("fwd_pad", i), (l.weight, l.bias), padded)
+        else:
+            w, b = l.weight.detach(), l.bias.detach()
+        z = f(hs[-1], w, b)
+        zs.append(z)
+        if i + 1 < len(lin):
+            hs.append(_act(a, z))
+    return {"lin": lin, "acts": acts, "hs": hs, "zs": zs, "out": zs[-1], "n_out": lin[-1].weight.shape[0], "net": net}
+
+
+@torch.no_grad()
+def backward_tc(state, d_out, need_dx=True):
+    """``backward`` with the input-gradient GEMMs (dh = g W) on ``bgx_linear``; the weight gradients dW = g^T h reduce
+    over the batch and stay on cuBLAS fp32.  ``d_out`` has the (padded) shape of ``state["out"]``; its pad columns
+    must be zero."""
+    lin, acts, hs, zs = state["lin"], state["acts"], state["hs"], state["zs"]
+    cache = _linear_cache(state["net"])
+    g = d_out
+    grads = [None] * (2 * len(lin))
+    d_x = None
+    for i in range(len(lin) - 1, -1, -1):
+        n = lin[i].weight.shape[0]
+        grads[2 * i] = (g.t() @ hs[i])[:n]            # dW = g^T h   [out, in]
+        grads[2 * i + 1] = g.sum(dim=0)[:n]
+        if i > 0 or need_dx:
+            def transposed(w=lin[i].weight, width=g.shape[1]):
+                wt = torch.zeros(w.shape[1], width, dtype=torch.float32, device=w.device)     # [in, pad4(out)]
+                wt[:, :w.shape[0]] = w.detach().t()
+                return wt
+            wt = _versioned(cache, ("wt", i), (lin[i].weight,), transposed)
+            f = cache.setdefault(("dx", i), engine.LinearTC())
+            gh = f(g, wt)                             # dh = g W     [B, in]  (a layer with weight W^T)
+            if i > 0:
+                g = _act_grad(acts[i - 1], zs[i - 1], gh)
+            else:
+                d_x = gh
+    return d_x, grads
 
 
 @torch.no_grad()

@@ -89,10 +89,12 @@ def _affine_explicit_ok(t, params):
     """Plain RealNVP block (shift and scale DenseNets, no volume preservation / circular wrap), every parameter
     trainable: the backward below applies; anything else re-evaluates the torch definition under autograd."""
     from . import engine, _mlp_grad
-    if engine.config.get("backward_gemm") != "bf16x3" or t._preserve_volume or t._is_circular:
+    mode = engine.config.get("backward_gemm")
+    if mode not in ("bf16x3", "tcgen05") or t._preserve_volume or t._is_circular:
         return False
     sh, sc = t._shift_transformation, t._scale_transformation
-    if sh is None or sc is None or not _mlp_grad.supported(sh) or not _mlp_grad.supported(sc):
+    ok = _mlp_grad.tc_supported if mode == "tcgen05" else _mlp_grad.supported
+    if sh is None or sc is None or not ok(sh) or not ok(sc):
         return False
     allp = list(t.parameters())
     return len(params) == len(allp) and len(allp) == 1 + len(list(sh.parameters())) + len(list(sc.parameters()))
@@ -111,8 +113,11 @@ def _affine_backward(t, cond, tr, grads, inverse):
     y2, x2 = y.reshape(-1, d_t), x.reshape(-1, x.shape[-1])
     g_out = torch.cat([g if g is not None else torch.zeros_like(v) for g, v in zip(grads[:-1], tr)], dim=-1).reshape(-1, d_t)
     g_dl = grads[-1].reshape(-1, 1) if grads[-1] is not None else None
-    st_mu = _mlp_grad.forward(t._shift_transformation, x2)
-    st_s = _mlp_grad.forward(t._scale_transformation, x2)
+    from . import engine
+    tc = engine.config.get("backward_gemm") == "tcgen05"
+    fwd, bwd = (_mlp_grad.forward_tc, _mlp_grad.backward_tc) if tc else (_mlp_grad.forward, _mlp_grad.backward)
+    st_mu = fwd(t._shift_transformation, x2)
+    st_s = fwd(t._scale_transformation, x2)
     alpha = torch.exp(t._log_alpha.detach())
     th = torch.tanh(st_s["out"])
     ls = th * alpha
@@ -132,8 +137,8 @@ def _affine_backward(t, cond, tr, grads, inverse):
             d_ls = d_ls - g_dl
     d_log_alpha = (d_ls * ls).sum().reshape(t._log_alpha.shape)       # d ls / d log_alpha = ls
     d_s = d_ls * alpha * (1 - th * th)
-    dx_mu, g_mu = _mlp_grad.backward(st_mu, d_mu.contiguous())
-    dx_s, g_s = _mlp_grad.backward(st_s, d_s)
+    dx_mu, g_mu = bwd(st_mu, d_mu.contiguous())
+    dx_s, g_s = bwd(st_s, d_s)
     d_x = (dx_mu + dx_s).reshape(*lead, x.shape[-1])
     g_cond = torch.split(d_x, [c.shape[-1] for c in cond], dim=-1)
     # parameter order of AffineTransformer.parameters(): registration order of the module's members
@@ -167,8 +172,8 @@ def _spline_backward(t, cond, tr, params, grads, inverse):
     st = t._default_settings
     out = {}
 
-    def transform_backward(p2):
-        k = p2.shape[-1] // (3 * d_t)
+    def transform_backward(p2, n_out=None):
+        k = (n_out or p2.shape[-1]) // (3 * d_t)
         d_p, out["d_y"] = engine.spline_backward(
             p2, y2, g_out.reshape(-1, d_t), g_dl.reshape(-1) if g_dl is not None else None,
             t._end_slope_cols(d_t, k, y.device), k, inverse=inverse, left=t._left, right=t._right, bottom=t._bottom,
@@ -178,8 +183,18 @@ def _spline_backward(t, cond, tr, params, grads, inverse):
 
     net = t._params_net
     all_params = list(t.parameters())
-    if (engine.config.get("backward_gemm") == "bf16x3" and _mlp_grad.supported(net)
-            and len(params) == len(all_params) and len(all_params) == len(list(net.parameters()))):
+    mode = engine.config.get("backward_gemm")
+    all_trainable = len(params) == len(all_params) and len(all_params) == len(list(net.parameters()))
+    if mode == "tcgen05" and _mlp_grad.tc_supported(net) and all_trainable:
+        x = torch.cat([c.detach() for c in cond], dim=-1) if len(cond) > 1 else cond[0].detach()
+        st_net = _mlp_grad.forward_tc(net, x.reshape(-1, x.shape[-1]))
+        d_p = transform_backward(st_net["out"], st_net["n_out"])
+        if d_p.shape[1] > st_net["n_out"]:
+            d_p[:, st_net["n_out"]:] = 0          # pad columns of the 16-byte aligned layout (never written by the kernel)
+        d_x, g_params = _mlp_grad.backward_tc(st_net, d_p)
+        g_cond = torch.split(d_x.reshape(*lead, x.shape[-1]), [c.shape[-1] for c in cond], dim=-1)
+        gin = (*g_cond, *g_params)
+    elif mode == "bf16x3" and _mlp_grad.supported(net) and all_trainable:
         x = torch.cat([c.detach() for c in cond], dim=-1) if len(cond) > 1 else cond[0].detach()
         d_x, g_params = _mlp_grad.forward_backward(net, x.reshape(-1, x.shape[-1]), transform_backward)
         g_cond = torch.split(d_x.reshape(*lead, x.shape[-1]), [c.shape[-1] for c in cond], dim=-1)

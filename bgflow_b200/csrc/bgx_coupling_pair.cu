@@ -82,7 +82,7 @@ struct alignas(16) PSmem {
   uint64_t dl_ready[2];    // 16: the four dim shares of every row's log-det are written
   uint64_t dl_free[2];     // 1: ... and summed (the buffer may be rewritten)
   uint32_t tmem_base, pad[3];
-  float dl_part[2][6][P_TM];       // [slot][dim share (epilogue warp of the quadrant)][row]
+  float dl_part[2][12][P_TM];      // [slot][log-det share][row]: EPW 4: (pass mod 4, role) cells, EPW 6: one per warp
 };
 
 // EPW = epilogue warps per TMEM lane quadrant.  4: 16 epilogue warps at <= 96 registers, a quadrant's five dims of a pass
@@ -263,8 +263,9 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
           const long long row = tile * P_TM + r;
           if (row < a.B) {
             const float base_dl = a.dlogp_in ? a.dlogp_in[row] : 0.f;
-            float sum = (dl[r] + dl[P_TM + r]) + (dl[2 * P_TM + r] + dl[3 * P_TM + r]);
-            if (EPW == 6) sum += dl[4 * P_TM + r] + dl[5 * P_TM + r];
+            float sum = 0.f;
+#pragma unroll
+            for (int cell = 0; cell < (EPW == 4 ? 12 : 6); ++cell) sum += dl[cell * P_TM + r];     // fixed order
             a.dlogp_out[row] = base_dl + sum;
           }
         }
@@ -378,14 +379,14 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
       tc_fence_after();
     };
 
-    float ld[2];
+    float ld[2][3];      // log-det shares of this thread: [slot][role] (EPW 6: [slot][0])
     int n_oob = 0;
     const int U = (G - 1) + (L - 1) + P;      // staging events of layer-0 groups 1.., hidden layers, last-layer passes
     for (long long it = 0; it < n_my; ++it) {
       const int nslots = slots_of(it);
       if (it == 0)
         for (int s = 0; s < nslots; ++s) stage_x(0, s, 0);
-      ld[0] = ld[1] = 0.f;
+      for (int s = 0; s < 2; ++s) ld[s][0] = ld[s][1] = ld[s][2] = 0.f;
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
 #pragma unroll 1
@@ -429,9 +430,11 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
             // roles {dims 0,1 packed | dims 2,3 packed | dim 4 | nothing}, rotating with c so the load evens out;
             // a pair of dims is evaluated in packed fp32 lanes (bgx_spline_reg2.cuh)
             const int c = u - (G + L - 2);
-            // (independent of the slot: a row's dims are grouped into the same log-det shares wherever the row sits
-            // in the batch, so its dlogp does not depend on the batch it travels in, bit for bit)
-            const int role = EPW == 4 ? ((j + c) & 3) : ((j + c) % 6);
+            // The roles rotate with the pass AND the slot (the warp that idles on slot 0's pass works on slot 1's).  A row's
+            // log-det must not depend on the slot it lands in, bit for bit (row independence is tested at full size), so the
+            // shares are kept per (pass mod 4, role) cell — the same grouping and the same order of additions whichever warp
+            // serves it — and the reducer adds the twelve cells in a fixed order.
+            const int role = EPW == 4 ? ((j + c + s) & 3) : ((j + c) % 6);
             const long long row = tile_of(it, s) * P_TM + r_in_tile;
             const bool live = row < a.B;
             if (!WIDE && c == 0) {
@@ -489,8 +492,9 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
                 yrow[dA] = lo(y2);
                 yrow[dA + 1] = hi(y2);
               }
-              ld[s] += lo(l2);
-              ld[s] += hi(l2);
+              const float l_pair = lo(l2) + hi(l2);
+              if (EPW == 6 || role == 0) ld[s][0] += l_pair;
+              else ld[s][1] += l_pair;
             } else if (hasA) {
               uint32_t va[25];
               tmem_ld25(acc_addr, va);
@@ -510,7 +514,9 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
               float y = xA, lad = 0.f;
               if (!(P_INSTR && (a.debug & 2))) rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
               if (!WIDE || live) yrow[dA] = y;
-              ld[s] += lad;
+              if (EPW == 6 || role == 0) ld[s][0] += lad;      // (roles 0 / 1 land here on a last pass with an odd dim count)
+              else if (role == 1) ld[s][1] += lad;
+              else ld[s][2] += lad;
             } else {
               release();
             }
@@ -526,7 +532,14 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
                 ok = ok && mbar_wait_sleep(&S->dl_free[s], ph_df[s], a.status);
                 ph_df[s] ^= 1;
               }
-              S->dl_part[s][j][r_in_tile] = ld[s];
+              if (EPW == 6) {
+                S->dl_part[s][j][r_in_tile] = ld[s][0];
+              } else {
+                // this warp served role r on the passes c with (c & 3) == ((r - j - s) & 3): cell index 3 (c & 3) + r;
+                // the fourth pass residue is the one it idled on (no cell)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) S->dl_part[s][3 * ((r - j - s) & 3) + r][r_in_tile] = ld[s][r];
+              }
               __syncwarp();
               if (lane == 0) mbar_arrive(&S->dl_ready[s]);
               if (it + 1 < n_my && tile_of(it + 1, s) < a.ntiles) stage_x(it + 1, s, 0);
@@ -616,6 +629,7 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   a.bias_last = net->spline_bias;
   a.G = ceil_div(net->K[0], 128);
   a.plain_cond = (net->K[0] == net->raw_width && net->periodic_scale == 0.f) ? 1 : 0;
+  if (a.plain_cond && wide && a.K0raw % 4 == 0 && ((uintptr_t)a.cond & 15) == 0) a.plain_cond = 2;   // vector row reads
   {
     int cap = 0;
     unsigned long long* tb = tc_get_trace(&cap);

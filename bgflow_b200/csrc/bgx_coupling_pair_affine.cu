@@ -369,6 +369,7 @@ int affine_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
   a.G = ceil_div(shift->K[0], 128);
   a.alpha = expf(log_alpha);
   a.plain_cond = (shift->K[0] == shift->raw_width && shift->periodic_scale == 0.f) ? 1 : 0;
+  if (a.plain_cond && a.K0raw % 4 == 0 && ((uintptr_t)a.cond & 15) == 0) a.plain_cond = 2;   // vector row reads
   a.vec_ok = (d_t % 4 == 0 && ((uintptr_t)a.tin & 15) == 0 && ((uintptr_t)a.tout & 15) == 0) ? 1 : 0;
   a.dlogp_in = io->dlogp_in;
   a.dlogp_out = io->dlogp_out;

@@ -1,0 +1,267 @@
+// Tensor-core linear layer  Y[B, N] = X[B, K] . W^T + b  with fp32-class accuracy (training path).
+//
+// The backward of a conditioner (bgflow/nn/dense.py:47-48 differentiated; the reference leaves it to torch autograd =
+// fp32 SIMT GEMMs on a GPU, 73 % of a KL training step: profiles/r2_train_profile_fp32.txt) needs the layer GEMMs
+// again: the recompute z = h W^T + b and the input gradients dh = g W.  This kernel runs them on tcgen05 with the
+// machinery of the pair kernels (bgx_pair.cuh): one persistent CTA per SM, two 128-row tiles ("slots") ping-ponging
+// on the tensor pipe and sharing the weight ring, operands split exactly into two bf16 terms (x = x1 + x2,
+// W = w1 + w2; products x1 w1 + x2 w1 + x1 w2, fp32 accumulation in tensor memory), the A operand staged by the
+// epilogue warps straight from the fp32 rows in global memory, weight tiles by bulk TMA from the pre-swizzled layout of
+// bgx_pack_mlp.  K is k-tiled in groups of 128 inputs accumulated in tensor memory (N <= 128), or N runs in 128-column
+// passes over one staged operand (K <= 128): the two shapes the conditioner backward needs (dh2 = dP . W2: K = 825,
+// N = 128;  P = h2 . W2^T + b2: K = 128, N = 825).  Anything else returns BGX_ERR_UNSUPPORTED (callers use torch).
+//
+//   warps 0-15 epilogue / operand staging (quadrant w % 4, column share w / 4), 16 weight producer, 17 idle,
+//   18 MMA issuer, 19 idle.  TMEM: slot s at 256 s: [0,128) accumulator, [128,192) / [192,256) the two A terms.
+#include <cstdlib>
+
+#include "bgx_pair.cuh"
+
+namespace bgx {
+
+struct LinArgs {
+  long long B;
+  const float* x;     // [B][K] dense
+  float* y;           // [B][N] dense
+  int K, N;
+  DevMlp net;         // one layer: K[0], Np[0], bias[0]
+  const uint16_t* wb[2];
+  int ktiles;
+  int G, P;           // 128-input groups, 128-column passes (one of them is 1)
+  int* status;
+  long long ntiles, npairs;
+  int vec_ok, plain;
+};
+
+struct alignas(16) LinSmem {
+  uint64_t w_full[P_STAGES], w_empty[P_STAGES];
+  uint64_t a_ready[2], acc_full[2], acc_empty[2];
+  uint32_t tmem_base, pad[3];
+};
+
+__global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_constant__ LinArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = base;
+  LinSmem* S = (LinSmem*)(base + P_STAGES * P_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.G, P = a.P;
+  const int U = G + P - 1;                 // units per tile: groups accumulate into one pass, or passes over one group
+  const long long n_my = (a.npairs > blockIdx.x) ? (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) {
+      mbar_init(&S->w_full[i], 1);
+      mbar_init(&S->w_empty[i], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&S->a_ready[s], P_EPI_WARPS);
+      mbar_init(&S->acc_full[s], 1);
+      mbar_init(&S->acc_empty[s], P_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 18) tmem_alloc<512>(&S->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S->tmem_base;
+  auto tile_of = [&](long long it, int s) { return 2 * (blockIdx.x + it * (long long)gridDim.x) + s; };
+  auto slots_of = [&](long long it) { return tile_of(it, 1) < a.ntiles ? 2 : 1; };
+
+  if (warp == 16) {
+    // ------------------------------------------------------------------ weight producer (one thread)
+    if (lane == 0) {
+      uint32_t ph_e[P_STAGES] = {0, 0};
+      int stage = 0;
+      long long nfill = 0;
+      bool ok = true;
+      for (long long it = 0; it < n_my && ok; ++it)
+        for (int u = 0; u < U && ok; ++u) {
+          const int g = P == 1 ? u : 0, c = P == 1 ? 0 : u;
+          const int nt = min(2, a.ktiles - 2 * g);
+          if (nfill >= P_STAGES) {
+            ok = mbar_wait(&S->w_empty[stage], ph_e[stage], a.status);
+            ph_e[stage] ^= 1;
+            if (!ok) break;
+          }
+          uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
+          mbar_expect_tx(&S->w_full[stage], (uint32_t)nt * P_KT_BYTES);
+          for (int t = 0; t < nt; ++t) {
+            const long long src = ((long long)c * a.ktiles + 2 * g + t) * 8192;
+            bulk_g2s(dst + (size_t)t * P_KT_BYTES, a.wb[0] + src, P_TILE_BYTES, &S->w_full[stage]);
+            bulk_g2s(dst + (size_t)t * P_KT_BYTES + P_TILE_BYTES, a.wb[1] + src, P_TILE_BYTES, &S->w_full[stage]);
+          }
+          ++nfill;
+          stage ^= 1;
+        }
+    }
+    __syncwarp();
+  } else if (warp == 18) {
+    // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
+    const uint32_t idesc = idesc_bf16(128, 128);
+    int stage = 0;
+    uint32_t ph_wf[P_STAGES] = {0, 0};
+    uint32_t ph_a[2] = {0, 0}, ph_e[2] = {0, 0};
+    bool ok = true;
+    for (long long it = 0; it < n_my && ok; ++it) {
+      const int nslots = slots_of(it);
+#pragma unroll 1
+      for (int u = 0; u < U && ok; ++u) {
+        const int g = P == 1 ? u : 0;
+        const int Kg = min(128, a.K - 128 * g);
+        const int ksteps = (Kg + 15) / 16;
+        const bool wait_a = P == 1 || u == 0;                  // a freshly staged group (every group; or once per tile)
+        const bool wait_e = P == 1 ? (u == 0 && it > 0) : (u > 0 || it > 0);   // the accumulator's previous pass was stored
+        const bool accum = P == 1 && u > 0;
+        ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
+        ph_wf[stage] ^= 1;
+        const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
+#pragma unroll 1
+        for (int s = 0; s < nslots && ok; ++s) {
+          if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
+          if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t acc_addr = tmem + s * P_SLOT + P_ACC;
+          uint32_t acc = accum ? 1u : 0u;
+#pragma unroll 1
+          for (int t = 0; t * 4 < ksteps; ++t) {
+            const uint32_t b1 = sb + (uint32_t)t * P_KT_BYTES, b2 = b1 + P_TILE_BYTES;
+            const uint64_t d1 = smem_desc_sw128(b1), d2 = smem_desc_sw128(b2);
+            const uint32_t a1 = tmem + s * P_SLOT + P_A + (uint32_t)(t * 32), a2 = a1 + P_A_STRIDE;
+            const int nk = min(4, ksteps - t * 4);
+#pragma unroll 1
+            for (int ks = 0; ks < nk; ++ks)
+              mma3_bf16x3_elect(acc_addr, a1 + ks * 8, a2 + ks * 8, d1 + 2 * ks, d2 + 2 * ks, idesc, ks == 0 ? acc : 1u);
+            acc = 1;
+          }
+          mma_commit_elect(&S->acc_full[s]);
+        }
+        mma_commit_elect(&S->w_empty[stage]);
+        stage ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp < P_EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue / staging warps (0..15)
+    const int q = warp & 3, j = warp >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_acc[2] = {0, 0};
+    auto stage_x = [&](long long it, int s, int g) {
+      const long long row = tile_of(it, s) * P_TM + r_in_tile;
+      pair_stage_x(a.net, a.plain, a.x + row * (long long)a.K, row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->a_ready[s]);
+    };
+    for (long long it = 0; it < n_my; ++it) {
+      const int nslots = slots_of(it);
+      if (it == 0)
+        for (int s = 0; s < nslots; ++s) stage_x(0, s, 0);
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+#pragma unroll 1
+        for (int s = 0; s < nslots; ++s) {
+          mbar_wait(&S->acc_full[s], ph_acc[s], a.status);
+          ph_acc[s] ^= 1;
+          tc_fence_after();
+          if (P == 1 && u < G - 1) {            // group u consumed: stage the next one (the accumulator keeps summing)
+            stage_x(it, s, u + 1);
+            continue;
+          }
+          // ---- a finished pass: columns [128 c + 32 j, + 32) of this thread's row -> + bias -> global
+          const int c = P == 1 ? 0 : u;
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_base + s * P_SLOT + P_ACC + j * 32, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S->acc_empty[s]);
+          const long long row = tile_of(it, s) * P_TM + r_in_tile;
+          const int col0 = c * 128 + j * 32;
+          const int ncol = min(32, a.N - col0);
+          if (row < a.B && ncol > 0) {
+            float* yo = a.y + row * (long long)a.N + col0;
+            const float* bb = a.net.bias[0] + col0;
+            if (ncol == 32 && a.vec_ok) {
+#pragma unroll
+              for (int k = 0; k < 32; k += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb + k));
+                float4 o;
+                o.x = __uint_as_float(v[k]) + b4.x;
+                o.y = __uint_as_float(v[k + 1]) + b4.y;
+                o.z = __uint_as_float(v[k + 2]) + b4.z;
+                o.w = __uint_as_float(v[k + 3]) + b4.w;
+                *reinterpret_cast<float4*>(yo + k) = o;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (k < ncol) yo[k] = __uint_as_float(v[k]) + __ldg(bb + k);
+            }
+          }
+          // the tile's last unit: every MMA that reads its A operand is complete -> stage the next tile's first group
+          if (u == U - 1 && it + 1 < n_my && tile_of(it + 1, s) < a.ntiles) stage_x(it + 1, s, 0);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 18) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace bgx
+
+using namespace bgx;
+
+// Y[B, N] = X[B, K] . W^T + b with W, b = the single layer of `net` (bgx_pack_mlp of a one-layer bgx_mlp, dims = {K, N}).
+extern "C" int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* net, float* y, int32_t* status,
+                          void* stream) {
+  if (batch < 0 || !net || net->n_layers != 1 || (batch > 0 && (!x || !y))) return BGX_ERR_INVALID;
+  if (!net->Wb[0][0] || !net->Wb[1][0] || net->raw_width != net->K[0]) return BGX_ERR_INVALID;
+  if (batch == 0) return BGX_OK;
+  const int K = net->K[0], N = net->N[0];
+  const int G = ceil_div(K, 128), P = ceil_div(N, 128);
+  if (G > 1 && P > 1) return BGX_ERR_UNSUPPORTED;
+  LinArgs a{};
+  a.B = batch;
+  a.x = x;
+  a.y = y;
+  a.K = K;
+  a.N = N;
+  mlp_to_dev(net, a.net);
+  a.wb[0] = (const uint16_t*)net->Wb[0][0];
+  a.wb[1] = (const uint16_t*)net->Wb[1][0];
+  a.ktiles = ceil_div(K, 64);
+  a.G = G;
+  a.P = P;
+  a.status = status;
+  a.ntiles = (batch + P_TM - 1) / P_TM;
+  a.npairs = (a.ntiles + 1) / 2;
+  a.vec_ok = (N % 4 == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0;
+  a.plain = (K % 4 == 0 && ((uintptr_t)x & 15) == 0) ? 2 : 1;
+  const size_t smem = 1024 + P_STAGES * P_STAGE_BYTES + sizeof(LinSmem) + 64;
+  static int sm_count = 0;
+  int rc;
+  if (!sm_count) {
+    int dev = 0;
+    rc = check(cudaGetDevice(&dev));
+    if (rc) return rc;
+    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    rc = check(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    configured = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(a.npairs, (long long)sm_count);
+  linear_tc_kernel<<<grid, P_THREADS, smem, (cudaStream_t)stream>>>(a);
+  return post_launch();
+}

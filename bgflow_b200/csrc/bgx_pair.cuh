@@ -24,6 +24,9 @@ constexpr int P_EPW_DEFAULT = 4;     // epilogue warps per quadrant of the splin
 // tensor memory.  Out of line on purpose: three call sites, and the epilogue's hot loop has to stay inside
 // the instruction cache (the first version of this kernel inlined it everywhere and lost 27 % of its warp
 // samples to instruction fetch).  WrapPeriodic (periodic.py:30-37) through sinpi / cospi: no slow path.
+// plain_cond: 0 = through the input map (WrapPeriodic), 1 = identity map, 2 = identity map and 16-byte aligned rows whose
+// width is a multiple of 4 (four LDG.128 per half instead of sixteen scalar loads: the per-thread row reads touch one
+// line per lane and instruction, so the number of instructions is what the L1 pays for)
 static __device__ __noinline__ void pair_stage_x(const DevMlp& net, int plain_cond, const float* crow, bool live, int g, int j,
                                                  uint32_t a_col) {
   const int K0 = net.K[0];
@@ -36,7 +39,14 @@ static __device__ __noinline__ void pair_stage_x(const DevMlp& net, int plain_co
     const int b0 = kg + j * 32 + h * 16;
     if (b0 >= kend) break;
     float xv[16];
-    if (plain_cond) {
+    if (plain_cond == 2) {
+      const float4* c4 = reinterpret_cast<const float4*>(crow + b0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = (live && b0 + 4 * i < kend) ? __ldg(c4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
+      }
+    } else if (plain_cond) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) xv[i] = (live && b0 + i < kend) ? crow[b0 + i] : 0.f;
     } else {

@@ -96,7 +96,9 @@ config = {"precision": "bf16x3", "force_simt": False,
           # affine blocks: "auto" (two-CTAs-per-SM / one-CTA kernels for narrow blocks, the pair kernel for wide
           # ones), "pair" (the pair kernel wherever eligible), "no_pair"
           "affine_kernel": "auto",
-          # conditioner GEMMs of the recompute backward (training path): "fp32" (default: torch autograd on cuBLAS fp32
+          # conditioner GEMMs of the recompute backward (training path): "tcgen05" (the recompute and the input-gradient
+          # GEMMs on our own tensor-core kernel bgx_linear, exact bf16 splits = fp32-class accuracy; the weight-gradient
+          # GEMMs, whose reduction runs over the batch, stay on cuBLAS fp32), "fp32" (default: torch autograd on cuBLAS fp32
           # GEMMs, the reference's semantics), "tf32" (the same with cuBLAS TF32 tensor-core GEMMs: 2^-11 per product)
           # or "bf16x3" (explicit backward, three bf16 products of exact two-term splits with fp32 accumulation:
           # fp32-class accuracy, but cuBLAS serves bf16 -> fp32-out GEMMs of these shapes with pre-Hopper kernels and the
@@ -186,6 +188,7 @@ class PackedNet:
         self._event = None
         self._pack_stream = None
         self._seen = set()
+        self._sources = None
         self.packed = _lib.bgx_packed_mlp()
 
     @_device_guard
@@ -260,6 +263,9 @@ class PackedNet:
         self._event.record(self._pack_stream)
         self._seen = set()
         self._buf, self.packed, self._key = buf, out, key
+        # the cache key is (storage address, version): hold on to the sources so that a freed temporary's address
+        # cannot come back with other contents and alias a stale pack
+        self._sources = (list(weights), list(biases))
         return out
 
 
@@ -415,6 +421,39 @@ def split_bf16(x):
                                 _stream())
         _lib.check(rc, "bgx_split_bf16")
     return hi, lo
+
+
+class LinearTC:
+    """One linear layer ``y = x W^T + b`` on the tensor cores (``bgx_linear``; training path).  ``W`` ``[N, K]`` and
+    ``b`` ``[N]`` (or None) are packed once per (storage, version)."""
+
+    def __init__(self):
+        self._net = PackedNet()
+        self._zero = None
+
+    @_device_guard
+    def __call__(self, x, weight, bias=None):
+        lib = _lib.load()
+        require_cuda_fp32(x, weight)
+        n, k = weight.shape
+        if x.dim() != 2 or x.shape[1] != k:
+            raise ValueError("LinearTC: x must be [B, K] for a weight [N, K]")
+        if bias is None:
+            if self._zero is None or self._zero.numel() != n or self._zero.device != x.device:
+                self._zero = torch.zeros(n, dtype=torch.float32, device=x.device)
+            bias = self._zero
+        packed = self._net.refresh([weight], [bias], _lib.ACT_NONE)
+        x = x.contiguous()
+        y = torch.empty(x.shape[0], n, dtype=torch.float32, device=x.device)
+        if x.shape[0]:
+            rc = lib.bgx_linear(x.shape[0], C.c_void_p(x.data_ptr()), C.byref(packed), C.c_void_p(y.data_ptr()),
+                                C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
+            _lib.check(rc, "bgx_linear")
+        return y
+
+    @staticmethod
+    def supports(n, k):
+        return n <= 128 or k <= 128
 
 
 class ZPlan:

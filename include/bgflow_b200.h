@@ -307,6 +307,13 @@ int bgx_split_merge(int64_t batch, const bgx_seg* whole, int32_t n_parts, const 
  * kernels.  x: n floats, 16-byte aligned; hi / lo: n bf16 values each, 8-byte aligned. */
 int bgx_split_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
 
+/* Training path: Y[batch, N] = X[batch, K] . W^T + b on tcgen05 with exact two-term bf16 operand splits and fp32
+ * accumulation (fp32-class accuracy), for the layer GEMMs of the conditioner's recompute and input-gradient backward
+ * (dense.py:47-48 differentiated; the reference uses torch autograd).  `layer` = bgx_pack_mlp of a ONE-layer bgx_mlp
+ * {dims = {K, N}, W = [N, K], b = [N]}.  Supported: K <= 128 with any N, or N <= 128 with any K (else
+ * BGX_ERR_UNSUPPORTED).  x, y dense row-major; `status` (or NULL) as in the bgx_spline_cfg struct. */
+int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* layer, float* y, int32_t* status, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T

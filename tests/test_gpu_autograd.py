@@ -100,7 +100,7 @@ def test_affine_variants_backward(variant, inverse):
 
 
 @pytest.mark.parametrize("kind", ["spline", "affine"])
-@pytest.mark.parametrize("mode,tol", [("tf32", 3e-2), ("bf16x3", 3e-3)])   # (TF32: 2^-11 per product, ReLU kinks flip)
+@pytest.mark.parametrize("mode,tol", [("tf32", 3e-2), ("bf16x3", 3e-3), ("tcgen05", 3e-3)])   # (TF32: 2^-11 per product, ReLU kinks flip)
 def test_backward_gemm_modes(kind, mode, tol):
     """engine.config["backward_gemm"]: the conditioner backward on cuBLAS TF32 GEMMs, or written out explicitly with
     three bf16 tensor-core products of exact operand splits (``_mlp_grad`` + ``bgx_split_bf16``; also the hand-written
@@ -110,7 +110,7 @@ def test_backward_gemm_modes(kind, mode, tol):
     engine.config["backward_gemm"] = mode
     try:
         dim, nblk = 10, 2
-        hidden = (128, 128) if kind == "spline" else (24, 24)
+        hidden = (128, 128) if kind == "spline" or mode == "tcgen05" else (24, 24)
         blocks, split = of.make_stack(kind, dim, nblk, hidden=hidden, seed=2)
         blocks64, _ = of.make_stack(kind, dim, nblk, hidden=hidden, seed=2, dtype=torch.float64)
         flow = stack_from(blocks, split, DEV)
@@ -133,7 +133,14 @@ def test_backward_gemm_modes(kind, mode, tol):
             assert len(ours) == len(gp_ref)
             for a, b in zip(ours, gp_ref):
                 sc = max(b.abs().max().item(), 1e-6)
-                np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=1.5 * tol * sc, rtol=1.5 * tol)
+                a64 = a.cpu().double()
+                if mode == "tf32":
+                    # a TF32 pre-activation that lands on the other side of a ReLU kink switches one sample's whole
+                    # contribution to a weight on or off: allow <= 1 % such elements, everything else within tol
+                    bad = (a64 - b).abs() > 1.5 * tol * sc + 1.5 * tol * b.abs()
+                    assert bad.double().mean().item() <= 0.01, (int(bad.sum()), bad.numel())
+                else:
+                    np.testing.assert_allclose(a64.numpy(), b.numpy(), atol=1.5 * tol * sc, rtol=1.5 * tol)
             if kind == "affine":      # log_alpha is not an oracle parameter: compare with the autograd (fp32) path
                 la = [m for m in flow.modules() if isinstance(m, bg.AffineTransformer)]
                 got = [t._log_alpha.grad.clone() for t in la]

@@ -141,3 +141,28 @@ def test_out_of_domain_inputs_are_clamped_and_counted():
     x_ref, d_ref = of.coupling_stack(blocks64, z.clamp(0.0, 1.0).double(), split)
     np.testing.assert_allclose(x.cpu().double().numpy(), x_ref.numpy(), atol=2e-5, rtol=2e-5)
     np.testing.assert_allclose(d.cpu().double().numpy(), d_ref.numpy(), atol=1e-3, rtol=1e-5)
+
+
+@pytest.mark.parametrize("k,n", [(33, 128), (128, 128), (128, 825), (825, 128), (128, 33), (1536, 128), (128, 1536), (24, 24),
+                                 (7, 200)])
+@pytest.mark.parametrize("batch", [1, 300, 4096 + 3])
+def test_linear_layer_on_tensor_cores(k, n, batch):
+    """bgx_linear (training path): y = x W^T + b with exact two-term bf16 splits on tcgen05 against fp64; K k-tiled in
+    128-input groups (N <= 128) or N in 128-column passes (K <= 128); odd widths, ragged batches, odd tile counts."""
+    g = torch.Generator().manual_seed(k * 1000 + n)
+    x = torch.randn(batch, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    f = engine.LinearTC()
+    y = f(x.to(DEV), w.to(DEV), b.to(DEV))
+    scale = ref.abs().max().item()
+    np.testing.assert_allclose(y.cpu().double().numpy(), ref.numpy(), atol=3e-5 * scale, rtol=1e-4)
+    y0 = f(x.to(DEV), w.to(DEV))          # no bias
+    np.testing.assert_allclose(y0.cpu().double().numpy(), (ref - b.double()).numpy(), atol=3e-5 * scale, rtol=1e-4)
+
+
+def test_linear_layer_rejects_shapes_it_does_not_cover():
+    f = engine.LinearTC()
+    with pytest.raises(_lib.BgxError):
+        f(torch.zeros(8, 200, device=DEV), torch.zeros(300, 200, device=DEV))

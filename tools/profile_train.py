@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from bgflow_b200.distributed import BucketedGradReducer
 
+from bgflow_b200 import engine
+if os.environ.get("BGX_BACKWARD_GEMM"):
+    engine.config["backward_gemm"] = os.environ["BGX_BACKWARD_GEMM"]
 dev = torch.device("cuda:0")
 kind, dim, n_blocks, hidden, _, _ = bench.WORKLOADS["ala2_spline_d66_8blk"]
 flow = bench.build_flow(kind, dim, n_blocks, hidden, dev)
