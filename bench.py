@@ -447,7 +447,8 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     res = {}
     from bgflow_b200 import engine as _engine
     gemm_modes = {}
-    for gm in ("tcgen05", "tf32", "bf16x3"):          # the conditioner backward's GEMM variants (engine.config["backward_gemm"])
+    default_gm = _engine.backward_gemm_mode()
+    for gm in ("fp32", "tf32", "bf16x3"):             # the other conditioner-backward variants (engine.config["backward_gemm"])
         old_gm = _engine.config["backward_gemm"]
         _engine.config["backward_gemm"] = gm
         red.overlap = True
@@ -470,11 +471,13 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     out = {"samples_per_s": rows * world / (res["overlap"] * 1e-3), "ms_per_step": res["overlap"], "rows_per_gpu": rows,
            "n_gpus": world, "allreduce_fp32_elems": red.n_elements, "allreduce_bytes": 4 * red.n_elements,
            "buckets": len(red.buckets), "ms_per_step_allreduce_after_backward": res["after_backward"],
-           "ms_per_step_no_allreduce": res["no_allreduce"], "backward_gemm": "fp32 (cuBLAS)",
+           "ms_per_step_no_allreduce": res["no_allreduce"], "backward_gemm": default_gm,
            "ms_per_step_other_backward_gemm_modes": gemm_modes,
-           "what": "fused-kernel forward; backward = conditioner re-run + its GEMM backward (torch/cuBLAS fp32) + "
-                   "bgx_spline_backward kernel; one NCCL all-reduce per coupling block launched from a gradient hook "
-                   "as soon as that block's backward is done (overlaps the remaining backward); Adam"}
+           "what": "fused-kernel forward; backward = conditioner re-run (bgx_linear) + bgx_spline_backward + input "
+                   "gradients (bgx_linear) + weight / bias gradients (bgx_gemm_tn): own tcgen05 kernels, exact bf16 "
+                   "operand splits, fp32 accumulation ('fp32' = the reference's semantics: torch autograd on cuBLAS "
+                   "fp32 GEMMs); one NCCL all-reduce per coupling block launched from a gradient hook as soon as that "
+                   "block's backward is done (overlaps the remaining backward); Adam"}
     if world > 1:
         alone = res["after_backward"] - res["no_allreduce"]
         exposed = res["overlap"] - res["no_allreduce"]

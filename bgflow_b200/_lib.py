@@ -126,6 +126,9 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_split_merge": (C.c_int, [C.c_int64, P(bgx_seg), C.c_int32, P(bgx_seg), C.c_int, C.c_void_p]),
     "bgx_linear": (C.c_int, [C.c_int64, C.c_void_p, P(bgx_packed_mlp), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgx_gemm_tn_slices": (C.c_int, [C.c_int64, C.c_int]),
+    "bgx_gemm_tn": (C.c_int, [C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_split_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_tc_selftest": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),

@@ -109,8 +109,8 @@ def _versioned(cache, key, params, make):
 @torch.no_grad()
 def forward_tc(net, x):
     """``forward`` with every layer GEMM on ``bgx_linear`` (tcgen05, exact bf16 splits).  The last layer's output is
-    padded with zero columns to a multiple of 4 floats (``state["out"]`` is ``[B, pad4(N)]``, row stride = width) so
-    that the backward's operand rows are 16-byte aligned; ``state["n_out"]`` is the true width."""
+    padded with zero columns to a multiple of 4 floats so that the backward's operand rows are 16-byte aligned:
+    ``state["out_padded"]`` is ``[B, pad4(N)]``, ``state["out"]`` its first ``N = state["n_out"]`` columns."""
     lin, acts = _layers(net)
     cache = _linear_cache(net)
     hs, zs = [x], []
@@ -131,23 +131,30 @@ def forward_tc(net, x):
         zs.append(z)
         if i + 1 < len(lin):
             hs.append(_act(a, z))
-    return {"lin": lin, "acts": acts, "hs": hs, "zs": zs, "out": zs[-1], "n_out": lin[-1].weight.shape[0], "net": net}
+    n_out = lin[-1].weight.shape[0]
+    return {"lin": lin, "acts": acts, "hs": hs, "zs": zs, "out": zs[-1][:, :n_out], "out_padded": zs[-1], "n_out": n_out,
+            "net": net}
 
 
 @torch.no_grad()
 def backward_tc(state, d_out, need_dx=True):
-    """``backward`` with the input-gradient GEMMs (dh = g W) on ``bgx_linear``; the weight gradients dW = g^T h reduce
-    over the batch and stay on cuBLAS fp32.  ``d_out`` has the (padded) shape of ``state["out"]``; its pad columns
-    must be zero."""
+    """``backward`` with the input-gradient GEMMs (dh = g W) on ``bgx_linear`` and the weight / bias gradients
+    (dW = g^T h, db = sum_b g: reductions over the batch) on ``bgx_gemm_tn``.
+    ``d_out`` is ``[B, N]``, or ``[B, pad4(N)]`` (the shape of ``state["out_padded"]``) with zero pad columns."""
     lin, acts, hs, zs = state["lin"], state["acts"], state["hs"], state["zs"]
     cache = _linear_cache(state["net"])
     g = d_out
+    if g.shape[1] != zs[-1].shape[1]:
+        g = torch.nn.functional.pad(g, (0, zs[-1].shape[1] - g.shape[1]))
     grads = [None] * (2 * len(lin))
     d_x = None
     for i in range(len(lin) - 1, -1, -1):
         n = lin[i].weight.shape[0]
-        grads[2 * i] = (g.t() @ hs[i])[:n]            # dW = g^T h   [out, in]
-        grads[2 * i + 1] = g.sum(dim=0)[:n]
+        if hs[i].shape[1] <= 128:
+            grads[2 * i], grads[2 * i + 1] = engine.gemm_tn(g, hs[i], n)     # dW = g^T h [out, in], db = sum_b g
+        else:
+            grads[2 * i] = (g.t() @ hs[i])[:n]
+            grads[2 * i + 1] = g.sum(dim=0)[:n]
         if i > 0 or need_dx:
             def transposed(w=lin[i].weight, width=g.shape[1]):
                 wt = torch.zeros(w.shape[1], width, dtype=torch.float32, device=w.device)     # [in, pad4(out)]

@@ -49,7 +49,7 @@ class _FusedCoupling(torch.autograd.Function):
             else:
                 from . import engine
                 tr = [x.detach().requires_grad_(True) for x in saved[ctx.n_cond:]]
-                with _matmul_mode(engine.config.get("backward_gemm")):
+                with _matmul_mode(engine.backward_gemm_mode()):
                     out, dlogp = _torch_math.affine(t, torch.cat(cond, dim=-1), torch.cat(tr, dim=-1), ctx.inverse)
                     outs = torch.split(out, [x.shape[-1] for x in tr], dim=-1)
                     # only outputs that carry a graph and an upstream gradient: for a shift-only (NICE) or
@@ -89,7 +89,7 @@ def _affine_explicit_ok(t, params):
     """Plain RealNVP block (shift and scale DenseNets, no volume preservation / circular wrap), every parameter
     trainable: the backward below applies; anything else re-evaluates the torch definition under autograd."""
     from . import engine, _mlp_grad
-    mode = engine.config.get("backward_gemm")
+    mode = engine.backward_gemm_mode()
     if mode not in ("bf16x3", "tcgen05") or t._preserve_volume or t._is_circular:
         return False
     sh, sc = t._shift_transformation, t._scale_transformation
@@ -114,7 +114,7 @@ def _affine_backward(t, cond, tr, grads, inverse):
     g_out = torch.cat([g if g is not None else torch.zeros_like(v) for g, v in zip(grads[:-1], tr)], dim=-1).reshape(-1, d_t)
     g_dl = grads[-1].reshape(-1, 1) if grads[-1] is not None else None
     from . import engine
-    tc = engine.config.get("backward_gemm") == "tcgen05"
+    tc = engine.backward_gemm_mode() == "tcgen05"
     fwd, bwd = (_mlp_grad.forward_tc, _mlp_grad.backward_tc) if tc else (_mlp_grad.forward, _mlp_grad.backward)
     st_mu = fwd(t._shift_transformation, x2)
     st_s = fwd(t._scale_transformation, x2)
@@ -183,12 +183,12 @@ def _spline_backward(t, cond, tr, params, grads, inverse):
 
     net = t._params_net
     all_params = list(t.parameters())
-    mode = engine.config.get("backward_gemm")
+    mode = engine.backward_gemm_mode()
     all_trainable = len(params) == len(all_params) and len(all_params) == len(list(net.parameters()))
     if mode == "tcgen05" and _mlp_grad.tc_supported(net) and all_trainable:
         x = torch.cat([c.detach() for c in cond], dim=-1) if len(cond) > 1 else cond[0].detach()
         st_net = _mlp_grad.forward_tc(net, x.reshape(-1, x.shape[-1]))
-        d_p = transform_backward(st_net["out"], st_net["n_out"])
+        d_p = transform_backward(st_net["out_padded"], st_net["n_out"])
         if d_p.shape[1] > st_net["n_out"]:
             d_p[:, st_net["n_out"]:] = 0          # pad columns of the 16-byte aligned layout (never written by the kernel)
         d_x, g_params = _mlp_grad.backward_tc(st_net, d_p)
@@ -200,7 +200,7 @@ def _spline_backward(t, cond, tr, params, grads, inverse):
         g_cond = torch.split(d_x.reshape(*lead, x.shape[-1]), [c.shape[-1] for c in cond], dim=-1)
         gin = (*g_cond, *g_params)
     else:
-        with _matmul_mode(engine.config.get("backward_gemm")):
+        with _matmul_mode(engine.backward_gemm_mode()):
             p = net(torch.cat(cond, dim=-1) if len(cond) > 1 else cond[0])
             d_p = transform_backward(p.detach().reshape(-1, p.shape[-1]))
             gin = torch.autograd.grad(p, [*cond, *params], grad_outputs=d_p.reshape(p.shape), allow_unused=True)

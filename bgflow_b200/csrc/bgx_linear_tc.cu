@@ -39,6 +39,63 @@ struct alignas(16) LinSmem {
   uint32_t tmem_base, pad[3];
 };
 
+// A tcgen05.ld / .st thread owns one ROW of the tile (32 consecutive columns of it), so reading or writing global
+// memory straight from those registers touches 32 different rows per instruction: half-used sectors and, measured,
+// 6 B / cycle / SM.  Every warp therefore transposes its own [32 rows x 32 columns] block through a private patch of
+// shared memory (row stride 36 floats: the float4 accesses of both views are bank-conflict free) and talks to global
+// memory with lanes along the columns: 4 rows x 128 contiguous bytes per instruction.
+constexpr int L_TW_STRIDE = 36;
+constexpr int L_TW_FLOATS = 32 * L_TW_STRIDE;
+
+// rows [row_base, + 32) x inputs [128 g + 32 j, + 32) of x -> this lane's row -> two bf16 terms -> tensor memory
+__device__ __forceinline__ void lin_stage(const LinArgs& a, float* tw, long long row_base, int g, int j, int lane,
+                                          uint32_t a_col) {
+  const int kg = 128 * g, kend = min(a.K, kg + 128);
+  const int c0 = kg + j * 32;
+  if (c0 < kend) {
+    const int rr = lane >> 3, c4 = lane & 7;
+    if (a.plain == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rr + 4 * i;
+        const long long row = row_base + r;
+        const int col = c0 + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < a.B && col < kend) v = __ldg(reinterpret_cast<const float4*>(a.x + row * (long long)a.K + col));
+        *reinterpret_cast<float4*>(tw + r * L_TW_STRIDE + 4 * c4) = v;
+      }
+    } else {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const long long row = row_base + r;
+        const int col = c0 + lane;
+        tw[r * L_TW_STRIDE + lane] = (row < a.B && col < kend) ? __ldg(a.x + row * (long long)a.K + col) : 0.f;
+      }
+    }
+    __syncwarp();
+    float xv[32];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const float4 t = *reinterpret_cast<const float4*>(tw + lane * L_TW_STRIDE + 4 * m);
+      xv[4 * m] = t.x; xv[4 * m + 1] = t.y; xv[4 * m + 2] = t.z; xv[4 * m + 3] = t.w;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (c0 + 16 * h < kend) {      // a half is written iff the group's k-steps read it
+        uint32_t t1[8], t2[8], t3[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_bf16(xv[16 * h + 2 * i], xv[16 * h + 2 * i + 1], 2, t1[i], t2[i], t3[i]);
+        const uint32_t col = a_col + (uint32_t)((j * 32 + 16 * h) / 2);
+        tmem_st8(col, t1);
+        tmem_st8(col + P_A_STRIDE, t2);
+      }
+    }
+  }
+  tmem_st_wait();
+  tc_fence_before();
+}
+
 __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_constant__ LinArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -146,12 +203,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
   } else if (warp < P_EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue / staging warps (0..15)
     const int q = warp & 3, j = warp >> 2;
-    const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t ph_acc[2] = {0, 0};
+    float* tw = reinterpret_cast<float*>(base + P_STAGES * P_STAGE_BYTES + 256) + warp * L_TW_FLOATS;
     auto stage_x = [&](long long it, int s, int g) {
-      const long long row = tile_of(it, s) * P_TM + r_in_tile;
-      pair_stage_x(a.net, a.plain, a.x + row * (long long)a.K, row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
+      lin_stage(a, tw, tile_of(it, s) * P_TM + q * 32, g, j, lane, tmem + lane_base + s * P_SLOT + P_A);
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->a_ready[s]);
     };
@@ -178,29 +234,37 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&S->acc_empty[s]);
-          const long long row = tile_of(it, s) * P_TM + r_in_tile;
-          const int col0 = c * 128 + j * 32;
-          const int ncol = min(32, a.N - col0);
-          if (row < a.B && ncol > 0) {
-            float* yo = a.y + row * (long long)a.N + col0;
-            const float* bb = a.net.bias[0] + col0;
-            if (ncol == 32 && a.vec_ok) {
+          // transpose the warp's 32 x 32 block: lanes along the columns for the global stores
 #pragma unroll
-              for (int k = 0; k < 32; k += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bb + k));
-                float4 o;
-                o.x = __uint_as_float(v[k]) + b4.x;
-                o.y = __uint_as_float(v[k + 1]) + b4.y;
-                o.z = __uint_as_float(v[k + 2]) + b4.z;
-                o.w = __uint_as_float(v[k + 3]) + b4.w;
-                *reinterpret_cast<float4*>(yo + k) = o;
+          for (int m = 0; m < 8; ++m)
+            *reinterpret_cast<uint4*>(tw + lane * L_TW_STRIDE + 4 * m) = make_uint4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
+          __syncwarp();
+          const long long row_base = tile_of(it, s) * P_TM + q * 32;
+          const int col0 = c * 128 + j * 32;
+          if (col0 < a.N) {
+            if (a.vec_ok) {
+              const int rr = lane >> 3, col = col0 + 4 * (lane & 7);
+              if (col < a.N) {                 // N % 4 == 0: the whole float4 is inside
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.net.bias[0] + col));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int r = rr + 4 * i;
+                  float4 o = *reinterpret_cast<const float4*>(tw + r * L_TW_STRIDE + 4 * (lane & 7));
+                  o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                  if (row_base + r < a.B) *reinterpret_cast<float4*>(a.y + (row_base + r) * (long long)a.N + col) = o;
+                }
               }
             } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k)
-                if (k < ncol) yo[k] = __uint_as_float(v[k]) + __ldg(bb + k);
+              const int col = col0 + lane;
+              if (col < a.N) {
+                const float bb = __ldg(a.net.bias[0] + col);
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r)
+                  if (row_base + r < a.B) a.y[(row_base + r) * (long long)a.N + col] = tw[r * L_TW_STRIDE + lane] + bb;
+              }
             }
           }
+          __syncwarp();
           // the tile's last unit: every MMA that reads its A operand is complete -> stage the next tile's first group
           if (u == U - 1 && it + 1 < n_my && tile_of(it + 1, s) < a.ntiles) stage_x(it + 1, s, 0);
         }
@@ -245,7 +309,8 @@ extern "C" int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* n
   a.npairs = (a.ntiles + 1) / 2;
   a.vec_ok = (N % 4 == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0;
   a.plain = (K % 4 == 0 && ((uintptr_t)x & 15) == 0) ? 2 : 1;
-  const size_t smem = 1024 + P_STAGES * P_STAGE_BYTES + sizeof(LinSmem) + 64;
+  const size_t smem = 1024 + P_STAGES * P_STAGE_BYTES + 256 + P_EPI_WARPS * L_TW_FLOATS * sizeof(float) + 64;
+  static_assert(sizeof(LinSmem) <= 256, "barrier block");
   static int sm_count = 0;
   int rc;
   if (!sm_count) {

@@ -32,25 +32,42 @@ struct SplineBwdArgs {
   int root;
 };
 
-template <int MAXK>
+// VEC (K == MAXK == 8, rows of P / dP 16-byte aligned): a dim's 8 widths / heights / slopes are 32 contiguous bytes,
+// read and written as two float4 each, so every lane moves whole sectors (the scalar form touches a sector eight
+// times with 4-byte accesses; measured 1.65 TB/s on the 2 x 217 MB of a B = 65536, 33-dim block).
+template <int MAXK, bool VEC>
 __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArgs a) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.B * a.D) return;
   const long long r = idx / a.D;
   const int d = (int)(idx - r * a.D);
-  const int K = a.K, KD = a.K * a.D;
+  const int K = VEC ? 8 : a.K, KD = K * a.D;
   const float* Pr = a.P + r * a.p_stride;
   float* dPr = a.dP + r * a.p_stride;
   const int ecol = a.end_col[d];
 
   float sw[MAXK], sh[MAXK], us[MAXK + 1], cw[MAXK + 1], ch[MAXK + 1];
   float mw = -INFINITY, mh = -INFINITY;
+  if (VEC) {
+    auto load8 = [](const float* p, float* o) {
+      const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
+    };
+    load8(Pr + d * 8, sw);
+    load8(Pr + KD + d * 8, sh);
+    load8(Pr + 2 * KD + d * 8, us);
+  } else {
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
+        sw[k] = Pr[d * K + k];
+        sh[k] = Pr[KD + d * K + k];
+        us[k] = Pr[2 * KD + d * K + k];
+      }
+  }
 #pragma unroll
   for (int k = 0; k < MAXK; ++k)
     if (k < K) {
-      sw[k] = Pr[d * K + k];
-      sh[k] = Pr[KD + d * K + k];
-      us[k] = Pr[2 * KD + d * K + k];
       mw = fmaxf(mw, sw[k]);
       mh = fmaxf(mh, sh[k]);
     }
@@ -183,17 +200,35 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
   const float sg1 = Gd1 / (1.f + expf(-a.beta * u1));
   const bool end_hit = (b + 1 == K);
   const bool circular = ecol < 3 * KD;
+  float ow[MAXK], oh[MAXK], os[MAXK];
 #pragma unroll
   for (int k = 0; k < MAXK; ++k)
     if (k < K) {
       const float gw = (k < b ? kw_b : 0.f) + (k <= b ? kw_b1 : 0.f);
       const float gh = (k < b ? kh_b : 0.f) + (k <= b ? kh_b1 : 0.f);
-      dPr[d * K + k] = sw[k] * (gw - dotw);
-      dPr[KD + d * K + k] = sh[k] * (gh - doth);
+      ow[k] = sw[k] * (gw - dotw);
+      oh[k] = sh[k] * (gh - doth);
       float gs = (k == b ? sg0 : 0.f) + (k == b + 1 ? sg1 : 0.f);
       if (k == 0 && circular && end_hit) gs += sg1;
-      dPr[2 * KD + d * K + k] = gs;
+      os[k] = gs;
     }
+  if (VEC) {
+    auto store8 = [](float* p, const float* o) {
+      reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    };
+    store8(dPr + d * 8, ow);
+    store8(dPr + KD + d * 8, oh);
+    store8(dPr + 2 * KD + d * 8, os);
+  } else {
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
+        dPr[d * K + k] = ow[k];
+        dPr[KD + d * K + k] = oh[k];
+        dPr[2 * KD + d * K + k] = os[k];
+      }
+  }
   if (!circular) dPr[ecol] = end_hit ? sg1 : 0.f;
   a.dy[idx] = (yin >= a.left && yin <= a.right) ? g_x : 0.f;
 }
@@ -220,8 +255,10 @@ extern "C" int bgx_spline_backward(int64_t batch, int32_t d_t, const float* para
   const long long n = batch * (long long)d_t;
   const unsigned grid = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.K <= 8) spline_backward_kernel<8><<<grid, 256, 0, st>>>(a);
-  else if (a.K <= 16) spline_backward_kernel<16><<<grid, 256, 0, st>>>(a);
-  else spline_backward_kernel<48><<<grid, 256, 0, st>>>(a);
+  const bool vec = a.K == 8 && params_stride % 4 == 0 && (((uintptr_t)params | (uintptr_t)d_params) & 15) == 0;
+  if (vec) spline_backward_kernel<8, true><<<grid, 256, 0, st>>>(a);
+  else if (a.K <= 8) spline_backward_kernel<8, false><<<grid, 256, 0, st>>>(a);
+  else if (a.K <= 16) spline_backward_kernel<16, false><<<grid, 256, 0, st>>>(a);
+  else spline_backward_kernel<48, false><<<grid, 256, 0, st>>>(a);
   return post_launch();
 }

@@ -96,14 +96,23 @@ config = {"precision": "bf16x3", "force_simt": False,
           # affine blocks: "auto" (two-CTAs-per-SM / one-CTA kernels for narrow blocks, the pair kernel for wide
           # ones), "pair" (the pair kernel wherever eligible), "no_pair"
           "affine_kernel": "auto",
-          # conditioner GEMMs of the recompute backward (training path): "tcgen05" (the recompute and the input-gradient
-          # GEMMs on our own tensor-core kernel bgx_linear, exact bf16 splits = fp32-class accuracy; the weight-gradient
-          # GEMMs, whose reduction runs over the batch, stay on cuBLAS fp32), "fp32" (default: torch autograd on cuBLAS fp32
-          # GEMMs, the reference's semantics), "tf32" (the same with cuBLAS TF32 tensor-core GEMMs: 2^-11 per product)
-          # or "bf16x3" (explicit backward, three bf16 products of exact two-term splits with fp32 accumulation:
-          # fp32-class accuracy, but cuBLAS serves bf16 -> fp32-out GEMMs of these shapes with pre-Hopper kernels and the
-          # step gets SLOWER, 27 ms vs 20 ms — measured, profiles/r2_train_profile_bf16x3.txt)
-          "backward_gemm": "fp32"}
+          # conditioner GEMMs of the recompute backward (training path):
+          #   "auto" (default) = "tcgen05" wherever the conditioner is a plain DenseNet whose layers have <= 128
+          #       inputs or <= 128 outputs, else "fp32";
+          #   "tcgen05": recompute and input gradients on bgx_linear, weight / bias gradients on bgx_gemm_tn — our own
+          #       tensor-core kernels with exact two-term bf16 operand splits (fp32-class accuracy, fp32 accumulation);
+          #   "fp32": torch autograd on cuBLAS fp32 (SIMT) GEMMs, the reference's semantics on a GPU;
+          #   "tf32": the same with cuBLAS TF32 tensor-core GEMMs (2^-11 per product);
+          #   "bf16x3": explicit backward on cuBLAS bf16 GEMMs of the split operands (fp32-class accuracy, but cuBLAS
+          #       serves bf16 -> fp32-out GEMMs of these shapes with pre-Hopper kernels and the step gets SLOWER,
+          #       27 ms vs 20 ms — measured, profiles/r2_train_profile_bf16x3.txt)
+          "backward_gemm": "auto"}
+
+
+def backward_gemm_mode():
+    """``config["backward_gemm"]`` with "auto" resolved."""
+    mode = config.get("backward_gemm", "auto")
+    return "tcgen05" if mode == "auto" else mode
 
 _status = {}
 
@@ -454,6 +463,35 @@ class LinearTC:
     @staticmethod
     def supports(n, k):
         return n <= 128 or k <= 128
+
+
+@_device_guard
+def gemm_tn(g, h, n=None):
+    """Weight gradient of a linear layer on the tensor cores (``bgx_gemm_tn``; training path):
+    ``dW = g[:, :n]^T h`` ``[n, K]`` and ``db = g[:, :n].sum(0)`` for ``g`` ``[B, >= n]`` (row stride free),
+    ``h`` ``[B, K]``, ``K <= 128``.  The kernel writes one partial per batch slice; they are added here in a fixed
+    order."""
+    lib = _lib.load()
+    require_cuda_fp32(g, h)
+    if g.dim() != 2 or h.dim() != 2 or g.shape[0] != h.shape[0] or g.stride(1) != 1 or h.stride(1) != 1:
+        raise ValueError("gemm_tn: g [B, N] and h [B, K] with unit column stride")
+    n = g.shape[1] if n is None else int(n)
+    B, k = h.shape
+    if k > 128 or n > g.shape[1]:
+        raise ValueError("gemm_tn: K <= 128 and n <= g.shape[1]")
+    if B == 0:
+        return g.new_zeros(n, k), g.new_zeros(n)
+    slices = lib.bgx_gemm_tn_slices(B, n)
+    if slices <= 0:
+        raise RuntimeError("bgx_gemm_tn_slices failed (no CUDA device?)")
+    rows = (n + 127) // 128 * 128
+    part_w = torch.empty(slices, rows, 128, dtype=torch.float32, device=g.device)
+    part_b = torch.empty(slices, rows, dtype=torch.float32, device=g.device)
+    rc = lib.bgx_gemm_tn(B, C.c_void_p(g.data_ptr()), g.stride(0), n, C.c_void_p(h.data_ptr()), h.stride(0), k, slices,
+                         C.c_void_p(part_w.data_ptr()), C.c_void_p(part_b.data_ptr()),
+                         C.c_void_p(pipeline_status(g.device).data_ptr()), _stream())
+    _lib.check(rc, "bgx_gemm_tn")
+    return part_w.sum(dim=0)[:n, :k], part_b.sum(dim=0)[:n]
 
 
 class ZPlan:

@@ -314,6 +314,17 @@ int bgx_split_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
  * BGX_ERR_UNSUPPORTED).  x, y dense row-major; `status` (or NULL) as in the bgx_spline_cfg struct. */
 int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* layer, float* y, int32_t* status, void* stream);
 
+/* Weight gradient of a layer on the tensor cores (same operand splits): the batch-reduced products
+ *   dW[n, k] = sum_b g[b, n] h[b, k]   and   db[n] = sum_b g[b, n]        (k <= 128, any n; else BGX_ERR_UNSUPPORTED)
+ * g = [batch, n] with row stride ldg, h = [batch, k] with row stride ldh (floats).  The batch is cut into `slices`
+ * (= bgx_gemm_tn_slices(batch, n)) contiguous ranges; every range writes its own partial sums
+ *   part_w[slices][128 ceil(n / 128)][128]   and   part_b[slices][128 ceil(n / 128)]   (part_b may be NULL),
+ * which the caller adds up over the first index (fixed order = reproducible gradients); rows >= n and columns >= k
+ * of the partials are zero. */
+int bgx_gemm_tn_slices(int64_t batch, int n);
+int bgx_gemm_tn(int64_t batch, const float* g, int64_t ldg, int n, const float* h, int64_t ldh, int k, int slices,
+                float* part_w, float* part_b, int32_t* status, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T

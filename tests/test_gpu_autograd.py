@@ -100,11 +100,13 @@ def test_affine_variants_backward(variant, inverse):
 
 
 @pytest.mark.parametrize("kind", ["spline", "affine"])
-@pytest.mark.parametrize("mode,tol", [("tf32", 3e-2), ("bf16x3", 3e-3), ("tcgen05", 3e-3)])   # (TF32: 2^-11 per product, ReLU kinks flip)
+@pytest.mark.parametrize("mode,tol", [("fp32", 3e-3), ("tf32", 3e-2), ("bf16x3", 3e-3), ("tcgen05", 3e-3)])   # (TF32: 2^-11 per product, ReLU kinks flip)
 def test_backward_gemm_modes(kind, mode, tol):
-    """engine.config["backward_gemm"]: the conditioner backward on cuBLAS TF32 GEMMs, or written out explicitly with
-    three bf16 tensor-core products of exact operand splits (``_mlp_grad`` + ``bgx_split_bf16``; also the hand-written
-    affine backward) — both against the fp64 oracle (fp32 cuBLAS is the default the other tests cover)."""
+    """engine.config["backward_gemm"]: the conditioner backward through torch autograd on cuBLAS fp32 or TF32 GEMMs, or
+    written out explicitly with three bf16 tensor-core products of exact operand splits — on cuBLAS (``bf16x3``:
+    ``_mlp_grad`` + ``bgx_split_bf16``) or on our own kernels (``tcgen05``: ``bgx_linear`` + ``bgx_gemm_tn``, what the
+    default "auto" resolves to and the other tests cover); also the hand-written affine backward.  All against the
+    fp64 oracle."""
     from bgflow_b200 import engine
     old = engine.config["backward_gemm"]
     engine.config["backward_gemm"] = mode

@@ -166,3 +166,33 @@ def test_linear_layer_rejects_shapes_it_does_not_cover():
     f = engine.LinearTC()
     with pytest.raises(_lib.BgxError):
         f(torch.zeros(8, 200, device=DEV), torch.zeros(300, 200, device=DEV))
+
+
+@pytest.mark.parametrize("batch,n,k,ldg", [(1, 5, 7, 5), (70, 5, 128, 8), (1000, 128, 10, 128), (4097, 300, 33, 300),
+                                           (8192 + 5, 825, 128, 828), (65536, 513, 128, 513), (200, 1100, 64, 1100)])
+def test_weight_gradient_on_tensor_cores(batch, n, k, ldg):
+    """bgx_gemm_tn (training path): dW = g^T h and db = sum_b g, reduced over the batch on tcgen05 with exact two-term
+    bf16 splits, against fp64; ragged batches, feature counts off the 128 / 8 grid, padded row strides (pad columns
+    hold garbage the kernel must not read), one to three feature-tile groups."""
+    gen = torch.Generator().manual_seed(batch + 7 * n + k)
+    gbuf = torch.randn(batch, ldg, generator=gen)
+    h = torch.randn(batch, k, generator=gen)
+    g = gbuf[:, :n]
+    ref_w = g.double().t() @ h.double()
+    ref_b = g.double().sum(0)
+    gd = gbuf.to(DEV)
+    if ldg > n:
+        gd[:, n:] = float("nan")
+    dw, db = engine.gemm_tn(gd, h.to(DEV), n)
+    assert dw.shape == (n, k) and db.shape == (n,)
+    # products carry 2^-17 relative error each (the dropped g2 h2 term), sums run in fp32
+    sw = (g.double().abs().t() @ h.double().abs()).max().item()
+    np.testing.assert_allclose(dw.cpu().double().numpy(), ref_w.numpy(), atol=3e-5 * sw, rtol=0)
+    np.testing.assert_allclose(db.cpu().double().numpy(), ref_b.numpy(), atol=1e-5 * g.double().abs().sum(0).max().item(), rtol=0)
+    dw2, db2 = engine.gemm_tn(gd, h.to(DEV), n)          # fixed summation order: reproducible
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+def test_weight_gradient_rejects_wide_inputs():
+    with pytest.raises(ValueError):
+        engine.gemm_tn(torch.zeros(8, 16, device=DEV), torch.zeros(8, 200, device=DEV))
