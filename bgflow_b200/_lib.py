@@ -49,6 +49,17 @@ class bgx_packed_mlp(C.Structure):
                 ("spline_bias", C.c_void_p), ("spline_bias_pad", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class bgx_train_mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (BGX_MAX_LAYERS + 1)), ("act", C.c_int32 * BGX_MAX_LAYERS),
+                ("fwd", bgx_packed_mlp * BGX_MAX_LAYERS), ("bwd", bgx_packed_mlp * BGX_MAX_LAYERS),
+                ("total_floats", C.c_int64)]
+
+
+class bgx_train_buffers(C.Structure):
+    _fields_ = [("z", C.c_void_p * BGX_MAX_LAYERS), ("h", C.c_void_p * BGX_MAX_LAYERS), ("g", C.c_void_p * BGX_MAX_LAYERS),
+                ("part", C.c_void_p)]
+
+
 class bgx_spline_layout(C.Structure):
     _fields_ = [("d_t", C.c_int32), ("n_bins", C.c_int32), ("is_circular", C.POINTER(C.c_uint8))]
 
@@ -126,6 +137,11 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_split_merge": (C.c_int, [C.c_int64, P(bgx_seg), C.c_int32, P(bgx_seg), C.c_int, C.c_void_p]),
     "bgx_linear": (C.c_int, [C.c_int64, C.c_void_p, P(bgx_packed_mlp), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgx_train_pack": (C.c_int, [P(bgx_mlp), P(C.c_int32), C.c_void_p, C.c_int64, P(bgx_train_mlp), C.c_void_p]),
+    "bgx_mlp_train_part_floats": (C.c_int64, [C.c_int64, P(bgx_train_mlp)]),
+    "bgx_mlp_forward_train": (C.c_int, [C.c_int64, P(bgx_train_mlp), C.c_void_p, P(bgx_train_buffers), C.c_void_p, C.c_void_p]),
+    "bgx_mlp_backward": (C.c_int, [C.c_int64, P(bgx_train_mlp), C.c_void_p, P(bgx_train_buffers), C.c_void_p, C.c_void_p,
+                                   P(C.c_void_p), P(C.c_void_p), C.c_void_p, C.c_void_p]),
     "bgx_gemm_tn_slices": (C.c_int, [C.c_int64, C.c_int]),
     "bgx_gemm_tn": (C.c_int, [C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -82,92 +82,37 @@ def _act_grad(mod, z, g):
     return g
 
 
-def _linear_cache(net):
-    c = net.__dict__.get("_bgx_linear_tc")
-    if c is None:
-        c = net.__dict__["_bgx_linear_tc"] = {}
-    return c
-
-
 def _tc_ok(lin):
     return all(engine.LinearTC.supports(*l.weight.shape) for l in lin)
 
 
-def _pad4(n):
-    return (n + 3) // 4 * 4
-
-
-def _versioned(cache, key, params, make):
-    """``make()`` once per version of ``params`` (cached under ``key``)."""
-    ver = tuple((p.data_ptr(), p._version) for p in params)
-    ent = cache.get(key)
-    if ent is None or ent[0] != ver:
-        ent = cache[key] = (ver, make())
-    return ent[1]
+def _train_net(net):
+    lin, acts = _layers(net)
+    tn = net.__dict__.get("_bgx_train_net")
+    if tn is None:
+        tn = net.__dict__["_bgx_train_net"] = engine.TrainNet()
+    tn.refresh([l.weight for l in lin], [l.bias for l in lin], [engine._ACT_CODES[type(a)] for a in acts])
+    return tn, lin
 
 
 @torch.no_grad()
 def forward_tc(net, x):
-    """``forward`` with every layer GEMM on ``bgx_linear`` (tcgen05, exact bf16 splits).  The last layer's output is
-    padded with zero columns to a multiple of 4 floats so that the backward's operand rows are 16-byte aligned:
-    ``state["out_padded"]`` is ``[B, pad4(N)]``, ``state["out"]`` its first ``N = state["n_out"]`` columns."""
-    lin, acts = _layers(net)
-    cache = _linear_cache(net)
-    hs, zs = [x], []
-    for i, (l, a) in enumerate(zip(lin, acts)):
-        f = cache.setdefault(("fwd", i), engine.LinearTC())
-        n = l.weight.shape[0]
-        if i + 1 == len(lin) and n % 4:
-            def padded(l=l, n=n):
-                w = torch.zeros(_pad4(n), l.weight.shape[1], dtype=torch.float32, device=l.weight.device)
-                w[:n] = l.weight.detach()
-                b = torch.zeros(_pad4(n), dtype=torch.float32, device=l.weight.device)
-                b[:n] = l.bias.detach()
-                return w, b
-            w, b = _versioned(cache, ("fwd_pad", i), (l.weight, l.bias), padded)
-        else:
-            w, b = l.weight.detach(), l.bias.detach()
-        z = f(hs[-1], w, b)
-        zs.append(z)
-        if i + 1 < len(lin):
-            hs.append(_act(a, z))
-    n_out = lin[-1].weight.shape[0]
-    return {"lin": lin, "acts": acts, "hs": hs, "zs": zs, "out": zs[-1][:, :n_out], "out_padded": zs[-1], "n_out": n_out,
-            "net": net}
+    """``forward`` on our own tensor-core kernels, the whole net in one host call (``engine.TrainNet.forward`` =
+    ``bgx_mlp_forward_train``: ``bgx_linear`` per layer, exact bf16 operand splits).  Every buffer is padded with zero
+    columns to a multiple of 4 floats so that rows are 16-byte aligned: ``state["out_padded"]`` is
+    ``[B, pad4(N)]``, ``state["out"]`` its first ``N = state["n_out"]`` columns."""
+    tn, lin = _train_net(net)
+    state = tn.forward(x)
+    state["net"], state["tn"], state["lin"] = net, tn, lin
+    return state
 
 
 @torch.no_grad()
 def backward_tc(state, d_out, need_dx=True):
-    """``backward`` with the input-gradient GEMMs (dh = g W) on ``bgx_linear`` and the weight / bias gradients
-    (dW = g^T h, db = sum_b g: reductions over the batch) on ``bgx_gemm_tn``.
-    ``d_out`` is ``[B, N]``, or ``[B, pad4(N)]`` (the shape of ``state["out_padded"]``) with zero pad columns."""
-    lin, acts, hs, zs = state["lin"], state["acts"], state["hs"], state["zs"]
-    cache = _linear_cache(state["net"])
-    g = d_out
-    if g.shape[1] != zs[-1].shape[1]:
-        g = torch.nn.functional.pad(g, (0, zs[-1].shape[1] - g.shape[1]))
-    grads = [None] * (2 * len(lin))
-    d_x = None
-    for i in range(len(lin) - 1, -1, -1):
-        n = lin[i].weight.shape[0]
-        if hs[i].shape[1] <= 128:
-            grads[2 * i], grads[2 * i + 1] = engine.gemm_tn(g, hs[i], n)     # dW = g^T h [out, in], db = sum_b g
-        else:
-            grads[2 * i] = (g.t() @ hs[i])[:n]
-            grads[2 * i + 1] = g.sum(dim=0)[:n]
-        if i > 0 or need_dx:
-            def transposed(w=lin[i].weight, width=g.shape[1]):
-                wt = torch.zeros(w.shape[1], width, dtype=torch.float32, device=w.device)     # [in, pad4(out)]
-                wt[:, :w.shape[0]] = w.detach().t()
-                return wt
-            wt = _versioned(cache, ("wt", i), (lin[i].weight,), transposed)
-            f = cache.setdefault(("dx", i), engine.LinearTC())
-            gh = f(g, wt)                             # dh = g W     [B, in]  (a layer with weight W^T)
-            if i > 0:
-                g = _act_grad(acts[i - 1], zs[i - 1], gh)
-            else:
-                d_x = gh
-    return d_x, grads
+    """``backward`` in one host call (``bgx_mlp_backward``): the input gradients dh = g W on ``bgx_linear``, the weight
+    and bias gradients dW = g^T h, db = sum_b g (reductions over the batch) on ``bgx_gemm_tn``.  ``d_out`` is
+    ``[B, N]``, or ``[B, pad4(N)]`` (the shape of ``state["out_padded"]``) with zero pad columns."""
+    return state["tn"].backward(state, d_out, need_dx)
 
 
 @torch.no_grad()

@@ -21,9 +21,10 @@ namespace bgx {
 
 struct LinArgs {
   long long B;
-  const float* x;     // [B][K] dense
-  float* y;           // [B][N] dense
-  int K, N;
+  const float* x;     // [B][K], row stride ldx
+  float* y;           // [B][N], row stride ldy
+  long long ldx, ldy;
+  int K, N;           // inputs read, outputs written (N may exceed the layer's width up to its padded width: zeros)
   DevMlp net;         // one layer: K[0], Np[0], bias[0]
   const uint16_t* wb[2];
   int ktiles;
@@ -61,7 +62,7 @@ __device__ __forceinline__ void lin_stage(const LinArgs& a, float* tw, long long
         const long long row = row_base + r;
         const int col = c0 + 4 * c4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < a.B && col < kend) v = __ldg(reinterpret_cast<const float4*>(a.x + row * (long long)a.K + col));
+        if (row < a.B && col < kend) v = __ldg(reinterpret_cast<const float4*>(a.x + row * a.ldx + col));
         *reinterpret_cast<float4*>(tw + r * L_TW_STRIDE + 4 * c4) = v;
       }
     } else {
@@ -69,7 +70,7 @@ __device__ __forceinline__ void lin_stage(const LinArgs& a, float* tw, long long
       for (int r = 0; r < 32; ++r) {
         const long long row = row_base + r;
         const int col = c0 + lane;
-        tw[r * L_TW_STRIDE + lane] = (row < a.B && col < kend) ? __ldg(a.x + row * (long long)a.K + col) : 0.f;
+        tw[r * L_TW_STRIDE + lane] = (row < a.B && col < kend) ? __ldg(a.x + row * a.ldx + col) : 0.f;
       }
     }
     __syncwarp();
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
                   const int r = rr + 4 * i;
                   float4 o = *reinterpret_cast<const float4*>(tw + r * L_TW_STRIDE + 4 * (lane & 7));
                   o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                  if (row_base + r < a.B) *reinterpret_cast<float4*>(a.y + (row_base + r) * (long long)a.N + col) = o;
+                  if (row_base + r < a.B) *reinterpret_cast<float4*>(a.y + (row_base + r) * a.ldy + col) = o;
                 }
               }
             } else {
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
                 const float bb = __ldg(a.net.bias[0] + col);
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r)
-                  if (row_base + r < a.B) a.y[(row_base + r) * (long long)a.N + col] = tw[r * L_TW_STRIDE + lane] + bb;
+                  if (row_base + r < a.B) a.y[(row_base + r) * a.ldy + col] = tw[r * L_TW_STRIDE + lane] + bb;
               }
             }
           }
@@ -283,19 +284,25 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
 
 using namespace bgx;
 
-// Y[B, N] = X[B, K] . W^T + b with W, b = the single layer of `net` (bgx_pack_mlp of a one-layer bgx_mlp, dims = {K, N}).
-extern "C" int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* net, float* y, int32_t* status,
-                          void* stream) {
+namespace bgx {
+// Y[:, :n_out] = X[:, :K] . W^T + b for the single layer of `net`; x / y row strides ldx / ldy (floats).  n_out may
+// exceed the layer's width N up to its padded width (the extra columns are written as zeros: packed rows and bias
+// beyond N are zero) — the training drivers keep every width a multiple of 4 floats that way.
+int linear_launch(int64_t batch, const float* x, int64_t ldx, const bgx_packed_mlp* net, float* y, int64_t ldy, int n_out,
+                  int32_t* status, cudaStream_t stream) {
   if (batch < 0 || !net || net->n_layers != 1 || (batch > 0 && (!x || !y))) return BGX_ERR_INVALID;
   if (!net->Wb[0][0] || !net->Wb[1][0] || net->raw_width != net->K[0]) return BGX_ERR_INVALID;
+  const int K = net->K[0], N = n_out;
+  if (N < 1 || N > net->Np[0] || ldx < K || ldy < N) return BGX_ERR_INVALID;
   if (batch == 0) return BGX_OK;
-  const int K = net->K[0], N = net->N[0];
   const int G = ceil_div(K, 128), P = ceil_div(N, 128);
   if (G > 1 && P > 1) return BGX_ERR_UNSUPPORTED;
   LinArgs a{};
   a.B = batch;
   a.x = x;
   a.y = y;
+  a.ldx = ldx;
+  a.ldy = ldy;
   a.K = K;
   a.N = N;
   mlp_to_dev(net, a.net);
@@ -307,8 +314,9 @@ extern "C" int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* n
   a.status = status;
   a.ntiles = (batch + P_TM - 1) / P_TM;
   a.npairs = (a.ntiles + 1) / 2;
-  a.vec_ok = (N % 4 == 0 && ((uintptr_t)y & 15) == 0) ? 1 : 0;
-  a.plain = (K % 4 == 0 && ((uintptr_t)x & 15) == 0) ? 2 : 1;
+  a.vec_ok = (N % 4 == 0 && ldy % 4 == 0 && (((uintptr_t)y | (uintptr_t)net->bias[0]) & 15) == 0) ? 1 : 0;
+  // vector row reads: float4 loads may run past K inside the row's padding (ldx >= round_up(K, 4): zero weights there)
+  a.plain = (ldx % 4 == 0 && ldx >= round_up(K, 4) && ((uintptr_t)x & 15) == 0) ? 2 : 1;
   const size_t smem = 1024 + P_STAGES * P_STAGE_BYTES + 256 + P_EPI_WARPS * L_TW_FLOATS * sizeof(float) + 64;
   static_assert(sizeof(LinSmem) <= 256, "barrier block");
   static int sm_count = 0;
@@ -327,6 +335,14 @@ extern "C" int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* n
     configured = true;
   }
   const unsigned grid = (unsigned)std::min<long long>(a.npairs, (long long)sm_count);
-  linear_tc_kernel<<<grid, P_THREADS, smem, (cudaStream_t)stream>>>(a);
+  linear_tc_kernel<<<grid, P_THREADS, smem, stream>>>(a);
   return post_launch();
+}
+}  // namespace bgx
+
+// Y[B, N] = X[B, K] . W^T + b with W, b = the single layer of `net` (bgx_pack_mlp of a one-layer bgx_mlp, dims = {K, N}).
+extern "C" int bgx_linear(int64_t batch, const float* x, const bgx_packed_mlp* net, float* y, int32_t* status,
+                          void* stream) {
+  if (!net || net->n_layers != 1) return BGX_ERR_INVALID;
+  return bgx::linear_launch(batch, x, net->K[0], net, y, net->N[0], net->N[0], status, (cudaStream_t)stream);
 }

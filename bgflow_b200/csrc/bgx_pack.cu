@@ -59,6 +59,63 @@ __global__ void pack_tc_tiles_kernel(const float* __restrict__ W, const int* __r
   t3[off] = b3;
 }
 
+// The same tiles (two terms) from a strided source: element (n, k) of the layer's weight is W[n * rs + k * cs], so
+// that the TRANSPOSED layer (dx = g W: a layer with weight W^T) is packed straight from nn.Linear.weight
+// (rs = 1, cs = K of the source).  Rows n >= N and inputs k >= K are zero.
+__global__ void pack_tc_tiles_strided_kernel(const float* __restrict__ W, long long rs, long long cs, int K, int N,
+                                             int ktiles, int Np, unsigned short* __restrict__ t1,
+                                             unsigned short* __restrict__ t2) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Np * ktiles * 64;
+  if (idx >= total) return;
+  int k = (int)(idx % (ktiles * 64)), n = (int)(idx / (ktiles * 64));
+  float w = (n < N && k < K) ? W[n * rs + k * cs] : 0.f;
+  unsigned short b1 = f32_to_bf16_rn(w);
+  float r1 = w - __uint_as_float((unsigned int)b1 << 16);
+  unsigned short b2 = f32_to_bf16_rn(r1);
+  int chunk = n >> 7, nr = n & 127, t = k >> 6, kk = k & 63;
+  long long off = ((long long)chunk * ktiles + t) * 8192 + (nr * 64 + ((((kk >> 3) ^ (nr & 7)) << 3) | (kk & 7)));
+  t1[off] = b1;
+  t2[off] = b2;
+}
+__global__ void pack_bias_kernel(const float* __restrict__ b, int N, int Np, float* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < Np) out[n] = (b && n < N) ? b[n] : 0.f;
+}
+
+// One plain linear layer for the tensor-core kernels only (bgx_linear / the training drivers): two bf16 terms + bias.
+long long pack_linear_floats(int K, int N) {
+  const long long kp64 = round_up(K, 64), Np = round_up(N, 128);
+  return ((kp64 * Np + Np) + 255) / 256 * 256;      // 2 terms x kp64 x Np bf16 = kp64 x Np floats, then the bias
+}
+int pack_linear(const float* W, long long rs, long long cs, const float* bias, int K, int N, float* dst, bgx_packed_mlp* out,
+                cudaStream_t st) {
+  if (!W || !dst || K < 1 || N < 1 || ((uintptr_t)dst & 255) != 0) return BGX_ERR_INVALID;
+  bgx_packed_mlp pk{};
+  pk.n_layers = 1;
+  pk.act = BGX_ACT_NONE;
+  pk.K[0] = K; pk.N[0] = N;
+  pk.Kp[0] = round_up(K, 16); pk.Np[0] = round_up(N, 128);
+  pk.raw_width = K;
+  const int kp64 = round_up(K, 64), Np = pk.Np[0];
+  unsigned short* t1 = reinterpret_cast<unsigned short*>(dst);
+  unsigned short* t2 = t1 + (long long)kp64 * Np;
+  float* bb = dst + (long long)kp64 * Np;
+  const long long total = (long long)kp64 * Np;
+  pack_tc_tiles_strided_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(W, rs, cs, K, N, kp64 / 64, Np, t1, t2);
+  int rc = post_launch();
+  if (rc) return rc;
+  pack_bias_kernel<<<(Np + 255) / 256, 256, 0, st>>>(bias, N, Np, bb);
+  rc = post_launch();
+  if (rc) return rc;
+  pk.Wb[0][0] = t1;
+  pk.Wb[1][0] = t2;
+  pk.bias[0] = bb;
+  pk.total_floats = pack_linear_floats(K, N);
+  *out = pk;
+  return BGX_OK;
+}
+
 // last-layer bias of a spline net once more, 16-byte aligned per dim: [pass][dim][pad]
 __global__ void pack_bias_pad_kernel(const float* __restrict__ bias, int npass, int dpp, int ps, int pad,
                                      float* __restrict__ out) {

@@ -465,6 +465,140 @@ class LinearTC:
         return n <= 128 or k <= 128
 
 
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class TrainNet:
+    """Training-path state of one conditioner (a plain ``DenseNet``): its layers packed for the tensor-core linear
+    kernel — forward and transposed (``bgx_train_pack``), cached on parameter versions — plus the two host calls that
+    run its whole recompute (``bgx_mlp_forward_train``) and its whole backward (``bgx_mlp_backward``)."""
+
+    def __init__(self):
+        self._key = None
+        self._buf = None
+        self._event = None
+        self._pack_stream = None
+        self._seen = set()
+        self._sources = None
+        self.packed = _lib.bgx_train_mlp()
+        self.dims = None
+
+    @_device_guard
+    def refresh(self, weights, biases, act_codes):
+        key = tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in zip(weights, biases))
+        key = (key, tuple(act_codes), weights[0].device)
+        if key == self._key:
+            cur = torch.cuda.current_stream(weights[0].device)
+            if cur != self._pack_stream and cur not in self._seen:
+                cur.wait_event(self._event)
+                self._seen.add(cur)
+            return self.packed
+        lib = _lib.load()
+        require_cuda_fp32(*weights, *biases)
+        n = len(weights)
+        if n > _lib.BGX_MAX_LAYERS:
+            raise NotImplementedError(f"at most {_lib.BGX_MAX_LAYERS} Linear layers per conditioner")
+        ws = [w.detach().contiguous() for w in weights]
+        bs = [b.detach().contiguous() for b in biases]
+        src = _lib.bgx_mlp()
+        src.n_layers = n
+        src.dims[0] = ws[0].shape[1]
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            if w.shape[1] != src.dims[i] or b.shape[0] != w.shape[0]:
+                raise ValueError("inconsistent DenseNet layer shapes")
+            src.dims[i + 1] = w.shape[0]
+            src.W[i] = w.data_ptr()
+            src.b[i] = b.data_ptr()
+        src.raw_width = src.dims[0]
+        acts = (C.c_int32 * max(n - 1, 1))(*[int(a) for a in act_codes[:n - 1]])
+        out = _lib.bgx_train_mlp()
+        rc = lib.bgx_train_pack(C.byref(src), acts, None, 0, C.byref(out), None)
+        _lib.check(rc, "bgx_train_pack(size)")
+        buf = torch.empty(int(out.total_floats), dtype=torch.float32, device=ws[0].device)
+        rc = lib.bgx_train_pack(C.byref(src), acts, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(out), _stream())
+        _lib.check(rc, "bgx_train_pack")
+        if self._buf is not None:
+            for st in self._seen:
+                self._buf.record_stream(st)
+        self._pack_stream = torch.cuda.current_stream(ws[0].device)
+        self._event = torch.cuda.Event()
+        self._event.record(self._pack_stream)
+        self._seen = set()
+        self._buf, self.packed, self._key = buf, out, key
+        self._sources = (ws, bs, list(weights), list(biases))
+        self.dims = [int(src.dims[i]) for i in range(n + 1)]
+        return out
+
+    @_device_guard
+    def forward(self, x):
+        """Recompute on ``x`` ``[B, dims[0]]``.  Returns the state ``backward`` needs; ``state["out_padded"]`` is the net's
+        output ``[B, pad4(dims[-1])]`` (zero pad columns), ``state["out"]`` its first ``dims[-1]`` columns."""
+        lib = _lib.load()
+        require_cuda_fp32(x)
+        x = x.contiguous()
+        B, dims = x.shape[0], self.dims
+        L = len(dims) - 1
+        widths = [_pad4(d) for d in dims[1:]]
+        part = int(lib.bgx_mlp_train_part_floats(B, C.byref(self.packed))) if B else 0
+        # one allocation: z_i, then h_i and g_i of the hidden layers, then the weight-gradient partials
+        sizes = [B * w for w in widths] + [B * w for w in widths[:-1]] * 2 + [part]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
+        views, off = [], 0
+        for sz in sizes:
+            views.append(flat[off:off + sz])
+            off += sz
+        bufs = _lib.bgx_train_buffers()
+        for i in range(L):
+            bufs.z[i] = views[i].data_ptr()
+            if i + 1 < L:
+                bufs.h[i] = views[L + i].data_ptr()
+                bufs.g[i] = views[2 * L - 1 + i].data_ptr()
+        bufs.part = views[-1].data_ptr()
+        if B:
+            rc = lib.bgx_mlp_forward_train(B, C.byref(self.packed), C.c_void_p(x.data_ptr()), C.byref(bufs),
+                                           C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
+            _lib.check(rc, "bgx_mlp_forward_train")
+        out_padded = views[L - 1].view(B, widths[-1])
+        return {"x": x, "flat": flat, "bufs": bufs, "out_padded": out_padded, "out": out_padded[:, :dims[-1]],
+                "n_out": dims[-1], "packed": self.packed, "dims": dims}
+
+    @_device_guard
+    def backward(self, state, d_out, need_dx=True):
+        """``d_out`` ``[B, dims[-1]]`` or ``[B, pad4(dims[-1])]`` with zero pad columns.  Returns ``(d_x or None,
+        [dW_0, db_0, dW_1, db_1, ...])``."""
+        lib = _lib.load()
+        x, dims = state["x"], state["dims"]
+        B, L = x.shape[0], len(dims) - 1
+        wl = _pad4(dims[-1])
+        if d_out.shape[1] != wl:
+            d_out = torch.nn.functional.pad(d_out, (0, wl - d_out.shape[1]))
+        d_out = d_out.contiguous()
+        sizes = []
+        for i in range(L):
+            sizes += [dims[i + 1] * dims[i], dims[i + 1]]
+        sizes = [(s + 3) // 4 * 4 for s in sizes]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device) if B else \
+            torch.zeros(sum(sizes), dtype=torch.float32, device=x.device)
+        grads, off = [], 0
+        d_w = (C.c_void_p * L)()
+        d_b = (C.c_void_p * L)()
+        for i in range(L):
+            w = flat[off:off + dims[i + 1] * dims[i]].view(dims[i + 1], dims[i])
+            off += sizes[2 * i]
+            b = flat[off:off + dims[i + 1]]
+            off += sizes[2 * i + 1]
+            d_w[i], d_b[i] = w.data_ptr(), b.data_ptr()
+            grads += [w, b]
+        d_x = torch.empty(B, dims[0], dtype=torch.float32, device=x.device) if need_dx else None
+        if B:
+            rc = lib.bgx_mlp_backward(B, C.byref(state["packed"]), C.c_void_p(x.data_ptr()), C.byref(state["bufs"]),
+                                      C.c_void_p(d_out.data_ptr()), C.c_void_p(d_x.data_ptr()) if need_dx else None,
+                                      d_w, d_b, C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
+            _lib.check(rc, "bgx_mlp_backward")
+        return d_x, grads
+
+
 @_device_guard
 def gemm_tn(g, h, n=None):
     """Weight gradient of a linear layer on the tensor cores (``bgx_gemm_tn``; training path):

@@ -325,6 +325,40 @@ int bgx_gemm_tn_slices(int64_t batch, int n);
 int bgx_gemm_tn(int64_t batch, const float* g, int64_t ldg, int n, const float* h, int64_t ldh, int k, int slices,
                 float* part_w, float* part_b, int32_t* status, void* stream);
 
+/* ---- training path: a conditioner's recompute and backward as one call each ------------------------
+ * (dense.py:10-48 under torch autograd in the reference.)  bgx_train_pack lays every layer out twice for bgx_linear's
+ * kernel: as y = x W^T + b (fwd) and transposed, dx = g W (bwd), straight from nn.Linear.weight.  Supported: every
+ * layer has <= 128 inputs or <= 128 outputs (else BGX_ERR_UNSUPPORTED); no WrapPeriodic (n_periodic == 0).
+ * `act` = n_layers - 1 activation codes (between the layers) or NULL for src->act everywhere. */
+typedef struct bgx_train_mlp {
+  int32_t n_layers;
+  int32_t dims[BGX_MAX_LAYERS + 1];       /* true widths */
+  int32_t act[BGX_MAX_LAYERS];            /* activation after layer i (BGX_ACT_NONE after the last) */
+  bgx_packed_mlp fwd[BGX_MAX_LAYERS];
+  bgx_packed_mlp bwd[BGX_MAX_LAYERS];
+  int64_t total_floats;
+} bgx_train_mlp;
+/* dst == NULL: size query (out->total_floats). */
+int bgx_train_pack(const bgx_mlp* src, const int32_t* act, float* dst, int64_t dst_floats, bgx_train_mlp* out,
+                   void* stream);
+
+/* Caller-owned device buffers of one recompute + backward.  pad4(n) = n rounded up to a multiple of 4. */
+typedef struct bgx_train_buffers {
+  float* z[BGX_MAX_LAYERS];   /* [batch, pad4(dims[i + 1])] pre-activations of layer i; z[n_layers - 1] = the net's output */
+  float* h[BGX_MAX_LAYERS];   /* [batch, pad4(dims[i + 1])] act(z[i]), i < n_layers - 1 */
+  float* g[BGX_MAX_LAYERS];   /* [batch, pad4(dims[i + 1])] gradient wrt z[i], i < n_layers - 1 (scratch) */
+  float* part;                /* bgx_mlp_train_part_floats(batch, net) floats (scratch of the weight gradients) */
+} bgx_train_buffers;
+int64_t bgx_mlp_train_part_floats(int64_t batch, const bgx_train_mlp* net);
+
+/* Recompute: fills buf->z[*] and buf->h[*] from x [batch, dims[0]] (dense).  Pad columns come out as zeros. */
+int bgx_mlp_forward_train(int64_t batch, const bgx_train_mlp* net, const float* x, const bgx_train_buffers* buf,
+                          int32_t* status, void* stream);
+/* Backward from d_out [batch, pad4(dims[n_layers])] (pad columns must be zero) with the buffers of the recompute:
+ * d_w[i] [dims[i + 1], dims[i]] and d_b[i] [dims[i + 1]] (dense, overwritten), d_x [batch, dims[0]] or NULL. */
+int bgx_mlp_backward(int64_t batch, const bgx_train_mlp* net, const float* x, const bgx_train_buffers* buf,
+                     const float* d_out, float* d_x, float* const* d_w, float* const* d_b, int32_t* status, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T
