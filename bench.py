@@ -661,7 +661,7 @@ def main():
             prior = (bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)) if kind == "spline"
                      else bg.NormalDistribution(dim)).to(dev)
             pipe = HostPipeline(flow, dim_in=dim, dim_out=dim, max_rows=B, device=dev, prior=prior,
-                                chunk_rows=int(os.environ.get("BGX_E2E_CHUNK", 1 << 17)),
+                                chunk_rows=int(os.environ.get("BGX_E2E_CHUNK", 0)) or None,     # default: 3 full waves
                                 n_streams=int(os.environ.get("BGX_E2E_STREAMS", 3)))
             for _ in range(args.warmup):
                 pipe.run(z_host)
@@ -669,7 +669,8 @@ def main():
             h2d, d2h = B * dim * 4, B * dim * 4 + B * 4            # per GPU per step
             e2e = {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s",
                    "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
-                   "ms_per_step": ms_e2e / args.steps, "api": "bgflow_b200.host.HostPipeline.run (pinned host in/out)"}
+                   "ms_per_step": ms_e2e / args.steps, "api": "bgflow_b200.host.HostPipeline.run (pinned host in/out)",
+                   "chunk_rows": pipe.chunk, "streams": len(pipe.streams)}
             # what the host <-> device link gives THIS rank while every rank copies both ways at once
             barrier()
             cc = copy_ceiling(dev)

@@ -72,6 +72,18 @@ __device__ __forceinline__ void mma3_bf16x3_ss_elect(uint32_t d_tmem, uint64_t a
 __device__ __forceinline__ void load_slab(float (&v)[16], const float* __restrict__ src, long long ld, int ncols, int col,
                                           long long row0, long long B, int wq) {
   const bool cok = col < ncols;
+  if (cok && row0 + 64 <= B) {
+    // whole slab inside the batch (all but the last batch tile): one base pointer, one multiply-add per load — the
+    // converters are bound by the instructions they issue, and the guarded form below costs ~12 integer
+    // instructions per load
+    const float* p = src + (row0 + 8 * wq) * ld + col;
+    const int ldi = (int)ld;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * u + i] = __ldg(p + (32 * u + i) * ldi);
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const long long c0 = row0 + 8 * (wq + 4 * u);
@@ -306,7 +318,7 @@ extern "C" int bgx_gemm_tn_slices(int64_t batch, int n) {
 extern "C" int bgx_gemm_tn(int64_t batch, const float* g, int64_t ldg, int n, const float* h, int64_t ldh, int k,
                            int slices, float* part_w, float* part_b, int32_t* status, void* stream) {
   if (batch <= 0 || n <= 0 || k <= 0 || !g || !h || !part_w || ldg < n || ldh < k) return BGX_ERR_INVALID;
-  if (k > 128) return BGX_ERR_UNSUPPORTED;
+  if (k > 128 || ldg > (1 << 24) || ldh > (1 << 24)) return BGX_ERR_UNSUPPORTED;
   TnArgs a{};
   a.B = batch;
   a.g = g; a.ldg = ldg; a.N = n;

@@ -20,7 +20,7 @@ import os
 
 import torch
 
-__all__ = ["HostPipeline", "bind_to_gpu_numa", "copy_ceiling"]
+__all__ = ["HostPipeline", "bind_to_gpu_numa", "copy_ceiling", "wave_rows"]
 
 
 def _parse_cpulist(text):
@@ -94,12 +94,23 @@ def copy_ceiling(device, nbytes=256 << 20, reps=4):
     return out
 
 
+def wave_rows(device, waves=3):
+    """Rows of ``waves`` full waves of the fused coupling kernels: one persistent CTA per SM working on two 128-row
+    tiles at a time, so a launch of 256 x SMs x waves rows keeps every SM busy to the end (a 2^17-row chunk is 3.46
+    waves on 148 SMs: the fourth one runs half empty, 13 % of the launch)."""
+    sms = torch.cuda.get_device_properties(torch.device(device)).multi_processor_count
+    return 256 * sms * int(waves)
+
+
 class HostPipeline:
-    def __init__(self, flow, dim_in, dim_out, max_rows, device, chunk_rows=1 << 17, n_streams=3,
+    def __init__(self, flow, dim_in, dim_out, max_rows, device, chunk_rows=None, n_streams=3,
                  inverse=False, prior=None, with_energy=False):
         self.flow = flow
         self.device = torch.device(device)
-        self.chunk = int(chunk_rows)
+        self.chunk = int(chunk_rows) if chunk_rows else wave_rows(self.device)
+        # the first chunk's host->device copy and the last chunk's device->host copy overlap nothing: start and end
+        # with short chunks (one, then two waves) when the batch is long enough and the chunking is the default
+        self.ramp = wave_rows(self.device, 1) if not chunk_rows else 0
         self.inverse = inverse
         self.prior = prior
         self.with_energy = with_energy
@@ -108,6 +119,23 @@ class HostPipeline:
         self.dlogp = torch.empty(max_rows, 1, dtype=torch.float32).pin_memory()
         self.energy = torch.empty(max_rows, 1, dtype=torch.float32).pin_memory() if with_energy else None
         self.dim_in = dim_in
+
+    def _ranges(self, B):
+        """Row ranges of the chunks of a batch of B rows."""
+        w = self.ramp
+        if w and B >= 6 * w + self.chunk:
+            sizes = [w, 2 * w]
+            mid = B - 6 * w
+            sizes += [self.chunk] * (mid // self.chunk)
+            if mid % self.chunk:
+                sizes.append(mid % self.chunk)
+            sizes += [2 * w, w]
+        else:
+            sizes = [self.chunk] * (B // self.chunk) + ([B % self.chunk] if B % self.chunk else [])
+        lo = 0
+        for n in sizes:
+            yield lo, lo + n
+            lo += n
 
     def _fan_out(self):
         cur = torch.cuda.current_stream(self.device)
@@ -128,8 +156,7 @@ class HostPipeline:
         if B > self.out.shape[0] or z_host.shape[1] != self.dim_in:
             raise ValueError("input does not fit the pipeline's buffers")
         cur = self._fan_out()
-        for n, lo in enumerate(range(0, B, self.chunk)):
-            hi = min(B, lo + self.chunk)
+        for n, (lo, hi) in enumerate(self._ranges(B)):
             s = self.streams[n % len(self.streams)]
             with torch.cuda.stream(s):
                 x = z_host[lo:hi].to(self.device, non_blocking=True)
@@ -150,8 +177,7 @@ class HostPipeline:
         if B > self.out.shape[0]:
             raise ValueError("n_samples does not fit the pipeline's buffers")
         cur = self._fan_out()
-        for n, lo in enumerate(range(0, B, self.chunk)):
-            hi = min(B, lo + self.chunk)
+        for n, (lo, hi) in enumerate(self._ranges(B)):
             s = self.streams[n % len(self.streams)]
             with torch.cuda.stream(s):
                 z = self.prior.sample(hi - lo, temperature=temperature)

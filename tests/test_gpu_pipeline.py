@@ -96,3 +96,28 @@ def test_config4_energy_direction_round_trip():
         assert float(e.median()) < 1e-5 and float(e.quantile(0.99)) < tol, (u.shape, float(e.max()))
     s = (dlogp + dinv).abs()
     assert float(s.median()) < 1e-3 and float(s.quantile(0.99)) < 5e-2
+
+
+@pytest.mark.parametrize("chunk", [None, 1000, 4096])
+def test_host_pipeline_matches_one_device_call(chunk):
+    """HostPipeline.run / .sample (pinned host buffers, chunks on a ring of streams — what bench.py's e2e number
+    times) give the rows a single device-side call gives, whatever the chunking; the default chunk is a whole number
+    of kernel waves."""
+    from bgflow_b200.host import HostPipeline, wave_rows
+    dim, rows = 10, 5000
+    blocks, split = of.make_stack("spline", dim, 2, hidden=(128, 128), seed=5)
+    from helpers import stack_from
+    flow = stack_from(blocks, split, DEV)
+    prior = bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)).to(DEV)
+    pipe = HostPipeline(flow, dim, dim, rows, DEV, chunk_rows=chunk, prior=prior, with_energy=True)
+    assert pipe.chunk == (chunk or wave_rows(DEV)) and wave_rows(DEV) % 256 == 0
+    z = torch.rand(rows, dim, generator=torch.Generator().manual_seed(0)).pin_memory()
+    x, d = pipe.run(z)
+    with torch.no_grad():
+        x_ref, d_ref = flow(z.to(DEV))
+    assert torch.equal(x, x_ref.cpu()) and torch.equal(d, d_ref.cpu())          # rows are independent: bit-exact
+    xs, ds, es = pipe.sample(rows)
+    assert xs.shape == (rows, dim) and ds.shape == (rows, 1) and es.shape == (rows, 1)
+    assert torch.isfinite(xs).all() and torch.isfinite(es).all()
+    with pytest.raises(ValueError):
+        pipe.run(torch.zeros(rows + 1, dim))
