@@ -661,7 +661,7 @@ def main():
             prior = (bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)) if kind == "spline"
                      else bg.NormalDistribution(dim)).to(dev)
             pipe = HostPipeline(flow, dim_in=dim, dim_out=dim, max_rows=B, device=dev, prior=prior,
-                                chunk_rows=int(os.environ.get("BGX_E2E_CHUNK", 0)) or None,     # default: 3 full waves
+                                chunk_rows=int(os.environ.get("BGX_E2E_CHUNK", 0)) or None,     # default: 4 full waves
                                 n_streams=int(os.environ.get("BGX_E2E_STREAMS", 3)))
             for _ in range(args.warmup):
                 pipe.run(z_host)

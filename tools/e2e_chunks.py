@@ -20,7 +20,7 @@ z = torch.rand(B, dim).pin_memory()
 prior = bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)).to(dev)
 w = wave_rows(dev, 1)
 for streams in (3, 4):
-    for chunk in (None, 3 * w, 1 << 17, 4 * w, None, 3 * w):        # None = default: 3 waves with short first / last chunks
+    for chunk in (None, 2 * w, 3 * w, 1 << 17, 4 * w, 6 * w):        # None = default (4 waves)
         pipe = HostPipeline(flow, dim, dim, B, dev, chunk_rows=chunk, n_streams=streams, prior=prior)
         chunk = chunk or -pipe.chunk
         for _ in range(3):
