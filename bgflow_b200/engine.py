@@ -135,6 +135,8 @@ def _poll_pipeline_status(device, every=64):
     """Asynchronous check on the product path: every ``every`` tensor-core launches the flag is copied to
     pinned host memory on the launch stream; the copy issued at the PREVIOUS poll is inspected (if it has
     completed) — no host synchronisation, and a pipeline timeout surfaces as an exception at most two polls later."""
+    if torch.cuda.is_current_stream_capturing():
+        return                          # inside a CUDA graph capture (host.HostPipeline): the graph's owner reads the flag
     key = torch.device(device)
     st = _poll.get(key)
     if st is None:

@@ -104,37 +104,82 @@ def wave_rows(device, waves=4):
 
 
 class HostPipeline:
+    """``use_graph``: the whole call — every chunk's copies and kernels on the ring of streams — is captured into ONE
+    CUDA graph the second time it is made with the same host buffer and row count, and replayed from then on: a
+    replay is one launch for the host instead of ~10 per coupling block and chunk, so the chunks can be short (the
+    un-overlapped first copy in / last copy out shrink with them) without the host becoming the bottleneck."""
+
     def __init__(self, flow, dim_in, dim_out, max_rows, device, chunk_rows=None, n_streams=3,
-                 inverse=False, prior=None, with_energy=False):
+                 inverse=False, prior=None, with_energy=False, use_graph=True):
         self.flow = flow
         self.device = torch.device(device)
-        self.chunk = int(chunk_rows) if chunk_rows else wave_rows(self.device)
+        self.chunk = int(chunk_rows) if chunk_rows else wave_rows(self.device, 2 if use_graph else 4)
+        self.chunk_eager = int(chunk_rows) if chunk_rows else wave_rows(self.device, 4)
         self.inverse = inverse
         self.prior = prior
         self.with_energy = with_energy
+        self.use_graph = use_graph
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         self.out = torch.empty(max_rows, dim_out, dtype=torch.float32).pin_memory()
         self.dlogp = torch.empty(max_rows, 1, dtype=torch.float32).pin_memory()
         self.energy = torch.empty(max_rows, 1, dtype=torch.float32).pin_memory() if with_energy else None
         self.dim_in = dim_in
+        self._status = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._graphs, self._warm = {}, set()
 
-    def _ranges(self, B):
+    def _flow_version(self):
+        """A graph holds the addresses of the packed parameters it was captured with: a parameter update (or move)
+        must not replay it."""
+        return tuple((p.data_ptr(), p._version) for p in self.flow.parameters())
+
+    def _ranges(self, B, chunk):
         """Row ranges of the chunks of a batch of B rows.  (Uniform chunks: starting and ending with one- and
-        two-wave chunks to shorten the un-overlapped first copy in / last copy out was measured SLOWER, 10.1 vs
-        9.3 ms per 2^20 rows — a one-wave chunk is 0.26 ms of kernels, less than the host needs to issue it.)"""
-        for lo in range(0, B, self.chunk):
-            yield lo, min(B, lo + self.chunk)
+        two-wave chunks to shorten the un-overlapped first copy in / last copy out was measured SLOWER without graphs,
+        10.1 vs 9.3 ms per 2^20 rows — a one-wave chunk is 0.26 ms of kernels, less than the host needs to issue it.)"""
+        for lo in range(0, B, chunk):
+            yield lo, min(B, lo + chunk)
 
-    def _fan_out(self):
+    def _issue(self, body, B, chunk):
+        """Fan out to the ring of streams, ``body(lo, hi)`` per chunk, fan in; the kernels' status flag comes back
+        with the results."""
+        from . import engine
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             s.wait_stream(cur)
-        return cur
-
-    def _fan_in(self, cur):
+        for n, (lo, hi) in enumerate(self._ranges(B, chunk)):
+            with torch.cuda.stream(self.streams[n % len(self.streams)]):
+                body(lo, hi)
         for s in self.streams:
             cur.wait_stream(s)
-        cur.synchronize()          # the results are host memory: the call returns them complete
+        self._status.copy_(engine.pipeline_status(self.device), non_blocking=True)
+
+    def _launch(self, key, body, B):
+        """``key`` None: always eager."""
+        with torch.cuda.device(self.device):
+            use_graph = self.use_graph and key is not None
+            g = self._graphs.get(key) if use_graph else None
+            if g is not None:
+                g.replay()
+            elif use_graph and key in self._warm:
+                # second call with this key: everything lazy (packs, kernel attributes, allocator pools) is warm
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._issue(body, B, self.chunk)
+                while len(self._graphs) >= 4:          # every graph owns the device buffers of its chunks
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = g
+                g.replay()
+            else:
+                if use_graph:
+                    if len(self._warm) > 64:
+                        self._warm.clear()
+                    self._warm.add(key)
+                self._issue(body, B, self.chunk if use_graph else self.chunk_eager)
+            torch.cuda.current_stream(self.device).synchronize()      # the results are host memory: return them complete
+        if int(self._status[0]) != 0:
+            from . import _lib
+            raise _lib.BgxError("tensor-core coupling kernel reported an internal pipeline timeout")
 
     @torch.no_grad()
     def run(self, z_host):
@@ -143,15 +188,16 @@ class HostPipeline:
         B = z_host.shape[0]
         if B > self.out.shape[0] or z_host.shape[1] != self.dim_in:
             raise ValueError("input does not fit the pipeline's buffers")
-        cur = self._fan_out()
-        for n, (lo, hi) in enumerate(self._ranges(B)):
-            s = self.streams[n % len(self.streams)]
-            with torch.cuda.stream(s):
-                x = z_host[lo:hi].to(self.device, non_blocking=True)
-                y, d = self.flow(x, inverse=self.inverse)
-                self.out[lo:hi].copy_(y, non_blocking=True)
-                self.dlogp[lo:hi].copy_(d, non_blocking=True)
-        self._fan_in(cur)
+
+        def body(lo, hi):
+            x = z_host[lo:hi].to(self.device, non_blocking=True)
+            y, d = self.flow(x, inverse=self.inverse)
+            self.out[lo:hi].copy_(y, non_blocking=True)
+            self.dlogp[lo:hi].copy_(d, non_blocking=True)
+
+        # a graph holds the ADDRESS of the host buffer: key on it (and only capture pinned, contiguous inputs)
+        key = ("run", z_host.data_ptr(), B, self._flow_version()) if z_host.is_pinned() and z_host.is_contiguous() else None
+        self._launch(key, body, B)
         return self.out[:B], self.dlogp[:B]
 
     @torch.no_grad()
@@ -164,17 +210,18 @@ class HostPipeline:
         B = int(n_samples)
         if B > self.out.shape[0]:
             raise ValueError("n_samples does not fit the pipeline's buffers")
-        cur = self._fan_out()
-        for n, (lo, hi) in enumerate(self._ranges(B)):
-            s = self.streams[n % len(self.streams)]
-            with torch.cuda.stream(s):
-                z = self.prior.sample(hi - lo, temperature=temperature)
-                y, d = self.flow(z, temperature=temperature)
-                self.out[lo:hi].copy_(y, non_blocking=True)
-                self.dlogp[lo:hi].copy_(d, non_blocking=True)
-                if self.with_energy:
-                    self.energy[lo:hi].copy_(self.prior.energy(z, temperature=temperature) + d, non_blocking=True)
-        self._fan_in(cur)
+
+        def body(lo, hi):
+            z = self.prior.sample(hi - lo, temperature=temperature)
+            y, d = self.flow(z, temperature=temperature)
+            self.out[lo:hi].copy_(y, non_blocking=True)
+            self.dlogp[lo:hi].copy_(d, non_blocking=True)
+            if self.with_energy:
+                self.energy[lo:hi].copy_(self.prior.energy(z, temperature=temperature) + d, non_blocking=True)
+
+        # eager: replays of a graph that draws from the torch generator were measured erratic (12 - 250 ms per 2^20
+        # rows against 9.4 ms eager), so the sampling call keeps 4-wave chunks issued from the host
+        self._launch(None, body, B)
         if self.with_energy:
             return self.out[:B], self.dlogp[:B], self.energy[:B]
         return self.out[:B], self.dlogp[:B]

@@ -98,26 +98,46 @@ def test_config4_energy_direction_round_trip():
     assert float(s.median()) < 1e-3 and float(s.quantile(0.99)) < 5e-2
 
 
+@pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("chunk", [None, 1000, 4096])
-def test_host_pipeline_matches_one_device_call(chunk):
+def test_host_pipeline_matches_one_device_call(chunk, graph):
     """HostPipeline.run / .sample (pinned host buffers, chunks on a ring of streams — what bench.py's e2e number
-    times) give the rows a single device-side call gives, whatever the chunking; the default chunk is a whole number
-    of kernel waves."""
+    times) give the rows a single device-side call gives, whatever the chunking, eagerly and as a replayed CUDA graph;
+    the default chunk is a whole number of kernel waves."""
     from bgflow_b200.host import HostPipeline, wave_rows
     dim, rows = 10, 5000
     blocks, split = of.make_stack("spline", dim, 2, hidden=(128, 128), seed=5)
     from helpers import stack_from
     flow = stack_from(blocks, split, DEV)
     prior = bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)).to(DEV)
-    pipe = HostPipeline(flow, dim, dim, rows, DEV, chunk_rows=chunk, prior=prior, with_energy=True)
-    assert pipe.chunk == (chunk or wave_rows(DEV)) and wave_rows(DEV) % 256 == 0
+    pipe = HostPipeline(flow, dim, dim, rows, DEV, chunk_rows=chunk, prior=prior, with_energy=True, use_graph=graph)
+    assert pipe.chunk == (chunk or wave_rows(DEV, 2 if graph else 4)) and wave_rows(DEV) % 256 == 0
     z = torch.rand(rows, dim, generator=torch.Generator().manual_seed(0)).pin_memory()
-    x, d = pipe.run(z)
     with torch.no_grad():
         x_ref, d_ref = flow(z.to(DEV))
-    assert torch.equal(x, x_ref.cpu()) and torch.equal(d, d_ref.cpu())          # rows are independent: bit-exact
-    xs, ds, es = pipe.sample(rows)
-    assert xs.shape == (rows, dim) and ds.shape == (rows, 1) and es.shape == (rows, 1)
-    assert torch.isfinite(xs).all() and torch.isfinite(es).all()
+    for call in range(4):             # eager, capture + replay, replay, replay on changed host data
+        if call == 3:
+            z.copy_(torch.rand(rows, dim, generator=torch.Generator().manual_seed(1)))
+            with torch.no_grad():
+                x_ref, d_ref = flow(z.to(DEV))
+        x, d = pipe.run(z)
+        assert torch.equal(x, x_ref.cpu()) and torch.equal(d, d_ref.cpu())      # rows are independent: bit-exact
+    assert (len(pipe._graphs) == 1) == graph
+    seen = []
+    for call in range(3):
+        xs, ds, es = pipe.sample(rows)
+        assert xs.shape == (rows, dim) and ds.shape == (rows, 1) and es.shape == (rows, 1)
+        assert torch.isfinite(xs).all() and torch.isfinite(es).all()
+        assert all(not torch.equal(xs, prev) for prev in seen)                  # every call draws new prior samples
+        seen.append(xs.clone())
+    with torch.no_grad():             # a parameter update invalidates the captured graph
+        for p in flow.parameters():
+            p.mul_(1.01)
+        x_ref, d_ref = flow(z.to(DEV))
+    for call in range(3):
+        x, d = pipe.run(z)
+        assert torch.equal(x, x_ref.cpu()) and torch.equal(d, d_ref.cpu())
+    x2, d2 = pipe.run(z.clone())      # an unpinned buffer: no graph, same rows
+    assert torch.equal(x2, x_ref.cpu())
     with pytest.raises(ValueError):
         pipe.run(torch.zeros(rows + 1, dim))

@@ -19,10 +19,9 @@ B = 1 << 20
 z = torch.rand(B, dim).pin_memory()
 prior = bg.UniformDistribution(torch.zeros(dim), torch.ones(dim)).to(dev)
 w = wave_rows(dev, 1)
-for streams in (3, 4):
-    for chunk in (None, 2 * w, 3 * w, 1 << 17, 4 * w, 6 * w):        # None = default (4 waves)
-        pipe = HostPipeline(flow, dim, dim, B, dev, chunk_rows=chunk, n_streams=streams, prior=prior)
-        chunk = chunk or -pipe.chunk
+for streams, graph in ((3, False), (3, True), (4, True), (2, True)):
+    for chunk in (w, 2 * w, 3 * w, 4 * w, 1 << 17):
+        pipe = HostPipeline(flow, dim, dim, B, dev, chunk_rows=chunk, n_streams=streams, prior=prior, use_graph=graph)
         for _ in range(3):
             pipe.run(z)
         torch.cuda.synchronize()
@@ -39,5 +38,5 @@ for streams in (3, 4):
         e1.record()
         torch.cuda.synchronize()
         ms_s = e0.elapsed_time(e1) / 10
-        print(f"streams {streams} chunk {chunk:7d} ({chunk / w:5.2f} waves): run {ms:6.2f} ms = {B / ms / 1e3:6.1f} M/s   sample {ms_s:6.2f} ms = {B / ms_s / 1e3:6.1f} M/s", flush=True)
+        print(f"graph {int(graph)} streams {streams} chunk {chunk:7d} ({chunk / w:5.2f} waves): run {ms:6.2f} ms = {B / ms / 1e3:6.1f} M/s   sample {ms_s:6.2f} ms = {B / ms_s / 1e3:6.1f} M/s", flush=True)
         del pipe
