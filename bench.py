@@ -468,16 +468,22 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
             fn()
         res[mode] = run_timed(fn, steps) / steps
     red.remove()
-    out = {"samples_per_s": rows * world / (res["overlap"] * 1e-3), "ms_per_step": res["overlap"], "rows_per_gpu": rows,
+    red.overlap = "auto"
+    policy = "overlap" if red._overlapping() else "after_backward"      # the reducer's default for gradients of this size
+    out = {"samples_per_s": rows * world / (res[policy] * 1e-3), "ms_per_step": res[policy], "rows_per_gpu": rows,
            "n_gpus": world, "allreduce_fp32_elems": red.n_elements, "allreduce_bytes": 4 * red.n_elements,
-           "buckets": len(red.buckets), "ms_per_step_allreduce_after_backward": res["after_backward"],
+           "allreduce_mode": policy + " (BucketedGradReducer default for this gradient size)",
+           "buckets": len(red.buckets), "ms_per_step_allreduce_overlapped": res["overlap"],
+           "ms_per_step_allreduce_after_backward": res["after_backward"],
            "ms_per_step_no_allreduce": res["no_allreduce"], "backward_gemm": default_gm,
            "ms_per_step_other_backward_gemm_modes": gemm_modes,
            "what": "fused-kernel forward; backward = conditioner re-run (bgx_linear) + bgx_spline_backward + input "
                    "gradients (bgx_linear) + weight / bias gradients (bgx_gemm_tn): own tcgen05 kernels, exact bf16 "
                    "operand splits, fp32 accumulation ('fp32' = the reference's semantics: torch autograd on cuBLAS "
-                   "fp32 GEMMs); one NCCL all-reduce per coupling block launched from a gradient hook as soon as that "
-                   "block's backward is done (overlaps the remaining backward); Adam"}
+                   "fp32 GEMMs); gradients of all blocks are views of one flat buffer: all-reduced with ONE NCCL "
+                   "collective after the backward (default below 64 MB), or per coupling block from gradient hooks "
+                   "while the rest of the backward runs (also timed: with 4 MB it loses, NCCL's CTAs take SMs from "
+                   "the persistent one-CTA-per-SM kernels); Adam"}
     if world > 1:
         alone = res["after_backward"] - res["no_allreduce"]
         exposed = res["overlap"] - res["no_allreduce"]
@@ -488,6 +494,7 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line only
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -164,7 +164,9 @@ class HostPipeline:
                 # second call with this key: everything lazy (packs, kernel attributes, allocator pools) is warm
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: other threads of the process (the NCCL watchdog of a multi-GPU job polls events) may
+                # make CUDA calls while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._issue(body, B, self.chunk)
                 while len(self._graphs) >= 4:          # every graph owns the device buffers of its chunks
                     self._graphs.pop(next(iter(self._graphs)))

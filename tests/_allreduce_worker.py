@@ -29,6 +29,8 @@ assert err < 1e-6, err
 net2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
 net2.load_state_dict(net.state_dict())
 red = bd.BucketedGradReducer(net2, bucket_modules=[net2[2], net2[0]], average=False)
+assert red.overlap == "auto" and not red._overlapping()       # a few hundred bytes: one collective after the backward
+red.overlap = True
 for step in range(2):                      # twice: the buckets are reused, gradients must not pile up
     red.zero_grad()
     (net2(full[lo:hi]).pow(2).sum() / 16).backward()
@@ -37,6 +39,13 @@ for step in range(2):                      # twice: the buckets are reused, grad
     assert n2 == n and err2 < 1e-6, (step, n2, err2)
 assert red.launched == 4, red.launched     # 2 buckets x 2 steps, each launched from a hook during backward
 assert all(p.grad.data_ptr() >= b["flat"].data_ptr() for b in red.buckets[:1] for p in net2[2].parameters())
+# the default for small gradients: nothing launched from the hooks, ONE all-reduce of the whole flat buffer in finish()
+red.overlap = "auto"
+red.zero_grad()
+(net2(full[lo:hi]).pow(2).sum() / 16).backward()
+assert red.finish() == n and red.launched == 4
+err3 = max((p.grad - q.grad).abs().max().item() for p, q in zip(net2.parameters(), ref.parameters()))
+assert err3 < 1e-6, err3
 if rank == 0:
     print(f"ALLREDUCE_OK world={world} elements={n} err={err:.2e} bucketed_err={err2:.2e}")
 dist.destroy_process_group()
