@@ -493,8 +493,22 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     return out
 
 
+_JSON_OUT = None
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line only
+    # stdout carries the ONE JSON line only: everything a library prints to file descriptor 1 (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, ...) goes to stderr; the line itself is written to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -549,7 +563,7 @@ def main():
             t_full = sum(time_cpu_port(blocks, kind, dim, rows, nchunk, threads))
             full = {"rows": nchunk * rows, "chunks": nchunk, "seconds": t_full, "value": nchunk * rows / t_full,
                     "unit": "samples/s"}
-        print(json.dumps({
+        _emit(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -589,7 +603,7 @@ def main():
         time.sleep(0.01 * (rank + 1))
         el = max_over_ranks(time.perf_counter() - t0)
         if rank == 0:
-            print(json.dumps({"metric": metric, "value": B * world * args.steps / el, "unit": "samples/s",
+            _emit(json.dumps({"metric": metric, "value": B * world * args.steps / el, "unit": "samples/s",
                               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "dryrun": True,
                               "scaling": "weak", "shard_rows": rows, "config": config}))
         if world > 1:
@@ -761,7 +775,7 @@ def main():
         if rank == 0:
             out["kl_train"] = tr
     if rank == 0:
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
