@@ -22,6 +22,26 @@ inline int post_launch() {
   return check(cudaPeekAtLastError());
 }
 
+// cudaFuncSetAttribute, occupancy figures and the SM count are properties of (function, DEVICE): the launch helpers
+// keep their once-flags per device, indexed by device_slot() (one process may drive several GPUs through the Python
+// mirror's device guard).
+constexpr int BGX_MAX_DEVICES = 64;
+inline int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= BGX_MAX_DEVICES) d = 0;
+  return d;
+}
+inline int device_sm_count(int* out) {
+  static int n[BGX_MAX_DEVICES] = {};
+  const int d = device_slot();
+  if (!n[d]) {
+    int rc = check(cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d));
+    if (rc) return rc;
+  }
+  *out = n[d];
+  return BGX_OK;
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

@@ -656,15 +656,9 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   a.ntiles = (a.B + P_TM - 1) / P_TM;
   a.npairs = (a.ntiles + 1) / 2;
   const size_t smem = pair_smem_bytes(net, d_t, a.K0raw, wide);
-  static int sm_count = 0;
-  int rc;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
+  int sm_count = 0;
+  int rc = device_sm_count(&sm_count);
+  if (rc) return rc;
   using KernT = void (*)(const PArgs);
 #define BGX_P_ROW(INV, W, E) \
   {spline_coupling_pair_kernel<INV, 0, W, E>, spline_coupling_pair_kernel<INV, 1, W, E>, \
@@ -677,7 +671,8 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   static const int epw6 = [] { const char* e = getenv("BGX_PAIR_EPW"); return (e ? atoi(e) : P_EPW_DEFAULT) == 6 ? 1 : 0; }();
   const int inv = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
   KernT kern = kerns[epw6][wide ? 1 : 0][inv][net->act];
-  static size_t configured[2][2][2][4] = {};
+  static size_t configured_all[BGX_MAX_DEVICES][2][2][2][4] = {};
+  auto& configured = configured_all[device_slot()];
   if (smem > configured[epw6][wide ? 1 : 0][inv][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
@@ -701,8 +696,8 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   lc.numAttrs = cs > 1 ? 1 : 0;
   long long ncl = sm_count / cs;
   if (cs > 1) {
-    static int max_clusters[2][2][2][2][4] = {};     // [cs == 4][epw6][wide][inv][act]: co-resident clusters of this kernel
-    int& mc = max_clusters[cs == 4][epw6][wide ? 1 : 0][inv][net->act];
+    static int max_clusters[BGX_MAX_DEVICES][2][2][2][2][4] = {};     // [device][cs == 4][epw6][wide][inv][act]: co-resident clusters
+    int& mc = max_clusters[device_slot()][cs == 4][epw6][wide ? 1 : 0][inv][net->act];
     if (!mc) {
       lc.gridDim = dim3((unsigned)(ncl * cs), 1, 1);
       rc = check(cudaOccupancyMaxActiveClusters(&mc, kern, &lc));

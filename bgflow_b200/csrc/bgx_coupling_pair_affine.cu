@@ -376,15 +376,9 @@ int affine_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
   a.status = status;
   a.ntiles = (a.B + P_TM - 1) / P_TM;
   const size_t smem = aff_pair_smem_bytes(shift);
-  static int sm_count = 0;
-  int rc;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
+  int sm_count = 0;
+  int rc = device_sm_count(&sm_count);
+  if (rc) return rc;
   using KernT = void (*)(const AffPArgs);
   static const KernT kerns[2][4] = {
       {affine_coupling_pair_kernel<false, 0>, affine_coupling_pair_kernel<false, 1>,
@@ -393,7 +387,8 @@ int affine_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* shift,
        affine_coupling_pair_kernel<true, 2>, affine_coupling_pair_kernel<true, 3>}};
   const int inv = (flags & BGX_FLAG_INVERSE) ? 1 : 0;
   KernT kern = kerns[inv][shift->act];
-  static size_t configured[2][4] = {};
+  static size_t configured_all[BGX_MAX_DEVICES][2][4] = {};
+  auto& configured = configured_all[device_slot()];
   if (smem > configured[inv][shift->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

@@ -375,7 +375,8 @@ static int launch(const CouplingArgs& a, cudaStream_t st) {
   size_t sb = smem_bytes(a.hb);
   if (sb > 227 * 1024) return BGX_ERR_UNSUPPORTED;
   auto kern = coupling_simt_kernel<SPLINE, INVERSE>;
-  static size_t configured = 0;
+  static size_t configured_all[BGX_MAX_DEVICES] = {};
+  size_t& configured = configured_all[device_slot()];
   if (sb > configured) {
     int rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
     if (rc) return rc;

@@ -595,14 +595,9 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
   a.trace = g_trace;
   a.trace_cap = g_trace_cap;
   a.ntiles = (a.B + TC_TM - 1) / TC_TM;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
+  int sm_count = 0;
+  rc = device_sm_count(&sm_count);
+  if (rc) return rc;
   a.bias_floats = bias_floats;
   auto dense16 = [](const Segs& sg) {
     return sg.n == 1 && sg.stride[0] == sg.width[0] && ((uintptr_t)sg.ptr[0] & 15) == 0;
@@ -626,7 +621,8 @@ int spline_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* net, con
        spline_coupling_tc_kernel<true, 3>}};
   if (net->act < 0 || net->act > 3) return BGX_ERR_INVALID;
   KernT kern = kerns[a.inverse][net->act];
-  static size_t configured[2][4] = {};
+  static size_t configured_all[BGX_MAX_DEVICES][2][4] = {};
+  auto& configured = configured_all[device_slot()];
   if (smem > configured[a.inverse][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

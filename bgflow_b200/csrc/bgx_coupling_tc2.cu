@@ -570,15 +570,9 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
   a.ntiles = (a.B + T2_TM - 1) / T2_TM;
   const size_t smem = 1024 + T2_SLOTS * T2_SLOT_BYTES + sizeof(T2Smem) +
                       sizeof(float) * ((size_t)bias_floats + (size_t)T2_TM * (a.D_t + a.K0raw)) + 64;
-  static int sm_count = 0;
-  int rc;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
+  int sm_count = 0;
+  int rc = device_sm_count(&sm_count);
+  if (rc) return rc;
   using KernT = void (*)(const T2Args);
 #define BGX_T2_ROW(INV, FAST, PK) \
   {spline_coupling_tc2_kernel<INV, 0, FAST, PK>, spline_coupling_tc2_kernel<INV, 1, FAST, PK>, \
@@ -599,7 +593,8 @@ int spline_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* net, co
     return fast ? (packed ? 2 : 1) : 0;
   }();
   KernT kern = kerns[pair][a.inverse][net->act];
-  static size_t configured[3][2][4] = {};
+  static size_t configured_all[BGX_MAX_DEVICES][3][2][4] = {};
+  auto& configured = configured_all[device_slot()];
   if (smem > configured[pair][a.inverse][net->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

@@ -440,15 +440,9 @@ int affine_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* shift, 
   }
   const size_t smem = 1024 + A2_SLOTS * A2_SLOT_BYTES + sizeof(A2Smem) +
                       sizeof(float) * (2 * (size_t)bias_floats + (size_t)A2_TM * (a.D_t + a.K0raw)) + 64;
-  static int sm_count = 0;
-  int rc;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
+  int sm_count = 0;
+  int rc = device_sm_count(&sm_count);
+  if (rc) return rc;
   using KernT = void (*)(const A2Args);
   static const KernT kerns[2][4] = {
       {affine_coupling_tc2_kernel<false, 0>, affine_coupling_tc2_kernel<false, 1>, affine_coupling_tc2_kernel<false, 2>,
@@ -457,7 +451,8 @@ int affine_coupling_tc2(const bgx_coupling_io* io, const bgx_packed_mlp* shift, 
        affine_coupling_tc2_kernel<true, 3>}};
   if (shift->act < 0 || shift->act > 3) return BGX_ERR_INVALID;
   KernT kern = kerns[a.inverse][shift->act];
-  static size_t configured[2][4] = {};
+  static size_t configured_all[BGX_MAX_DEVICES][2][4] = {};
+  auto& configured = configured_all[device_slot()];
   if (smem > configured[a.inverse][shift->act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

@@ -477,14 +477,9 @@ int affine_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* shift, c
   while (a.stages > 3 && fixed + (size_t)a.stages * slot_bytes > 227 * 1024) a.stages -= 1;
   const size_t smem = fixed + (size_t)a.stages * slot_bytes;
   if (smem > 227 * 1024) return BGX_ERR_UNSUPPORTED;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
+  int sm_count = 0;
+  rc = device_sm_count(&sm_count);
+  if (rc) return rc;
   using KernT = void (*)(const AfArgs);
   static const KernT kerns[2][4] = {
       {affine_coupling_tc_kernel<false, 0>, affine_coupling_tc_kernel<false, 1>, affine_coupling_tc_kernel<false, 2>,
@@ -493,7 +488,8 @@ int affine_coupling_tc(const bgx_coupling_io* io, const bgx_packed_mlp* shift, c
        affine_coupling_tc_kernel<true, 3>}};
   if (a.act < 0 || a.act > 3) return BGX_ERR_INVALID;
   KernT kern = kerns[a.inverse][a.act];
-  static size_t configured[2][4] = {};
+  static size_t configured_all[BGX_MAX_DEVICES][2][4] = {};
+  auto& configured = configured_all[device_slot()];
   if (smem > configured[a.inverse][a.act]) {
     rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

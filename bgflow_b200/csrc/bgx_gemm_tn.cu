@@ -288,18 +288,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tn_kernel(const __grid_cons
   }
 }
 
-static int tn_sm_count(int* out) {
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    int rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
-  *out = sm_count;
-  return BGX_OK;
-}
+static int tn_sm_count(int* out) { return device_sm_count(out); }
 
 }  // namespace bgx
 
@@ -330,7 +319,8 @@ extern "C" int bgx_gemm_tn(int64_t batch, const float* g, int64_t ldg, int n, co
   a.slices = slices;
   a.status = status;
   const size_t smem = 1024 + (T_HBUFS + T_GBUFS) * T_BUF + sizeof(TnSmem) + 64;
-  static bool configured = false;
+  static bool configured_all[BGX_MAX_DEVICES] = {};
+  bool& configured = configured_all[device_slot()];
   if (!configured) {
     int rc = check(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

@@ -544,9 +544,9 @@ static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // raise a kernel's dynamic shared-memory limit once per (kernel, size) instead of on every launch
 template <typename K>
 static int ensure_smem(K kern, size_t bytes) {
-  static std::map<const void*, size_t> seen;
+  static std::map<std::pair<int, const void*>, size_t> seen;      // per (device, kernel)
   if (bytes <= 48 * 1024) return BGX_OK;
-  size_t& cur = seen[(const void*)kern];
+  size_t& cur = seen[std::make_pair(device_slot(), (const void*)kern)];
   if (bytes <= cur) return BGX_OK;
   int rc = check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   if (!rc) cur = bytes;

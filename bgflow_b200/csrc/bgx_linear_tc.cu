@@ -319,16 +319,11 @@ int linear_launch(int64_t batch, const float* x, int64_t ldx, const bgx_packed_m
   a.plain = (ldx % 4 == 0 && ldx >= round_up(K, 4) && ((uintptr_t)x & 15) == 0) ? 2 : 1;
   const size_t smem = 1024 + P_STAGES * P_STAGE_BYTES + 256 + P_EPI_WARPS * L_TW_FLOATS * sizeof(float) + 64;
   static_assert(sizeof(LinSmem) <= 256, "barrier block");
-  static int sm_count = 0;
-  int rc;
-  if (!sm_count) {
-    int dev = 0;
-    rc = check(cudaGetDevice(&dev));
-    if (rc) return rc;
-    rc = check(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    if (rc) return rc;
-  }
-  static bool configured = false;
+  int sm_count = 0;
+  int rc = device_sm_count(&sm_count);
+  if (rc) return rc;
+  static bool configured_all[BGX_MAX_DEVICES] = {};
+  bool& configured = configured_all[device_slot()];
   if (!configured) {
     rc = check(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;

@@ -196,3 +196,30 @@ def test_weight_gradient_on_tensor_cores(batch, n, k, ldg):
 def test_weight_gradient_rejects_wide_inputs():
     with pytest.raises(ValueError):
         engine.gemm_tn(torch.zeros(8, 16, device=DEV), torch.zeros(8, 200, device=DEV))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """One process driving two GPUs through the mirror's device guard: the launch helpers keep their once-flags
+    (dynamic shared-memory limits, cluster occupancy, SM count) per device, so the first call on cuda:1 configures
+    its kernels there too.  Same weights and inputs on both devices: bit-identical rows, and gradients that agree."""
+    results = []
+    for dev in ("cuda:0", "cuda:1"):
+        outs = []
+        for kind, dim in (("spline", 66), ("affine", 66), ("spline", 384), ("affine", 384)):
+            blocks, split = of.make_stack(kind, dim, 2, seed=3)
+            flow = stack_from(blocks, split, dev)
+            g = torch.Generator().manual_seed(dim)
+            z = (torch.rand(700, dim, generator=g) if kind == "spline" else torch.randn(700, dim, generator=g)).to(dev)
+            z.requires_grad_(True)
+            x, d = flow(z)
+            (x.sum() + d.sum()).backward()
+            outs += [x.detach().cpu(), d.detach().cpu(), z.grad.cpu()]
+        w = torch.randn(300, 200, generator=torch.Generator().manual_seed(1))
+        h = torch.randn(300, 64, generator=torch.Generator().manual_seed(2))
+        dw, db = engine.gemm_tn(w.to(dev), h.to(dev))
+        outs += [dw.cpu(), db.cpu()]
+        engine.check_pipeline_status(dev)
+        results.append(outs)
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
