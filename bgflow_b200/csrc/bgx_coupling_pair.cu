@@ -140,6 +140,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     }
     if (!WIDE)
       for (int i = threadIdx.x; i < a.last_bias_floats; i += NTHREADS) bias_l[i] = a.bias_last[i];
+    // log-det cells of pass residues a narrow block never reaches (fewer than four passes) stay zero for good
+    for (int i = threadIdx.x; i < 2 * 12 * P_TM; i += NTHREADS) (&S->dl_part[0][0][0])[i] = 0.f;
   }
   if (warp == W_MMA) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
@@ -156,16 +158,16 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
   if (warp == W_PROD) {
     // ------------------------------------------------------------------ weight producer (one thread)
     if (lane == 0) {
-      uint32_t ph_e[P_STAGES] = {0, 0};
+      Phases ph;
       int stage = 0;
       long long nfill = 0, t_prod = 0;
       const long long t_begin = P_INSTR ? clock64() : 0;
       auto fill = [&](int l, int c, int t0, int nt) -> bool {
         if (nfill >= P_STAGES) {
           const long long c0 = P_INSTR ? clock64() : 0;
-          if (!mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status)) return false;
+          if (!mbar_wait_sleep(&S->w_empty[stage], ph.get(4 + stage), a.status)) return false;
           if (P_INSTR) t_prod += clock64() - c0;
-          ph_e[stage] ^= 1;
+          ph.flip(4 + stage);
         }
         uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
         mbar_expect_tx(&S->w_full[stage], (uint32_t)nt * P_KT_BYTES);
@@ -191,8 +193,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
       }
       // drain: the last stages' release arrivals (from every CTA of the cluster) have landed before this CTA may leave
       for (int k = 0; k < P_STAGES && k < nfill && ok; ++k) {
-        ok = mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status);
-        ph_e[stage] ^= 1;
+        ok = mbar_wait_sleep(&S->w_empty[stage], ph.get(4 + stage), a.status);
+        ph.flip(4 + stage);
         stage ^= 1;
       }
       if (P_INSTR && a.trace && blockIdx.x == 0) {
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         mbar_expect_tx(&S->y_full[s], nb);
         bulk_g2s(ybuf + s * ystride, a.tin + tile * P_TM * (long long)a.D_t, nb, &S->y_full[s]);
       };
-      uint32_t ph_cf[2] = {0, 0}, ph_yd[2] = {0, 0};
+      Phases ph;
       if (n_my > 0)
         for (int s = 0; s < 2; ++s) { load_c(0, s); load_y(0, s); }
       bool ok = true;
@@ -227,16 +229,16 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
         // conditioner tile of iteration k+1: the buffer is free once iteration k's operand is staged
         for (int s = 0; s < 2 && ok; ++s) {
           if (tile_of(k, s) >= a.ntiles || k + 1 >= n_my) continue;
-          ok = mbar_wait_sleep(&S->c_free[s], ph_cf[s], a.status);
-          ph_cf[s] ^= 1;
+          ok = mbar_wait_sleep(&S->c_free[s], ph.get(14 + s), a.status);
+          ph.flip(14 + s);
           load_c(k + 1, s);
         }
         // transformed tile: store iteration k's result, then fetch iteration k+1's input
         for (int s = 0; s < 2 && ok; ++s) {
           const long long tile = tile_of(k, s);
           if (tile >= a.ntiles) continue;
-          ok = mbar_wait_sleep(&S->y_done[s], ph_yd[s], a.status);
-          ph_yd[s] ^= 1;
+          ok = mbar_wait_sleep(&S->y_done[s], ph.get(16 + s), a.status);
+          ph.flip(16 + s);
           if (!ok) break;
           bulk_s2g(a.tout + tile * P_TM * (long long)a.D_t, ybuf + s * ystride, (uint32_t)(rows_of(tile) * a.D_t * 4));
           bulk_store_wait_read();
@@ -249,14 +251,14 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
   } else if (warp == W_RED) {
     // ------------------------------------------------------------------ log-det reducer: sums the four dim shares
     // of every row in a fixed order (deterministic) and adds the running dlogp; keeps that wait off the epilogue warps
-    uint32_t ph_r[2] = {0, 0};
+    Phases ph;
     bool ok = true;
     for (long long it = 0; it < n_my && ok; ++it)
       for (int s = 0; s < 2 && ok; ++s) {
         const long long tile = tile_of(it, s);
         if (tile >= a.ntiles) continue;
-        ok = mbar_wait_sleep(&S->dl_ready[s], ph_r[s], a.status);
-        ph_r[s] ^= 1;
+        ok = mbar_wait_sleep(&S->dl_ready[s], ph.get(18 + s), a.status);
+        ph.flip(18 + s);
         const float* dl = &S->dl_part[s][0][0];
 #pragma unroll
         for (int r = lane; r < P_TM; r += 32) {
@@ -276,8 +278,7 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
     const uint32_t idesc = idesc_bf16(128, 128);
     int stage = 0;
-    uint32_t ph_wf[P_STAGES] = {0, 0};
-    uint32_t ph_a[2] = {0, 0}, ph_e[2] = {0, 0};
+    Phases ph;
     bool ok = true;
     // one unit on both slots: `wait_a` = a freshly staged A operand is needed, `wait_e` = the accumulator must
     // have been pulled by the epilogue (a last-layer pass preceded), `accum` = keep the accumulator (layer-0 group > 0)
@@ -287,17 +288,17 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     auto unit = [&](int nslots, int K, bool wait_a, bool wait_e, bool accum) {
       if (!ok) return;
       long long c0 = tr ? clock64() : 0;
-      ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
+      ok = mbar_wait(&S->w_full[stage], ph.get(0 + stage), a.status);
       if (tr) t_w += clock64() - c0;
-      ph_wf[stage] ^= 1;
+      ph.flip(0 + stage);
       const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
       const int ksteps = (K + 15) / 16;
 #pragma unroll 1
       for (int s = 0; s < nslots && ok; ++s) {
         long long c1 = tr ? clock64() : 0;
-        if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
+        if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph.get(2 + s), a.status); ph.flip(2 + s); }
         long long c2 = tr ? clock64() : 0;
-        if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
+        if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph.get(4 + s), a.status); ph.flip(4 + s); }
         if (tr) { t_a += c2 - c1; t_e += clock64() - c2; }
         if (!ok) break;
         tc_fence_after();
@@ -351,14 +352,14 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     const int q = warp & 3, j = warp >> 2;            // TMEM lane quadrant, column / dim share
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t ph_acc[2] = {0, 0}, ph_c[2] = {0, 0}, ph_y[2] = {0, 0}, ph_df[2] = {0, 0};
+    Phases ph;
     bool ok = true;
 
     auto stage_x = [&](long long it, int s, int g) {
       const long long row = tile_of(it, s) * P_TM + r_in_tile;
       if (!WIDE && g == 0) {
-        ok = ok && mbar_wait_sleep(&S->c_full[s], ph_c[s], a.status);
-        ph_c[s] ^= 1;
+        ok = ok && mbar_wait_sleep(&S->c_full[s], ph.get(8 + s), a.status);
+        ph.flip(8 + s);
       }
       const float* crow = WIDE ? a.cond + row * (long long)a.K0raw : cbuf + (s * P_TM + r_in_tile) * a.K0raw;
       if (j < 4) pair_stage_x(a.net, a.plain_cond, crow, !WIDE || row < a.B, g, j, tmem + lane_base + s * P_SLOT + P_A);
@@ -373,9 +374,9 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
     const long long t_begin = P_INSTR ? clock64() : 0;
     auto wait_acc = [&](int s) {
       const long long c0 = tr ? clock64() : 0;
-      ok = ok && mbar_wait_sleep(&S->acc_full[s], ph_acc[s], a.status);
+      ok = ok && mbar_wait_sleep(&S->acc_full[s], ph.get(6 + s), a.status);
       if (tr) t_acc += clock64() - c0;
-      ph_acc[s] ^= 1;
+      ph.flip(6 + s);
       tc_fence_after();
     };
 
@@ -438,8 +439,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
             const long long row = tile_of(it, s) * P_TM + r_in_tile;
             const bool live = row < a.B;
             if (!WIDE && c == 0) {
-              ok = ok && mbar_wait_sleep(&S->y_full[s], ph_y[s], a.status);
-              ph_y[s] ^= 1;
+              ok = ok && mbar_wait_sleep(&S->y_full[s], ph.get(10 + s), a.status);
+              ph.flip(10 + s);
             }
             const int iA = EPW == 4 ? (role == 2 ? 4 : 2 * role) : role;   // first dim of this warp inside the pass
             const int dA = P_DPP * c + iA;
@@ -456,6 +457,13 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
               if (hasB) xB = yrow[dA + 1];
             }
             const float* bsrc = (WIDE ? a.bias_last : bias_l) + ((size_t)c * P_DPP + iA) * P_BPAD;
+            // EPW 4: the log-det share of (pass, role) is accumulated straight in its canonical shared-memory cell
+            // (first touch of a tile = plain store): no per-thread accumulators to carry through the unit loop
+            float* cell = &S->dl_part[s][3 * (c & 3) + (role < 3 ? role : 0)][r_in_tile];
+            if (EPW == 4 && c == 0 && it > 0) {      // the reducer has summed this slot's previous tile
+              ok = ok && mbar_wait_sleep(&S->dl_free[s], ph.get(12 + s), a.status);
+              ph.flip(12 + s);
+            }
             wait_acc(s);
             const uint32_t acc_addr = tmem + lane_base + s * P_SLOT + P_ACC + iA * P_PS;
             auto release = [&]() {
@@ -493,8 +501,8 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
                 yrow[dA + 1] = hi(y2);
               }
               const float l_pair = lo(l2) + hi(l2);
-              if (EPW == 6 || role == 0) ld[s][0] += l_pair;
-              else ld[s][1] += l_pair;
+              if (EPW == 6) ld[s][0] += l_pair;
+              else *cell = c < 4 ? l_pair : *cell + l_pair;
             } else if (hasA) {
               uint32_t va[25];
               tmem_ld25(acc_addr, va);
@@ -514,11 +522,11 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
               float y = xA, lad = 0.f;
               if (!(P_INSTR && (a.debug & 2))) rqs_eval_reg<!INVERSE, true>(pp, a.ck, xA, y, lad);
               if (!WIDE || live) yrow[dA] = y;
-              if (EPW == 6 || role == 0) ld[s][0] += lad;      // (roles 0 / 1 land here on a last pass with an odd dim count)
-              else if (role == 1) ld[s][1] += lad;
-              else ld[s][2] += lad;
+              if (EPW == 6) ld[s][0] += lad;      // (roles 0 / 1 land here on a last pass with an odd dim count)
+              else *cell = c < 4 ? lad : *cell + lad;
             } else {
               release();
+              if (EPW == 4 && role < 3 && c < 4) *cell = 0.f;      // a role without dims on this pass: clear the cell
             }
             if (c == P - 1) {
               // ---- end of this slot's tile: hand the output tile to the I/O thread and the log-det shares to the
@@ -528,17 +536,12 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S->y_done[s]);
               }
-              if (it > 0) {
-                ok = ok && mbar_wait_sleep(&S->dl_free[s], ph_df[s], a.status);
-                ph_df[s] ^= 1;
-              }
               if (EPW == 6) {
+                if (it > 0) {
+                  ok = ok && mbar_wait_sleep(&S->dl_free[s], ph.get(12 + s), a.status);
+                  ph.flip(12 + s);
+                }
                 S->dl_part[s][j][r_in_tile] = ld[s][0];
-              } else {
-                // this warp served role r on the passes c with (c & 3) == ((r - j - s) & 3): cell index 3 (c & 3) + r;
-                // the fourth pass residue is the one it idled on (no cell)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) S->dl_part[s][3 * ((r - j - s) & 3) + r][r_in_tile] = ld[s][r];
               }
               __syncwarp();
               if (lane == 0) mbar_arrive(&S->dl_ready[s]);

@@ -60,6 +60,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* t
   return ok != 0;
 }
 
+// Parity bits of up to 32 mbarriers in ONE register: `uint32_t phase[2]` indexed by a runtime slot lives in local
+// memory (a load and a store around every wait).
+struct Phases {
+  uint32_t bits = 0;
+  __device__ __forceinline__ uint32_t get(int i) const { return (bits >> i) & 1u; }
+  __device__ __forceinline__ void flip(int i) { bits ^= 1u << i; }
+};
+
 __device__ __forceinline__ bool mbar_wait_sleep(uint64_t* bar, uint32_t parity, int* timeout_flag) {
   return mbar_wait(bar, parity, timeout_flag);
 }
