@@ -142,6 +142,10 @@ SYMBOLS = {
     "bgx_mlp_forward_train": (C.c_int, [C.c_int64, P(bgx_train_mlp), C.c_void_p, P(bgx_train_buffers), C.c_void_p, C.c_void_p]),
     "bgx_mlp_backward": (C.c_int, [C.c_int64, P(bgx_train_mlp), C.c_void_p, P(bgx_train_buffers), C.c_void_p, C.c_void_p,
                                    P(C.c_void_p), P(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "bgx_spline_coupling_backward": (C.c_int, [C.c_int64, P(bgx_train_mlp), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, P(bgx_spline_cfg), C.c_int, P(bgx_train_buffers),
+                                               C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_void_p), P(C.c_void_p),
+                                               C.c_void_p, C.c_void_p]),
     "bgx_gemm_tn_slices": (C.c_int, [C.c_int64, C.c_int]),
     "bgx_gemm_tn": (C.c_int, [C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -186,12 +186,15 @@ def _spline_backward(t, cond, tr, params, grads, inverse):
     mode = engine.backward_gemm_mode()
     all_trainable = len(params) == len(all_params) and len(all_params) == len(list(net.parameters()))
     if mode == "tcgen05" and _mlp_grad.tc_supported(net) and all_trainable:
+        # recompute, spline chain rule and conditioner backward in ONE host call (bgx_spline_coupling_backward)
         x = torch.cat([c.detach() for c in cond], dim=-1) if len(cond) > 1 else cond[0].detach()
-        st_net = _mlp_grad.forward_tc(net, x.reshape(-1, x.shape[-1]))
-        d_p = transform_backward(st_net["out_padded"], st_net["n_out"])
-        if d_p.shape[1] > st_net["n_out"]:
-            d_p[:, st_net["n_out"]:] = 0          # pad columns of the 16-byte aligned layout (never written by the kernel)
-        d_x, g_params = _mlp_grad.backward_tc(st_net, d_p)
+        tn, lin = _mlp_grad._train_net(net)
+        k = lin[-1].weight.shape[0] // (3 * d_t)
+        d_x, out["d_y"], g_params = tn.spline_block_backward(
+            x.reshape(-1, x.shape[-1]), y2, g_out.reshape(-1, d_t), g_dl.reshape(-1) if g_dl is not None else None,
+            t._end_slope_cols(d_t, k, y.device), k, inverse=inverse, left=t._left, right=t._right, bottom=t._bottom,
+            top=t._top, min_bin_width=st["min_bin_width"], min_bin_height=st["min_bin_height"],
+            min_derivative=st["min_derivative"], identity_init=st["enable_identity_init"])
         g_cond = torch.split(d_x.reshape(*lead, x.shape[-1]), [c.shape[-1] for c in cond], dim=-1)
         gin = (*g_cond, *g_params)
     elif mode == "bf16x3" and _mlp_grad.supported(net) and all_trainable:

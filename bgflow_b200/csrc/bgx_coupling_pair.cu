@@ -54,6 +54,7 @@ struct PArgs {
   const float* tin;     // [B][D_t] dense
   float* tout;          // [B][D_t] dense
   int D_t, K0raw;
+  int role_stride;      // role offset between the two slots (see the role comment in the epilogue)
   DevMlp net;
   const uint16_t* wb[2][BGX_MAX_LAYERS];
   int ktiles[BGX_MAX_LAYERS];
@@ -431,11 +432,11 @@ __global__ void __launch_bounds__((4 * EPW + 4) * 32, 1) spline_coupling_pair_ke
             // roles {dims 0,1 packed | dims 2,3 packed | dim 4 | nothing}, rotating with c so the load evens out;
             // a pair of dims is evaluated in packed fp32 lanes (bgx_spline_reg2.cuh)
             const int c = u - (G + L - 2);
-            // The roles rotate with the pass AND the slot (the warp that idles on slot 0's pass works on slot 1's).  A row's
+            // The roles rotate with the pass AND the slot (a warp that idles or has one dim on slot 0's pass has a pair on slot 1's).  A row's
             // log-det must not depend on the slot it lands in, bit for bit (row independence is tested at full size), so the
             // shares are kept per (pass mod 4, role) cell — the same grouping and the same order of additions whichever warp
             // serves it — and the reducer adds the twelve cells in a fixed order.
-            const int role = EPW == 4 ? ((j + c + s) & 3) : ((j + c) % 6);
+            const int role = EPW == 4 ? ((j + c + a.role_stride * s) & 3) : ((j + c) % 6);
             const long long row = tile_of(it, s) * P_TM + r_in_tile;
             const bool live = row < a.B;
             if (!WIDE && c == 0) {
@@ -656,6 +657,10 @@ int spline_coupling_pair(const bgx_coupling_io* io, const bgx_packed_mlp* net, c
   a.dlogp_in = io->dlogp_in;
   a.dlogp_out = io->dlogp_out;
   a.status = status;
+  // roles {dims 0,1 | dims 2,3 | dim 4 | idle} cost {2, 2, 1, 0} evaluations: with an offset of 2 between the slots a
+  // warp's two concurrent events cost 2+1, 2+0, 1+2, 0+2 (max 3) instead of 2+2, 2+1, 1+0, 0+2 (max 4) with offset 1
+  static const int role_stride = [] { const char* e = getenv("BGX_PAIR_ROLE_STRIDE"); return e ? atoi(e) : 2; }();
+  a.role_stride = role_stride;
   a.ntiles = (a.B + P_TM - 1) / P_TM;
   a.npairs = (a.ntiles + 1) / 2;
   const size_t smem = pair_smem_bytes(net, d_t, a.K0raw, wide);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
   if (warp == 16) {
     // ------------------------------------------------------------------ weight producer (one thread)
     if (lane == 0) {
-      uint32_t ph_e[P_STAGES] = {0, 0};
+      Phases ph;
       int stage = 0;
       long long nfill = 0;
       bool ok = true;
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
           const int nt = u < G ? min(2, a.ktiles[0] - 2 * u) : a.ktiles[l];
           for (int n = 0; n < 2 && ok; ++n) {
             if (nfill >= P_STAGES) {
-              ok = mbar_wait_sleep(&S->w_empty[stage], ph_e[stage], a.status);
-              ph_e[stage] ^= 1;
+              ok = mbar_wait_sleep(&S->w_empty[stage], ph.get(4 + stage), a.status);
+              ph.flip(4 + stage);
               if (!ok) break;
             }
             uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
@@ -145,8 +145,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
     // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
     const uint32_t idesc = idesc_bf16(128, 128);
     int stage = 0;
-    uint32_t ph_wf[P_STAGES] = {0, 0};
-    uint32_t ph_a[2] = {0, 0}, ph_e[2] = {0, 0};
+    Phases ph;
     bool ok = true;
     for (long long it = 0; it < n_my && ok; ++it) {
 #pragma unroll 1
@@ -158,10 +157,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
         const int ksteps = (K + 15) / 16;
 #pragma unroll 1
         for (int s = 0; s < 2 && ok; ++s) {
-          ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
-          ph_wf[stage] ^= 1;
-          if (wait_a && ok) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
-          if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
+          ok = mbar_wait(&S->w_full[stage], ph.get(0 + stage), a.status);
+          ph.flip(0 + stage);
+          if (wait_a && ok) { ok = mbar_wait(&S->a_ready[s], ph.get(2 + s), a.status); ph.flip(2 + s); }
+          if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph.get(4 + s), a.status); ph.flip(4 + s); }
           if (!ok) break;
           tc_fence_after();
           const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
@@ -196,7 +195,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
     const int q = warp & 3, j = warp >> 2;
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t ph_acc[2] = {0, 0}, ph_df = 0;
+    Phases ph;
+    uint32_t ph_df = 0;
 
     auto stage_x = [&](long long it, int s, int g) {
       const long long row = tile_of(it) * P_TM + r_in_tile;
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) affine_coupling_pair_kernel(cons
       if (lane == 0) mbar_arrive(&S->a_ready[s]);
     };
     auto wait_acc = [&](int s) {
-      mbar_wait_sleep(&S->acc_full[s], ph_acc[s], a.status);
-      ph_acc[s] ^= 1;
+      mbar_wait_sleep(&S->acc_full[s], ph.get(6 + s), a.status);
+      ph.flip(6 + s);
       tc_fence_after();
     };
 

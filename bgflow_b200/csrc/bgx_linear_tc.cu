@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
   if (warp == 16) {
     // ------------------------------------------------------------------ weight producer (one thread)
     if (lane == 0) {
-      uint32_t ph_e[P_STAGES] = {0, 0};
+      Phases ph;
       int stage = 0;
       long long nfill = 0;
       bool ok = true;
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
           const int g = P == 1 ? u : 0, c = P == 1 ? 0 : u;
           const int nt = min(2, a.ktiles - 2 * g);
           if (nfill >= P_STAGES) {
-            ok = mbar_wait(&S->w_empty[stage], ph_e[stage], a.status);
-            ph_e[stage] ^= 1;
+            ok = mbar_wait(&S->w_empty[stage], ph.get(4 + stage), a.status);
+            ph.flip(4 + stage);
             if (!ok) break;
           }
           uint8_t* dst = ring + (size_t)stage * P_STAGE_BYTES;
@@ -159,8 +159,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
     // ------------------------------------------------------------------ MMA issuer (warp-wide, elected lane issues)
     const uint32_t idesc = idesc_bf16(128, 128);
     int stage = 0;
-    uint32_t ph_wf[P_STAGES] = {0, 0};
-    uint32_t ph_a[2] = {0, 0}, ph_e[2] = {0, 0};
+    Phases ph;
     bool ok = true;
     for (long long it = 0; it < n_my && ok; ++it) {
       const int nslots = slots_of(it);
@@ -172,13 +171,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
         const bool wait_a = P == 1 || u == 0;                  // a freshly staged group (every group; or once per tile)
         const bool wait_e = P == 1 ? (u == 0 && it > 0) : (u > 0 || it > 0);   // the accumulator's previous pass was stored
         const bool accum = P == 1 && u > 0;
-        ok = mbar_wait(&S->w_full[stage], ph_wf[stage], a.status);
-        ph_wf[stage] ^= 1;
+        ok = mbar_wait(&S->w_full[stage], ph.get(0 + stage), a.status);
+        ph.flip(0 + stage);
         const uint32_t sb = smem_u32(ring + (size_t)stage * P_STAGE_BYTES);
 #pragma unroll 1
         for (int s = 0; s < nslots && ok; ++s) {
-          if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph_a[s], a.status); ph_a[s] ^= 1; }
-          if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph_e[s], a.status); ph_e[s] ^= 1; }
+          if (wait_a) { ok = mbar_wait(&S->a_ready[s], ph.get(2 + s), a.status); ph.flip(2 + s); }
+          if (wait_e && ok) { ok = mbar_wait(&S->acc_empty[s], ph.get(4 + s), a.status); ph.flip(4 + s); }
           if (!ok) break;
           tc_fence_after();
           const uint32_t acc_addr = tmem + s * P_SLOT + P_ACC;
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
     // ------------------------------------------------------------------ epilogue / staging warps (0..15)
     const int q = warp & 3, j = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t ph_acc[2] = {0, 0};
+    Phases ph;
     float* tw = reinterpret_cast<float*>(base + P_STAGES * P_STAGE_BYTES + 256) + warp * L_TW_FLOATS;
     auto stage_x = [&](long long it, int s, int g) {
       lin_stage(a, tw, tile_of(it, s) * P_TM + q * 32, g, j, lane, tmem + lane_base + s * P_SLOT + P_A);
@@ -220,8 +219,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) linear_tc_kernel(const __grid_co
       for (int u = 0; u < U; ++u) {
 #pragma unroll 1
         for (int s = 0; s < nslots; ++s) {
-          mbar_wait(&S->acc_full[s], ph_acc[s], a.status);
-          ph_acc[s] ^= 1;
+          mbar_wait(&S->acc_full[s], ph.get(6 + s), a.status);
+          ph.flip(6 + s);
           tc_fence_after();
           if (P == 1 && u < G - 1) {            // group u consumed: stage the next one (the accumulator keeps summing)
             stage_x(it, s, u + 1);

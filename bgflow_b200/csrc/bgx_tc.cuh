@@ -39,7 +39,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // that the compiler cannot wrap it in its BSSY / BREAK / predicate bookkeeping.  (Measured: the C++ polling loops
 // and a try_wait-with-suspend-hint variant, which ptxas lowers to TRYWAIT + NANOSLEEP.SYNCS pairs, executed
 // 20-70 k instructions per 128-row tile — up to half of everything the kernel issued — and competed with the
-// working warps for issue slots.)  Bounded: after 2^22 attempts (seconds) the flag is raised instead of hanging.
+// working warps for issue slots.)  Bounded: after 2^22 attempts (seconds) the flag is raised instead of hanging; the attempt counter is
+// checked once per four attempts (a waiting warp issues 3.75 instead of 6 instructions per attempt: the spin loops were
+// a third of all instructions the pair kernel executed).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* timeout_flag) {
   uint32_t ok;
   asm volatile(
@@ -47,8 +49,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* t
       "BGX_WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "@p bra BGX_WAIT_DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra BGX_WAIT_DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra BGX_WAIT_DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra BGX_WAIT_DONE;\n\t"
       "add.u32 n, n, 1;\n\t"
-      "setp.lt.u32 p, n, 4194304;\n\t"
+      "setp.lt.u32 p, n, 1048576;\n\t"
       "@p bra BGX_WAIT_LOOP;\n\t"
       "setp.ne.u32 p, n, n;\n"          // timed out: p = false
       "BGX_WAIT_DONE:\n\t"

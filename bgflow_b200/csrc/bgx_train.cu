@@ -221,3 +221,32 @@ extern "C" int bgx_mlp_backward(int64_t batch, const bgx_train_mlp* net, const f
   }
   return BGX_OK;
 }
+
+extern "C" int bgx_spline_backward(int64_t batch, int32_t d_t, const float* params, int64_t params_stride,
+                                   const float* y, const float* g_out, const float* g_dlogp,
+                                   const int32_t* end_slope_col, const bgx_spline_cfg* cfg, int flags,
+                                   float* d_params, float* d_y, void* stream);
+
+// The whole backward of one spline coupling block (coupling.py:161-180 + spline.py:87-188 + dense.py:47-48 under
+// autograd in the reference) in ONE host call: conditioner recompute -> spline chain rule (dP, dy) -> conditioner
+// backward (d cond, every dW, db).  `d_p` is scratch [batch, pad4(dims[n_layers])].
+extern "C" int bgx_spline_coupling_backward(int64_t batch, const bgx_train_mlp* net, const float* cond, int32_t d_t,
+                                            const float* y, const float* g_out, const float* g_dlogp,
+                                            const int32_t* end_slope_col, const bgx_spline_cfg* cfg, int flags,
+                                            const bgx_train_buffers* buf, float* d_p, float* d_cond, float* d_y,
+                                            float* const* d_w, float* const* d_b, int32_t* status, void* stream) {
+  int rc = check_net(net);
+  if (rc) return rc;
+  if (batch <= 0 || !buf || !cond || !y || !g_out || !d_p || !d_y || !cfg) return BGX_ERR_INVALID;
+  const int L = net->n_layers, n_out = net->dims[L], ldp = pad4(n_out);
+  rc = bgx_mlp_forward_train(batch, net, cond, buf, status, stream);
+  if (rc) return rc;
+  if (ldp > n_out) {     // pad columns of dP are operands of the backward GEMMs and never written by the transform kernel
+    rc = check(cudaMemset2DAsync(d_p + n_out, (size_t)ldp * sizeof(float), 0, (size_t)(ldp - n_out) * sizeof(float),
+                                 (size_t)batch, (cudaStream_t)stream));
+    if (rc) return rc;
+  }
+  rc = bgx_spline_backward(batch, d_t, buf->z[L - 1], ldp, y, g_out, g_dlogp, end_slope_col, cfg, flags, d_p, d_y, stream);
+  if (rc) return rc;
+  return bgx_mlp_backward(batch, net, cond, buf, d_p, d_cond, d_w, d_b, status, stream);
+}

@@ -532,20 +532,17 @@ class TrainNet:
         self.dims = [int(src.dims[i]) for i in range(n + 1)]
         return out
 
-    @_device_guard
-    def forward(self, x):
-        """Recompute on ``x`` ``[B, dims[0]]``.  Returns the state ``backward`` needs; ``state["out_padded"]`` is the net's
-        output ``[B, pad4(dims[-1])]`` (zero pad columns), ``state["out"]`` its first ``dims[-1]`` columns."""
+    def _buffers(self, B, device, extra=()):
+        """One allocation for a recompute + backward: z_i, then h_i and g_i of the hidden layers, the weight-gradient
+        partials, then ``extra`` sizes.  Returns (flat tensor, views, bgx_train_buffers)."""
         lib = _lib.load()
-        require_cuda_fp32(x)
-        x = x.contiguous()
-        B, dims = x.shape[0], self.dims
+        dims = self.dims
         L = len(dims) - 1
         widths = [_pad4(d) for d in dims[1:]]
         part = int(lib.bgx_mlp_train_part_floats(B, C.byref(self.packed))) if B else 0
-        # one allocation: z_i, then h_i and g_i of the hidden layers, then the weight-gradient partials
-        sizes = [B * w for w in widths] + [B * w for w in widths[:-1]] * 2 + [part]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
+        sizes = [B * w for w in widths] + [B * w for w in widths[:-1]] * 2 + [part] + [int(e) for e in extra]
+        sizes = [(sz + 3) // 4 * 4 for sz in sizes]          # keep every view 16-byte aligned
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=device)
         views, off = [], 0
         for sz in sizes:
             views.append(flat[off:off + sz])
@@ -556,7 +553,72 @@ class TrainNet:
             if i + 1 < L:
                 bufs.h[i] = views[L + i].data_ptr()
                 bufs.g[i] = views[2 * L - 1 + i].data_ptr()
-        bufs.part = views[-1].data_ptr()
+        bufs.part = views[2 * L - 1 + L - 1].data_ptr()
+        return flat, views, bufs
+
+    def _grad_buffers(self, device, zero=False):
+        dims = self.dims
+        L = len(dims) - 1
+        sizes = []
+        for i in range(L):
+            sizes += [dims[i + 1] * dims[i], dims[i + 1]]
+        sizes = [(sz + 3) // 4 * 4 for sz in sizes]
+        flat = (torch.zeros if zero else torch.empty)(sum(sizes), dtype=torch.float32, device=device)
+        grads, off = [], 0
+        d_w = (C.c_void_p * L)()
+        d_b = (C.c_void_p * L)()
+        for i in range(L):
+            w = flat[off:off + dims[i + 1] * dims[i]].view(dims[i + 1], dims[i])
+            off += sizes[2 * i]
+            b = flat[off:off + dims[i + 1]]
+            off += sizes[2 * i + 1]
+            d_w[i], d_b[i] = w.data_ptr(), b.data_ptr()
+            grads += [w, b]
+        return grads, d_w, d_b
+
+    @_device_guard
+    def spline_block_backward(self, x, y, g_out, g_dlogp, end_slope_col, n_bins, inverse=False, left=0.0, right=1.0,
+                              bottom=0.0, top=1.0, min_bin_width=1e-3, min_bin_height=1e-3, min_derivative=1e-3,
+                              identity_init=True):
+        """The whole backward of a spline coupling block whose conditioner this is, in ONE host call
+        (``bgx_spline_coupling_backward``): ``x`` ``[B, dims[0]]`` the conditioner input, ``y`` ``[B, d_t]`` the block's
+        transformed input, ``g_out`` / ``g_dlogp`` the upstream gradients.  Returns ``(d_x, d_y, [dW_0, db_0, ...])``."""
+        lib = _lib.load()
+        require_cuda_fp32(x, y, g_out)
+        x, y, g_out = x.contiguous(), y.contiguous(), g_out.contiguous()
+        B, d_t = y.shape
+        dims = self.dims
+        grads, d_w, d_b = self._grad_buffers(x.device, zero=(B == 0))
+        wl = _pad4(dims[-1])
+        flat, views, bufs = self._buffers(B, x.device, extra=(B * wl, B * d_t, B * dims[0]))
+        d_p, d_y, d_x = views[-3], views[-2][:B * d_t].view(B, d_t), views[-1][:B * dims[0]].view(B, dims[0])
+        if B == 0:
+            return d_x, d_y, grads
+        gd = g_dlogp.reshape(-1).contiguous() if g_dlogp is not None else None
+        cfg = _lib.bgx_spline_cfg()
+        cfg.n_bins = n_bins
+        cfg.left, cfg.right, cfg.bottom, cfg.top = float(left), float(right), float(bottom), float(top)
+        cfg.min_bin_width, cfg.min_bin_height, cfg.min_derivative = min_bin_width, min_bin_height, min_derivative
+        cfg.identity_init = 1 if identity_init else 0
+        rc = lib.bgx_spline_coupling_backward(
+            B, C.byref(self.packed), C.c_void_p(x.data_ptr()), d_t, C.c_void_p(y.data_ptr()), C.c_void_p(g_out.data_ptr()),
+            C.c_void_p(gd.data_ptr()) if gd is not None else None, C.c_void_p(end_slope_col.data_ptr()), C.byref(cfg),
+            _lib.FLAG_INVERSE if inverse else 0, C.byref(bufs), C.c_void_p(d_p.data_ptr()), C.c_void_p(d_x.data_ptr()),
+            C.c_void_p(d_y.data_ptr()), d_w, d_b, C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
+        _lib.check(rc, "bgx_spline_coupling_backward")
+        return d_x, d_y, grads
+
+    @_device_guard
+    def forward(self, x):
+        """Recompute on ``x`` ``[B, dims[0]]``.  Returns the state ``backward`` needs; ``state["out_padded"]`` is the net's
+        output ``[B, pad4(dims[-1])]`` (zero pad columns), ``state["out"]`` its first ``dims[-1]`` columns."""
+        lib = _lib.load()
+        require_cuda_fp32(x)
+        x = x.contiguous()
+        B, dims = x.shape[0], self.dims
+        L = len(dims) - 1
+        widths = [_pad4(d) for d in dims[1:]]
+        flat, views, bufs = self._buffers(B, x.device)
         if B:
             rc = lib.bgx_mlp_forward_train(B, C.byref(self.packed), C.c_void_p(x.data_ptr()), C.byref(bufs),
                                            C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
@@ -576,22 +638,7 @@ class TrainNet:
         if d_out.shape[1] != wl:
             d_out = torch.nn.functional.pad(d_out, (0, wl - d_out.shape[1]))
         d_out = d_out.contiguous()
-        sizes = []
-        for i in range(L):
-            sizes += [dims[i + 1] * dims[i], dims[i + 1]]
-        sizes = [(s + 3) // 4 * 4 for s in sizes]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x.device) if B else \
-            torch.zeros(sum(sizes), dtype=torch.float32, device=x.device)
-        grads, off = [], 0
-        d_w = (C.c_void_p * L)()
-        d_b = (C.c_void_p * L)()
-        for i in range(L):
-            w = flat[off:off + dims[i + 1] * dims[i]].view(dims[i + 1], dims[i])
-            off += sizes[2 * i]
-            b = flat[off:off + dims[i + 1]]
-            off += sizes[2 * i + 1]
-            d_w[i], d_b[i] = w.data_ptr(), b.data_ptr()
-            grads += [w, b]
+        grads, d_w, d_b = self._grad_buffers(x.device, zero=(B == 0))
         d_x = torch.empty(B, dims[0], dtype=torch.float32, device=x.device) if need_dx else None
         if B:
             rc = lib.bgx_mlp_backward(B, C.byref(state["packed"]), C.c_void_p(x.data_ptr()), C.byref(state["bufs"]),

@@ -359,6 +359,18 @@ int bgx_mlp_forward_train(int64_t batch, const bgx_train_mlp* net, const float* 
 int bgx_mlp_backward(int64_t batch, const bgx_train_mlp* net, const float* x, const bgx_train_buffers* buf,
                      const float* d_out, float* d_x, float* const* d_w, float* const* d_b, int32_t* status, void* stream);
 
+/* The whole backward of one RQ-spline coupling block in one call (coupling.py:161-180, spline.py:87-188 and
+ * dense.py:47-48 under torch autograd in the reference): conditioner recompute, the transform's chain rule
+ * (bgx_spline_backward) and the conditioner's backward.  cond [batch, dims[0]] and y [batch, d_t] (the block's
+ * transformed INPUT) dense; g_out [batch, d_t], g_dlogp [batch] or NULL the upstream gradients; flags / cfg /
+ * end_slope_col as for bgx_spline_backward.  Outputs: d_cond [batch, dims[0]] (or NULL), d_y [batch, d_t], d_w[i],
+ * d_b[i] as for bgx_mlp_backward.  d_p: scratch, batch * pad4(dims[n_layers]) floats. */
+int bgx_spline_coupling_backward(int64_t batch, const bgx_train_mlp* net, const float* cond, int32_t d_t,
+                                 const float* y, const float* g_out, const float* g_dlogp,
+                                 const int32_t* end_slope_col, const bgx_spline_cfg* cfg, int flags,
+                                 const bgx_train_buffers* buf, float* d_p, float* d_cond, float* d_y,
+                                 float* const* d_w, float* const* d_b, int32_t* status, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T
