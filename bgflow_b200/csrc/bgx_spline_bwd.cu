@@ -30,6 +30,7 @@ struct SplineBwdArgs {
   float* dy;
   float left, right, bottom, top, min_w, min_h, min_d, beta;
   int root;
+  int zero_from;      // >= 0: columns [zero_from, p_stride) of dP are written as zeros (row padding that later GEMMs read)
 };
 
 // VEC (K == MAXK == 8, rows of P / dP 16-byte aligned): a dim's 8 widths / heights / slopes are 32 contiguous bytes,
@@ -230,15 +231,29 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
       }
   }
   if (!circular) dPr[ecol] = end_hit ? sg1 : 0.f;
+  if (a.zero_from >= 0 && d == 0)
+    for (long long c = a.zero_from; c < a.p_stride; ++c) dPr[c] = 0.f;
   a.dy[idx] = (yin >= a.left && yin <= a.right) ? g_x : 0.f;
 }
 
 }  // namespace bgx
 
+namespace bgx {
+int spline_backward_launch(int64_t batch, int32_t d_t, const float* params, int64_t params_stride, const float* y,
+                           const float* g_out, const float* g_dlogp, const int32_t* end_slope_col, const bgx_spline_cfg* cfg,
+                           int flags, float* d_params, float* d_y, int zero_from, void* stream);
+}
 extern "C" int bgx_spline_backward(int64_t batch, int32_t d_t, const float* params, int64_t params_stride,
                                    const float* y, const float* g_out, const float* g_dlogp,
                                    const int32_t* end_slope_col, const bgx_spline_cfg* cfg, int flags,
                                    float* d_params, float* d_y, void* stream) {
+  return bgx::spline_backward_launch(batch, d_t, params, params_stride, y, g_out, g_dlogp, end_slope_col, cfg, flags,
+                                     d_params, d_y, -1, stream);
+}
+int bgx::spline_backward_launch(int64_t batch, int32_t d_t, const float* params, int64_t params_stride, const float* y,
+                                const float* g_out, const float* g_dlogp, const int32_t* end_slope_col,
+                                const bgx_spline_cfg* cfg, int flags, float* d_params, float* d_y, int zero_from,
+                                void* stream) {
   using namespace bgx;
   if (!cfg || batch < 0 || d_t <= 0 || cfg->n_bins < 1 || cfg->n_bins > 48) return BGX_ERR_INVALID;
   if (batch == 0) return BGX_OK;
@@ -252,6 +267,7 @@ extern "C" int bgx_spline_backward(int64_t batch, int32_t d_t, const float* para
   a.min_w = cfg->min_bin_width; a.min_h = cfg->min_bin_height; a.min_d = cfg->min_derivative;
   a.beta = cfg->identity_init ? logf(2.f) / (1.f - cfg->min_derivative) : 1.f;
   a.root = (flags & BGX_FLAG_INVERSE) ? 0 : 1;
+  a.zero_from = zero_from;
   const long long n = batch * (long long)d_t;
   const unsigned grid = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;

@@ -7,6 +7,9 @@
 // issue the same work from C++ — bgx_linear (recompute, input gradients), bgx_gemm_tn (weight / bias gradients), and
 // three small kernels of this file (activation, activation gradient, the fixed-order sum of bgx_gemm_tn's per-slice
 // partials) — a few microseconds per launch, no allocation, nothing returned to the interpreter in between.
+// (Folding the activation and its slope into bgx_linear's store path was measured and dropped: the precise expf / tanhf
+// forms run on the critical path of that kernel's tile pipeline, +0.8 ms per step against 0.37 ms of HBM-bound
+// elementwise kernels saved.)
 //
 // Layout: every activation / gradient buffer of layer i is [batch, pad4(dims[i + 1])] (row stride = a multiple of 4
 // floats: 16-byte aligned rows for the vector paths of bgx_linear and bgx_spline_backward); pad columns are written
@@ -222,10 +225,11 @@ extern "C" int bgx_mlp_backward(int64_t batch, const bgx_train_mlp* net, const f
   return BGX_OK;
 }
 
-extern "C" int bgx_spline_backward(int64_t batch, int32_t d_t, const float* params, int64_t params_stride,
-                                   const float* y, const float* g_out, const float* g_dlogp,
-                                   const int32_t* end_slope_col, const bgx_spline_cfg* cfg, int flags,
-                                   float* d_params, float* d_y, void* stream);
+namespace bgx {
+int spline_backward_launch(int64_t batch, int32_t d_t, const float* params, int64_t params_stride, const float* y,
+                           const float* g_out, const float* g_dlogp, const int32_t* end_slope_col, const bgx_spline_cfg* cfg,
+                           int flags, float* d_params, float* d_y, int zero_from, void* stream);
+}
 
 // The whole backward of one spline coupling block (coupling.py:161-180 + spline.py:87-188 + dense.py:47-48 under
 // autograd in the reference) in ONE host call: conditioner recompute -> spline chain rule (dP, dy) -> conditioner
@@ -241,12 +245,10 @@ extern "C" int bgx_spline_coupling_backward(int64_t batch, const bgx_train_mlp* 
   const int L = net->n_layers, n_out = net->dims[L], ldp = pad4(n_out);
   rc = bgx_mlp_forward_train(batch, net, cond, buf, status, stream);
   if (rc) return rc;
-  if (ldp > n_out) {     // pad columns of dP are operands of the backward GEMMs and never written by the transform kernel
-    rc = check(cudaMemset2DAsync(d_p + n_out, (size_t)ldp * sizeof(float), 0, (size_t)(ldp - n_out) * sizeof(float),
-                                 (size_t)batch, (cudaStream_t)stream));
-    if (rc) return rc;
-  }
-  rc = bgx_spline_backward(batch, d_t, buf->z[L - 1], ldp, y, g_out, g_dlogp, end_slope_col, cfg, flags, d_p, d_y, stream);
+  // pad columns of dP are operands of the backward GEMMs: the transform kernel writes them as zeros (a 2-D memset of
+  // three columns x 65,536 rows took 38 us)
+  rc = spline_backward_launch(batch, d_t, buf->z[L - 1], ldp, y, g_out, g_dlogp, end_slope_col, cfg, flags, d_p, d_y,
+                              ldp > n_out ? n_out : -1, stream);
   if (rc) return rc;
   return bgx_mlp_backward(batch, net, cond, buf, d_p, d_cond, d_w, d_b, status, stream);
 }
