@@ -73,15 +73,20 @@ __device__ __forceinline__ void load_slab(float (&v)[16], const float* __restric
                                           long long row0, long long B, int wq) {
   const bool cok = col < ncols;
   if (cok && row0 + 64 <= B) {
-    // whole slab inside the batch (all but the last batch tile): one base pointer, one multiply-add per load — the
-    // converters are bound by the instructions they issue, and the guarded form below costs ~12 integer
-    // instructions per load
+    // whole slab inside the batch (all but the last batch tile): one base pointer, no per-load guards (120 -> 94 us)
     const float* p = src + (row0 + 8 * wq) * ld + col;
-    const int ldi = (int)ld;
+    const long long ld4 = ld * 4;          // row stride in bytes
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 2; ++u) {
+      // walk the 8 rows of an octet with one 64-bit add per load (the guarded form below costs ~12 integer
+      // instructions per load, index arithmetic from the row number ~5)
+      const char* q = reinterpret_cast<const char*>(p) + 32 * u * ld4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[8 * u + i] = __ldg(p + (32 * u + i) * ldi);
+      for (int i = 0; i < 8; ++i) {
+        v[8 * u + i] = __ldg(reinterpret_cast<const float*>(q));
+        q += ld4;
+      }
+    }
     return;
   }
 #pragma unroll
@@ -196,6 +201,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tn_kernel(const __grid_cons
         load_slab(v, a.g, a.ldg, a.N, (nt0 + kind - 1) * 128 + r, row0, a.B, wq);
       }
     };
+    // (A third register buffer — loads two slabs ahead — and cheaper load addressing were both measured: no change,
+    // 94-96 us at N = 825, B = 65536.  Neither load latency nor issue slots bound the kernel any more; what is left is
+    // the SS-mode MMA itself, which reads 8 KB of operands from shared memory per instruction — at 64 cycles per MMA
+    // that is the whole 128 B/clk of the SM's shared memory, shared with the converters' stores.  Likely limit, not
+    // verified in isolation; moving the H operand to tensor memory would halve it at the price of one accumulator.)
     float va[16], vb[16];
     if (total > 0) issue_loads(va, 0, 0);
     long long i = 0;
