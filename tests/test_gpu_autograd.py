@@ -333,3 +333,37 @@ def test_conditioner_recompute_and_backward_drivers(dims, act, batch):
         assert a.shape == b.shape
         s = max(b.abs().max().item(), 1e-6)
         np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), atol=1e-3 * s, rtol=3e-3)   # (a ReLU kink flip moves one sample)
+
+
+def test_training_entry_points_reject_what_they_do_not_cover():
+    """Error behaviour of the training-path C ABI: shapes outside the tensor-core linear kernel's cover are refused at
+    pack time (the Python side then stays on torch autograd), inconsistent arguments come back as error codes, and a
+    block with a conditioner the drivers do not cover still trains (through the autograd path) with the default mode."""
+    import ctypes as C
+    from bgflow_b200 import _lib, _mlp_grad, engine
+    lib = _lib.load()
+    wide = bg.DenseNet([200, 300, 5], activation=torch.nn.SiLU()).to(DEV)        # a 200 -> 300 layer: > 128 on both sides
+    assert not _mlp_grad.tc_supported(wide)
+    with pytest.raises(_lib.BgxError):
+        engine.TrainNet().refresh([l.weight for l in wide._layers if isinstance(l, torch.nn.Linear)],
+                                  [l.bias for l in wide._layers if isinstance(l, torch.nn.Linear)],
+                                  [_lib.ACT_SILU, _lib.ACT_NONE])
+    g = torch.zeros(64, 8, device=DEV)
+    h = torch.zeros(64, 8, device=DEV)
+    part = torch.zeros(4 * 128 * 129, device=DEV)
+    args = (C.c_void_p(g.data_ptr()), 8, 8, C.c_void_p(h.data_ptr()), 8, 8)
+    assert lib.bgx_gemm_tn(64, *args, 2, C.c_void_p(part.data_ptr()), None, None, None) != 0      # 2 slices > 1 batch tile
+    assert lib.bgx_gemm_tn(64, *args, 0, C.c_void_p(part.data_ptr()), None, None, None) != 0
+    assert lib.bgx_gemm_tn(64, C.c_void_p(g.data_ptr()), 4, 8, C.c_void_p(h.data_ptr()), 8, 8, 1,
+                           C.c_void_p(part.data_ptr()), None, None, None) != 0                         # row stride < width
+    assert lib.bgx_gemm_tn_slices(0, 8) == 0 and lib.bgx_gemm_tn_slices(64, 8) == 1
+    # a spline block whose conditioner is too wide for the drivers: default mode falls back to autograd and still matches
+    torch.manual_seed(0)
+    net = bg.DenseNet([6, 200, 300, 3 * 8 * 4 + 4], activation=torch.nn.SiLU()).to(DEV)
+    tr = bg.ConditionalSplineTransformer(net, is_circular=False)
+    cond = torch.randn(50, 6, device=DEV, requires_grad=True)
+    y = torch.rand(50, 4, device=DEV, requires_grad=True)
+    out, dl = tr.forward(cond, y)
+    (out.sum() + dl.sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    assert torch.isfinite(cond.grad).all() and torch.isfinite(y.grad).all()
