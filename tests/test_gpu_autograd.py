@@ -359,7 +359,8 @@ def test_training_entry_points_reject_what_they_do_not_cover():
     assert lib.bgx_gemm_tn_slices(0, 8) == 0 and lib.bgx_gemm_tn_slices(64, 8) == 1
     # a spline block whose conditioner is too wide for the drivers: default mode falls back to autograd and still matches
     torch.manual_seed(0)
-    net = bg.DenseNet([6, 200, 300, 3 * 8 * 4 + 4], activation=torch.nn.SiLU()).to(DEV)
+    net = bg.DenseNet([6, 200, 130, 3 * 8 * 4 + 4], activation=torch.nn.SiLU()).to(DEV)
+    assert not _mlp_grad.tc_supported(net)
     tr = bg.ConditionalSplineTransformer(net, is_circular=False)
     cond = torch.randn(50, 6, device=DEV, requires_grad=True)
     y = torch.rand(50, 4, device=DEV, requires_grad=True)
