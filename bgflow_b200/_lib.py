@@ -146,6 +146,11 @@ SYMBOLS = {
                                                C.c_void_p, C.c_void_p, P(bgx_spline_cfg), C.c_int, P(bgx_train_buffers),
                                                C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_void_p), P(C.c_void_p),
                                                C.c_void_p, C.c_void_p]),
+    "bgx_affine_backward_scratch_floats": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "bgx_affine_coupling_backward": (C.c_int, [C.c_int64, P(bgx_train_mlp), P(bgx_train_mlp), C.c_void_p, C.c_void_p, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, P(bgx_train_buffers),
+                                               P(bgx_train_buffers), C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_void_p),
+                                               P(C.c_void_p), P(C.c_void_p), P(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgx_gemm_tn_slices": (C.c_int, [C.c_int64, C.c_int]),
     "bgx_gemm_tn": (C.c_int, [C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

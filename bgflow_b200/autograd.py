@@ -115,7 +115,15 @@ def _affine_backward(t, cond, tr, grads, inverse):
     g_dl = grads[-1].reshape(-1, 1) if grads[-1] is not None else None
     from . import engine
     tc = engine.backward_gemm_mode() == "tcgen05"
-    fwd, bwd = (_mlp_grad.forward_tc, _mlp_grad.backward_tc) if tc else (_mlp_grad.forward, _mlp_grad.backward)
+    if tc:
+        # recompute of both conditioners, elementwise chain rule and both conditioner backwards in ONE host call
+        tn_mu, _ = _mlp_grad._train_net(t._shift_transformation)
+        tn_s, _ = _mlp_grad._train_net(t._scale_transformation)
+        d_x2, d_y, g_mu, g_s, d_la = engine.affine_block_backward(
+            tn_mu, tn_s, t._log_alpha.detach(), x2, y2, g_out, g_dl.reshape(-1) if g_dl is not None else None, inverse)
+        return _affine_pack_grads(t, cond, d_x2.reshape(*lead, x.shape[-1]), g_mu, g_s, d_la.reshape(t._log_alpha.shape)), \
+            torch.split(d_y.reshape(*lead, d_t), widths, dim=-1)
+    fwd, bwd = _mlp_grad.forward, _mlp_grad.backward
     st_mu = fwd(t._shift_transformation, x2)
     st_s = fwd(t._scale_transformation, x2)
     alpha = torch.exp(t._log_alpha.detach())
@@ -140,7 +148,13 @@ def _affine_backward(t, cond, tr, grads, inverse):
     dx_mu, g_mu = bwd(st_mu, d_mu.contiguous())
     dx_s, g_s = bwd(st_s, d_s)
     d_x = (dx_mu + dx_s).reshape(*lead, x.shape[-1])
+    return _affine_pack_grads(t, cond, d_x, g_mu, g_s, d_log_alpha), torch.split(d_y.reshape(*lead, d_t), widths, dim=-1)
+
+
+def _affine_pack_grads(t, cond, d_x, g_mu, g_s, d_log_alpha):
+    """(grads of cond, then the parameter gradients in ``t.parameters()`` order)."""
     g_cond = torch.split(d_x, [c.shape[-1] for c in cond], dim=-1)
+    g_mu, g_s = list(g_mu), list(g_s)
     # parameter order of AffineTransformer.parameters(): registration order of the module's members
     named = dict(shift=g_mu, scale=g_s)
     order = []
@@ -153,7 +167,7 @@ def _affine_backward(t, cond, tr, grads, inverse):
             order.append(named["scale"].pop(0))
         else:
             raise RuntimeError(f"unexpected parameter {name} in an AffineTransformer")
-    return (*g_cond, *order), torch.split(d_y.reshape(*lead, d_t), widths, dim=-1)
+    return (*g_cond, *order)
 
 
 def _spline_backward(t, cond, tr, params, grads, inverse):

@@ -82,6 +82,76 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict
   }
 }
 
+// Elementwise part of the RealNVP block's backward (affine.py:35-70 differentiated):  ls = tanh(s) exp(log_alpha),
+//   forward  y' = y exp(ls) + mu,      dlogp = +sum ls:   dy = g e^{ls},   dmu = g,     dls = dy y + g_dl
+//   inverse  y' = (y - mu) exp(-ls),   dlogp = -sum ls:   dy = g e^{-ls},  dmu = -dy,   dls = -dy (y - mu) - g_dl
+//   ds = dls exp(log_alpha) (1 - tanh^2 s),   d log_alpha = sum dls ls  (per-block partials, added in index order)
+// mu / s / dmu / ds are [B][wp] (wp = pad4(d_t); pad columns of the outputs are written as zeros), y / g / dy [B][d_t].
+__global__ void __launch_bounds__(256) affine_backward_kernel(long long B, int d_t, int wp, const float* __restrict__ mu,
+                                                              const float* __restrict__ sc, const float* __restrict__ y,
+                                                              const float* __restrict__ g_out, const float* __restrict__ g_dl,
+                                                              const float* __restrict__ log_alpha, int inverse,
+                                                              float* __restrict__ d_y, float* __restrict__ d_mu,
+                                                              float* __restrict__ d_s, float* __restrict__ part_alpha) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (idx < B * wp) {
+    const long long row = idx / wp;
+    const int col = (int)(idx - row * wp);
+    float o_mu = 0.f, o_s = 0.f;
+    if (col < d_t) {
+      const float alpha = expf(__ldg(log_alpha));
+      const float th = tanhf(sc[idx]);
+      const float ls = th * alpha;
+      const float g = g_out[row * d_t + col], yy = y[row * d_t + col];
+      const float gd = g_dl ? g_dl[row] : 0.f;
+      float dy, dls;
+      if (!inverse) {
+        dy = g * expf(ls);
+        o_mu = g;
+        dls = dy * yy + gd;
+      } else {
+        dy = g * expf(-ls);
+        o_mu = -dy;
+        dls = -dy * (yy - mu[idx]) - gd;
+      }
+      d_y[row * d_t + col] = dy;
+      o_s = dls * alpha * (1.f - th * th);
+      contrib = dls * ls;
+    }
+    d_mu[idx] = o_mu;
+    d_s[idx] = o_s;
+  }
+  // block sum in a fixed order: lanes by shuffle tree, then the 8 warps in index order
+  __shared__ float wsum[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += wsum[w];
+    part_alpha[blockIdx.x] = t;
+  }
+}
+// out[0] = sum of part[0..n) in index order (one block); dst[i] += src[i]
+__global__ void __launch_bounds__(256) sum_vector_kernel(const float* __restrict__ part, long long n, float* __restrict__ out) {
+  __shared__ float acc[256];
+  float t = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) t += part[i];
+  acc[threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 256; ++i) tot += acc[i];
+    out[0] = tot;
+  }
+}
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 static inline int pad4(int n) { return (n + 3) / 4 * 4; }
 static inline int width_in(const bgx_train_mlp* net, int i) { return i == 0 ? net->dims[0] : pad4(net->dims[i]); }
 
@@ -251,4 +321,61 @@ extern "C" int bgx_spline_coupling_backward(int64_t batch, const bgx_train_mlp* 
                               ldp > n_out ? n_out : -1, stream);
   if (rc) return rc;
   return bgx_mlp_backward(batch, net, cond, buf, d_p, d_cond, d_w, d_b, status, stream);
+}
+
+// scratch floats of bgx_affine_coupling_backward
+extern "C" int64_t bgx_affine_backward_scratch_floats(int64_t batch, int32_t d_t, int32_t cond_width) {
+  if (batch <= 0 || d_t <= 0 || cond_width <= 0) return 0;
+  const int64_t wp = pad4(d_t);
+  const int64_t blocks = (batch * wp + 255) / 256;
+  return 2 * batch * wp + (batch * cond_width + 3) / 4 * 4 + (blocks + 3) / 4 * 4;
+}
+
+// The whole backward of one RealNVP coupling block (coupling.py:161-180 + affine.py:35-70 + dense.py:47-48 under
+// autograd in the reference) in ONE host call: both conditioners recomputed, the elementwise chain rule, both
+// conditioner backwards, d cond = their sum, d log_alpha.  Plain blocks only (shift and scale nets, no volume
+// preservation, no circular wrap).
+extern "C" int bgx_affine_coupling_backward(int64_t batch, const bgx_train_mlp* shift, const bgx_train_mlp* scale,
+                                            const float* log_alpha, const float* cond, int32_t d_t, const float* y,
+                                            const float* g_out, const float* g_dlogp, int flags,
+                                            const bgx_train_buffers* buf_shift, const bgx_train_buffers* buf_scale,
+                                            float* scratch, float* d_cond, float* d_y, float* const* d_w_shift,
+                                            float* const* d_b_shift, float* const* d_w_scale, float* const* d_b_scale,
+                                            float* d_log_alpha, int32_t* status, void* stream) {
+  int rc = check_net(shift);
+  if (rc) return rc;
+  rc = check_net(scale);
+  if (rc) return rc;
+  if (batch <= 0 || !log_alpha || !cond || !y || !g_out || !buf_shift || !buf_scale || !scratch || !d_cond || !d_y ||
+      !d_log_alpha)
+    return BGX_ERR_INVALID;
+  const int Ls = shift->n_layers, Lc = scale->n_layers;
+  if (shift->dims[Ls] != d_t || scale->dims[Lc] != d_t || shift->dims[0] != scale->dims[0]) return BGX_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wp = pad4(d_t), k0 = shift->dims[0];
+  const long long nel = batch * (long long)wp;
+  const long long blocks = (nel + 255) / 256;
+  float* d_mu = scratch;
+  float* d_s = d_mu + nel;
+  float* dx_s = d_s + nel;
+  float* part = dx_s + (batch * (long long)k0 + 3) / 4 * 4;
+  rc = bgx_mlp_forward_train(batch, shift, cond, buf_shift, status, stream);
+  if (rc) return rc;
+  rc = bgx_mlp_forward_train(batch, scale, cond, buf_scale, status, stream);
+  if (rc) return rc;
+  affine_backward_kernel<<<(unsigned)blocks, 256, 0, st>>>(batch, d_t, wp, buf_shift->z[Ls - 1], buf_scale->z[Lc - 1], y, g_out,
+                                                         g_dlogp, log_alpha, (flags & BGX_FLAG_INVERSE) ? 1 : 0, d_y, d_mu,
+                                                         d_s, part);
+  rc = post_launch();
+  if (rc) return rc;
+  sum_vector_kernel<<<1, 256, 0, st>>>(part, blocks, d_log_alpha);
+  rc = post_launch();
+  if (rc) return rc;
+  rc = bgx_mlp_backward(batch, shift, cond, buf_shift, d_mu, d_cond, d_w_shift, d_b_shift, status, stream);
+  if (rc) return rc;
+  rc = bgx_mlp_backward(batch, scale, cond, buf_scale, d_s, dx_s, d_w_scale, d_b_scale, status, stream);
+  if (rc) return rc;
+  const long long nx = batch * (long long)k0;
+  add_inplace_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(d_cond, dx_s, nx);
+  return post_launch();
 }

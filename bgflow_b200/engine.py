@@ -649,6 +649,37 @@ class TrainNet:
 
 
 @_device_guard
+def affine_block_backward(tn_shift, tn_scale, log_alpha, x, y, g_out, g_dlogp, inverse=False):
+    """The whole backward of a plain RealNVP coupling block in ONE host call (``bgx_affine_coupling_backward``):
+    ``tn_shift`` / ``tn_scale`` the refreshed ``TrainNet`` of its two conditioners, ``log_alpha`` the block's device
+    scalar, ``x`` ``[B, K0]`` the conditioner input, ``y`` ``[B, d_t]`` the block's transformed input, ``g_out`` /
+    ``g_dlogp`` the upstream gradients.  Returns ``(d_x, d_y, shift grads, scale grads, d_log_alpha[1])``."""
+    lib = _lib.load()
+    require_cuda_fp32(x, y, g_out, log_alpha)
+    x, y, g_out = x.contiguous(), y.contiguous(), g_out.contiguous()
+    B, d_t = y.shape
+    k0 = x.shape[1]
+    g_mu, dw_mu, db_mu = tn_shift._grad_buffers(x.device, zero=(B == 0))
+    g_s, dw_s, db_s = tn_scale._grad_buffers(x.device, zero=(B == 0))
+    d_la = torch.zeros(1, dtype=torch.float32, device=x.device)
+    scratch = int(lib.bgx_affine_backward_scratch_floats(B, d_t, k0)) if B else 0
+    flat_mu, views_mu, bufs_mu = tn_shift._buffers(B, x.device, extra=(scratch, B * d_t, B * k0))
+    flat_s, _, bufs_s = tn_scale._buffers(B, x.device)
+    d_y, d_x = views_mu[-2][:B * d_t].view(B, d_t), views_mu[-1][:B * k0].view(B, k0)
+    if B == 0:
+        return d_x, d_y, g_mu, g_s, d_la
+    gd = g_dlogp.reshape(-1).contiguous() if g_dlogp is not None else None
+    rc = lib.bgx_affine_coupling_backward(
+        B, C.byref(tn_shift.packed), C.byref(tn_scale.packed), C.c_void_p(log_alpha.data_ptr()), C.c_void_p(x.data_ptr()),
+        d_t, C.c_void_p(y.data_ptr()), C.c_void_p(g_out.data_ptr()), C.c_void_p(gd.data_ptr()) if gd is not None else None,
+        _lib.FLAG_INVERSE if inverse else 0, C.byref(bufs_mu), C.byref(bufs_s), C.c_void_p(views_mu[-3].data_ptr()),
+        C.c_void_p(d_x.data_ptr()), C.c_void_p(d_y.data_ptr()), dw_mu, db_mu, dw_s, db_s, C.c_void_p(d_la.data_ptr()),
+        C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
+    _lib.check(rc, "bgx_affine_coupling_backward")
+    return d_x, d_y, g_mu, g_s, d_la
+
+
+@_device_guard
 def gemm_tn(g, h, n=None):
     """Weight gradient of a linear layer on the tensor cores (``bgx_gemm_tn``; training path):
     ``dW = g[:, :n]^T h`` ``[n, K]`` and ``db = g[:, :n].sum(0)`` for ``g`` ``[B, >= n]`` (row stride free),

@@ -371,6 +371,21 @@ int bgx_spline_coupling_backward(int64_t batch, const bgx_train_mlp* net, const 
                                  const bgx_train_buffers* buf, float* d_p, float* d_cond, float* d_y,
                                  float* const* d_w, float* const* d_b, int32_t* status, void* stream);
 
+/* The whole backward of one RealNVP coupling block in one call (coupling.py:161-180, affine.py:35-70 and dense.py:47-48
+ * under torch autograd in the reference): both conditioners recomputed, the transform's chain rule, both conditioner
+ * backwards.  Plain blocks only (shift and scale nets with dims[0] equal and dims[n_layers] == d_t; no volume
+ * preservation, no circular wrap).  log_alpha: the device scalar of AffineTransformer._log_alpha; cond, y, g_out,
+ * g_dlogp, flags as for bgx_spline_coupling_backward; scratch: bgx_affine_backward_scratch_floats(...) floats.
+ * Outputs: d_cond [batch, dims[0]], d_y [batch, d_t], the weight / bias gradients of both nets, d_log_alpha[1]. */
+int64_t bgx_affine_backward_scratch_floats(int64_t batch, int32_t d_t, int32_t cond_width);
+int bgx_affine_coupling_backward(int64_t batch, const bgx_train_mlp* shift, const bgx_train_mlp* scale,
+                                 const float* log_alpha, const float* cond, int32_t d_t, const float* y,
+                                 const float* g_out, const float* g_dlogp, int flags,
+                                 const bgx_train_buffers* buf_shift, const bgx_train_buffers* buf_scale,
+                                 float* scratch, float* d_cond, float* d_y, float* const* d_w_shift,
+                                 float* const* d_b_shift, float* const* d_w_scale, float* const* d_b_scale,
+                                 float* d_log_alpha, int32_t* status, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 / TMEM / bulk-TMA building blocks: out[128][128] = A[128][K] . W[128][K]^T
