@@ -202,10 +202,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tn_kernel(const __grid_cons
       }
     };
     // (A third register buffer — loads two slabs ahead — and cheaper load addressing were both measured: no change,
-    // 94-96 us at N = 825, B = 65536.  Neither load latency nor issue slots bound the kernel any more; what is left is
-    // the SS-mode MMA itself, which reads 8 KB of operands from shared memory per instruction — at 64 cycles per MMA
-    // that is the whole 128 B/clk of the SM's shared memory, shared with the converters' stores.  Likely limit, not
-    // verified in isolation; moving the H operand to tensor memory would halve it at the price of one accumulator.)
+    // 94-96 us at N = 825, B = 65536.  The SS-mode MMAs are not the limit either: tools/mma_rate.py runs them at 64.1
+    // cycles per 128x128x16, the same as TS mode.  What is left is the converters' own instruction stream — ncu: ~300
+    // warp instructions per warp and slab at an IPC of 2, issue slots 51 % busy, against 768 cycles of MMA work.)
     float va[16], vb[16];
     if (total > 0) issue_loads(va, 0, 0);
     long long i = 0;

@@ -4,6 +4,7 @@
 //   mode 1: A from tensor memory (TS), B from shared memory
 //   mode 2: as 1, accumulator read back at unaligned column offsets
 //   mode 3: kind::f16 (bf16), A = packed bf16 pairs in tensor memory, B = bf16 tiles (the production path)
+//   mode 4 / 5 / 6: rate probes of the production issue pattern (TS N = 128, TS N = 256, SS N = 128: bgx_gemm_tn's)
 // B tiles arrive through 1-D bulk TMA copies of pre-swizzled tiles, the accumulator lives in
 // TMEM and is read back with tcgen05.ld.  tests/test_gpu_tc.py checks it against exact integer
 // products, so every descriptor bit is validated before the big kernel relies on it.
@@ -95,7 +96,19 @@ __global__ void __launch_bounds__(192, 1) st_gemm_kernel(int mode_reps, const fl
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t d1 = smem_desc_sw128(smem_u32(Bs)) + 2 * ks, d2 = smem_desc_sw128(smem_u32(Bs) + 32768) + 2 * ks;
-          mma3_bf16x3_elect(tmem + ST_ACC_COL, tmem + acol + ks * 8, tmem + acol + 64 + ks * 8, d1, d2, idesc, 1u);
+          if (mode == 6) {
+            // SS mode: the A terms come from shared memory too (two other 16 KB tiles): 8 KB of operands per MMA
+            const uint64_t a1 = smem_desc_sw128(smem_u32(Bs) + 16384) + 2 * ks, a2 = smem_desc_sw128(smem_u32(Bs) + 49152) + 2 * ks;
+            asm volatile(
+                "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, 1;\n\t"
+                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, 1;\n\t"
+                "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, 1;\n\t}" ::"r"(tmem + ST_ACC_COL),
+                "l"(a1), "l"(a2), "l"(d1), "l"(d2), "r"(idesc)
+                : "memory");
+          } else {
+            mma3_bf16x3_elect(tmem + ST_ACC_COL, tmem + acol + ks * 8, tmem + acol + 64 + ks * 8, d1, d2, idesc, 1u);
+          }
         }
         if (v_commit && (rep % 2) == 1) mma_commit_elect(dummy_bar);     // one commit per 24 MMAs, as the kernels do
       }
@@ -227,7 +240,7 @@ using namespace bgx;
 // loop when the mode carries a repeat count (mode | reps << 4; throughput probe, results then meaningless).
 extern "C" int bgx_tc_selftest(int mode, const float* A, const float* W, int K, float* scratch, float* out,
                                int* status, void* stream) {
-  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 5 || mode < 0 || ((mode & 15) >= 3 && K % 64))
+  if (!A || !W || !scratch || !out || !status || K < 32 || K > 128 || K % 32 || (mode & 15) > 6 || mode < 0 || ((mode & 15) >= 3 && K % 64))
     return BGX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   if ((mode & 15) >= 3) st_swizzle_w_bf16<<<(128 * K + 255) / 256, 256, 0, st>>>(W, K, (unsigned short*)scratch);

@@ -51,6 +51,15 @@ for mode, name, cols in ((4, "bf16x3 TS N=128", 128), (5, "bf16x3 TS N=256", 256
         cyc = int(st[1]) / n
         print(f"{name:18s} {label:22s}: {cyc:6.1f} cycles/MMA = {cyc * 128 / cols:6.1f} per 128x128x16 (rc={rc}, timeout={int(st[0])})")
 
+print("--- SS mode (both operands from shared memory: the weight-gradient kernel bgx_gemm_tn) against TS mode, same issue pattern")
+for mode, name in ((4, "bf16x3 TS N=128 (A in TMEM)"), (6, "bf16x3 SS N=128 (A in smem)")):
+    st = torch.zeros(4, dtype=torch.int32, device=dev)
+    reps = 512
+    rc = lib.bgx_tc_selftest(mode | (reps << 4), A.data_ptr(), W.data_ptr(), K, scratch.data_ptr(), out.data_ptr(), st.data_ptr(), None)
+    torch.cuda.synchronize()
+    n = reps * 12
+    print(f"{name:30s}: {int(st[1]) / n:6.1f} cycles per 128x128x16 MMA (rc={rc}, timeout={int(st[0])})")
+
 print("--- does tcgen05.ld share the TMEM read port with the A-operand fetch of TS-mode MMAs?  (4 warps loop on tcgen05.ld.x32 of the accumulator)")
 for mode, name, cols in ((4, "bf16x3 TS N=128", 128), (5, "bf16x3 TS N=256", 256)):
     for label, bits in (("alone", 0), ("+ concurrent tcgen05.ld", 1 << 30)):
