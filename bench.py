@@ -467,6 +467,20 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
         for _ in range(3):
             fn()
         res[mode] = run_timed(fn, steps) / steps
+    # the same step (default all-reduce policy) captured into ONE CUDA graph and replayed: what is left of the step
+    # once the ~6 ms of Python that issue its ~300 kernels are gone
+    graphed = None
+    try:
+        from bgflow_b200.distributed import GraphedStep
+        red.overlap = "auto"
+        opt = torch.optim.Adam(flow.parameters(), lr=1e-5, capturable=True)     # (train_step picks it up: no host syncs)
+        with GraphedStep(train_step, list(flow.parameters()), warmup=2) as gs:
+            for _ in range(4):
+                gs()
+            graphed = run_timed(gs, steps) / steps
+    except Exception as exc:  # noqa: BLE001  (a capture that fails must not take the bench line with it)
+        graphed = f"unavailable: {type(exc).__name__}: {exc}"[:200]
+        torch.cuda.synchronize()
     red.remove()
     red.overlap = "auto"
     policy = "overlap" if red._overlapping() else "after_backward"      # the reducer's default for gradients of this size
@@ -475,7 +489,9 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
            "allreduce_mode": policy + " (BucketedGradReducer default for this gradient size)",
            "buckets": len(red.buckets), "ms_per_step_allreduce_overlapped": res["overlap"],
            "ms_per_step_allreduce_after_backward": res["after_backward"],
-           "ms_per_step_no_allreduce": res["no_allreduce"], "backward_gemm": default_gm,
+           "ms_per_step_no_allreduce": res["no_allreduce"], "ms_per_step_cuda_graph": graphed,
+           "samples_per_s_cuda_graph": (rows * world / (graphed * 1e-3)) if isinstance(graphed, float) else None,
+           "backward_gemm": default_gm,
            "ms_per_step_other_backward_gemm_modes": gemm_modes,
            "what": "fused-kernel forward; backward = conditioner re-run (bgx_linear) + bgx_spline_backward + input "
                    "gradients (bgx_linear) + weight / bias gradients (bgx_gemm_tn): own tcgen05 kernels, exact bf16 "

@@ -1,6 +1,8 @@
 // Parameter re-layout for the kernels (no reference counterpart: the reference keeps
 // nn.Linear weights [out,in] and lets ATen pick a GEMM; spline.py:113-125 then slices the
 // conditioner output by column blocks).  Here the slicing is folded into the weight layout once.
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "bgx_common.cuh"
@@ -131,6 +133,14 @@ static int spline_dims_per_pass(int n_bins) { return 128 / (3 * n_bins + 1); }
 
 using namespace bgx;
 
+// index maps interned by content: the returned pointer is valid for the life of the process (std::set nodes never move)
+static const int* stable_host(const std::vector<int>& v) {
+  static std::mutex mu;
+  static std::set<std::vector<int>> pool;
+  std::lock_guard<std::mutex> lock(mu);
+  return pool.insert(v).first->data();
+}
+
 extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline, float* dst, int64_t dst_floats,
                             bgx_packed_mlp* out, void* stream) {
   if (!src || !out || src->n_layers < 1 || src->n_layers > BGX_MAX_LAYERS) return BGX_ERR_INVALID;
@@ -234,10 +244,15 @@ extern "C" int bgx_pack_mlp(const bgx_mlp* src, const bgx_spline_layout* spline,
   }
   int* d_inmap = reinterpret_cast<int*>(dst + o_inmap);
   int* d_lastmap = last_map.empty() ? nullptr : reinterpret_cast<int*>(dst + o_lastmap);
-  int rc = check(cudaMemcpyAsync(d_inmap, in_map.data(), in_map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  // The host side of these copies must outlive the call: inside a CUDA-graph capture (a whole training step,
+  // distributed.GraphedStep) the copy becomes a graph node that reads its HOST source again at every replay.
+  // stable_host() interns the map by content (a model has a handful of distinct layouts), so the pointer stays valid.
+  const int* h_inmap = stable_host(in_map);
+  int rc = check(cudaMemcpyAsync(d_inmap, h_inmap, in_map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   if (rc) return rc;
   if (d_lastmap) {
-    rc = check(cudaMemcpyAsync(d_lastmap, last_map.data(), last_map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int* h_lastmap = stable_host(last_map);
+    rc = check(cudaMemcpyAsync(d_lastmap, h_lastmap, last_map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     if (rc) return rc;
   }
   pk.in_map = d_inmap;

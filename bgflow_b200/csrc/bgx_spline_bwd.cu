@@ -14,6 +14,7 @@
 // the caller (bgflow_b200/autograd.py).  Checked against autograd of the oracle in fp64
 // (tests/test_gpu_autograd.py).
 #include "bgx_common.cuh"
+#include "bgx_fastmath.cuh"
 
 namespace bgx {
 
@@ -47,6 +48,19 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
   float* dPr = a.dP + r * a.p_stride;
   const int ecol = a.end_col[d];
 
+  // VEC is the training drivers' path: the MUFU forms of the fused forward kernels (ex2 / lg2 / rcp / sqrt approx,
+  // ~1e-6 relative) instead of expf / logf / IEEE division — the kernel issued ~990 instructions per thread, 56 % of
+  // the issue slots, and a third of them were the software expansions of those functions
+  constexpr bool FAST = VEC;
+  auto ex = [](float v) { return FAST ? ex2_fast(v * 1.4426950408889634f) : expf(v); };
+  auto rc = [](float v) { return FAST ? rcp_fast(v) : 1.f / v; };
+  auto sq = [](float v) { return FAST ? sqrt_fast(v) : sqrtf(v); };
+  auto dv = [](float n, float d) { return FAST ? n * rcp_fast(d) : n / d; };      // (the precise path keeps IEEE division)
+  auto splus = [&](float x, float beta, float inv_beta) {
+    if (!FAST) return softplus_beta(x, beta, inv_beta);
+    const float bx = beta * x;
+    return bx > 20.f ? x : lg2_fast(1.f + ex2_fast(bx * 1.4426950408889634f)) * 0.6931471805599453f * inv_beta;
+  };
   float sw[MAXK], sh[MAXK], us[MAXK + 1], cw[MAXK + 1], ch[MAXK + 1];
   float mw = -INFINITY, mh = -INFINITY;
   if (VEC) {
@@ -77,12 +91,12 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
 #pragma unroll
   for (int k = 0; k < MAXK; ++k)
     if (k < K) {
-      sw[k] = expf(sw[k] - mw);
-      sh[k] = expf(sh[k] - mh);
+      sw[k] = ex(sw[k] - mw);
+      sh[k] = ex(sh[k] - mh);
       zw += sw[k];
       zh += sh[k];
     }
-  const float izw = 1.f / zw, izh = 1.f / zh;
+  const float izw = rc(zw), izh = rc(zh);
   const float fw = 1.f - a.min_w * K, fh = 1.f - a.min_h * K;
   const float span_w = a.right - a.left, span_h = a.top - a.bottom;
   float accw = 0.f, acch = 0.f;
@@ -124,10 +138,11 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
       if (k == b + 1) u1 = us[k];
     }
   const float in_w = in_cw1 - in_cw, in_h = in_ch1 - in_ch;
-  const float inv_beta = 1.f / a.beta;
-  const float d0 = a.min_d + softplus_beta(u0, a.beta, inv_beta);
-  const float d1 = a.min_d + softplus_beta(u1, a.beta, inv_beta);
-  const float delta = in_h / in_w;
+  const float inv_beta = rc(a.beta);
+  const float d0 = a.min_d + splus(u0, a.beta, inv_beta);
+  const float d1 = a.min_d + splus(u1, a.beta, inv_beta);
+  const float iw = rc(in_w);
+  const float delta = dv(in_h, in_w);
   const float ss = d0 + d1 - 2.f * delta;
   float th;
   if (a.root) {
@@ -135,21 +150,21 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
     const float qa = q * ss + in_h * (delta - d0);
     const float qb = in_h * d0 - q * ss;
     const float qc = -delta * q;
-    th = 2.f * qc / (-qb - sqrtf(fmaxf(qb * qb - 4.f * qa * qc, 0.f)));
+    th = dv(2.f * qc, -qb - sq(fmaxf(qb * qb - 4.f * qa * qc, 0.f)));
   } else {
-    th = (x - in_cw) / in_w;
+    th = dv(x - in_cw, in_w);
   }
   const float om = 1.f - th;
   const float t1 = th * om;
   const float den = delta + ss * t1;
   const float N = delta * th * th + d0 * t1;
   const float A = d1 * th * th + 2.f * delta * t1 + d0 * om * om;
-  const float iA = 1.f / A, iden = 1.f / den;
+  const float iA = rc(A), iden = rc(den);
   const float go = a.g_out[idx];
   const float gL = (a.g_dl ? a.g_dl[r] : 0.f) * (a.root ? -1.f : 1.f);
   const float den_th = ss * (1.f - 2.f * th);
   const float L_th = (2.f * d1 * th + 2.f * delta * (1.f - 2.f * th) - 2.f * d0 * om) * iA - 2.f * den_th * iden;
-  const float L_de = 2.f / delta + 2.f * t1 * iA - 2.f * (1.f - 2.f * t1) * iden;
+  const float L_de = dv(2.f, delta) + 2.f * t1 * iA - 2.f * (1.f - 2.f * t1) * iden;
   const float L_d0 = om * om * iA - 2.f * t1 * iden;
   const float L_d1 = th * th * iA - 2.f * t1 * iden;
   const float N_th = 2.f * delta * th + d0 * (1.f - 2.f * th);
@@ -159,7 +174,6 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
   const float G_d0 = hid2 * (t1 * den - N * t1);
   const float G_d1 = hid2 * (-N * t1);
   const float G_h = N * iden;
-  const float iw = 1.f / in_w;
   float g_x, g_cw, g_w, g_ch, g_h, Gde, Gd0, Gd1;
   if (!a.root) {
     const float Gth = go * G_th + gL * L_th;
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
     g_h = go * G_h;
     g_ch = go;
   } else {
-    const float rr = (go * in_w + gL * L_th) / G_th;
+    const float rr = dv(go * in_w + gL * L_th, G_th);
     g_x = rr;
     g_ch = -rr;
     g_h = -rr * G_h;
@@ -197,8 +211,8 @@ __global__ void __launch_bounds__(256) spline_backward_kernel(const SplineBwdArg
       dotw += gw * sw[k];
       doth += gh * sh[k];
     }
-  const float sg0 = Gd0 / (1.f + expf(-a.beta * u0));
-  const float sg1 = Gd1 / (1.f + expf(-a.beta * u1));
+  const float sg0 = dv(Gd0, 1.f + ex(-a.beta * u0));
+  const float sg1 = dv(Gd1, 1.f + ex(-a.beta * u1));
   const bool end_hit = (b + 1 == K);
   const bool circular = ecol < 3 * KD;
   float ow[MAXK], oh[MAXK], os[MAXK];

@@ -471,6 +471,9 @@ def _pad4(n):
     return (n + 3) // 4 * 4
 
 
+_train_workspaces = {}      # (device, stream, layout) -> (flat, views, bgx_train_buffers): scratch of the block backwards
+
+
 class TrainNet:
     """Training-path state of one conditioner (a plain ``DenseNet``): its layers packed for the tensor-core linear
     kernel — forward and transposed (``bgx_train_pack``), cached on parameter versions — plus the two host calls that
@@ -532,9 +535,14 @@ class TrainNet:
         self.dims = [int(src.dims[i]) for i in range(n + 1)]
         return out
 
-    def _buffers(self, B, device, extra=()):
+    def _buffers(self, B, device, extra=(), scratch=False):
         """One allocation for a recompute + backward: z_i, then h_i and g_i of the hidden layers, the weight-gradient
-        partials, then ``extra`` sizes.  Returns (flat tensor, views, bgx_train_buffers)."""
+        partials, then ``extra`` sizes.  Returns (flat tensor, views, bgx_train_buffers).
+
+        ``scratch``: nothing of the allocation outlives the call that asks for it (the block-backward entry points: every
+        result is copied out or lives in ``extra`` buffers of its own), so one workspace per (device, stream, layout)
+        is shared by all blocks of that shape — they run one after the other on the stream — instead of a fresh
+        450 MB allocation and a dozen views per block and step."""
         lib = _lib.load()
         dims = self.dims
         L = len(dims) - 1
@@ -542,6 +550,13 @@ class TrainNet:
         part = int(lib.bgx_mlp_train_part_floats(B, C.byref(self.packed))) if B else 0
         sizes = [B * w for w in widths] + [B * w for w in widths[:-1]] * 2 + [part] + [int(e) for e in extra]
         sizes = [(sz + 3) // 4 * 4 for sz in sizes]          # keep every view 16-byte aligned
+        key = None
+        if scratch and not torch.cuda.is_current_stream_capturing():     # a graph must own what it captured
+            dev = torch.device(device)
+            key = (dev, torch.cuda.current_stream(dev).cuda_stream, tuple(sizes), L)
+            hit = _train_workspaces.get(key)
+            if hit is not None:
+                return hit
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=device)
         views, off = [], 0
         for sz in sizes:
@@ -554,6 +569,10 @@ class TrainNet:
                 bufs.h[i] = views[L + i].data_ptr()
                 bufs.g[i] = views[2 * L - 1 + i].data_ptr()
         bufs.part = views[2 * L - 1 + L - 1].data_ptr()
+        if key is not None:
+            if len(_train_workspaces) >= 8:
+                _train_workspaces.pop(next(iter(_train_workspaces)))
+            _train_workspaces[key] = (flat, views, bufs)
         return flat, views, bufs
 
     def _grad_buffers(self, device, zero=False):
@@ -590,8 +609,10 @@ class TrainNet:
         dims = self.dims
         grads, d_w, d_b = self._grad_buffers(x.device, zero=(B == 0))
         wl = _pad4(dims[-1])
-        flat, views, bufs = self._buffers(B, x.device, extra=(B * wl, B * d_t, B * dims[0]))
-        d_p, d_y, d_x = views[-3], views[-2][:B * d_t].view(B, d_t), views[-1][:B * dims[0]].view(B, dims[0])
+        flat, views, bufs = self._buffers(B, x.device, extra=(B * wl,), scratch=True)
+        d_p = views[-1]
+        res = torch.empty(B * d_t + B * dims[0], dtype=torch.float32, device=x.device)      # handed to autograd: fresh
+        d_y, d_x = res[:B * d_t].view(B, d_t), res[B * d_t:].view(B, dims[0])
         if B == 0:
             return d_x, d_y, grads
         gd = g_dlogp.reshape(-1).contiguous() if g_dlogp is not None else None
@@ -663,16 +684,18 @@ def affine_block_backward(tn_shift, tn_scale, log_alpha, x, y, g_out, g_dlogp, i
     g_s, dw_s, db_s = tn_scale._grad_buffers(x.device, zero=(B == 0))
     d_la = torch.zeros(1, dtype=torch.float32, device=x.device)
     scratch = int(lib.bgx_affine_backward_scratch_floats(B, d_t, k0)) if B else 0
-    flat_mu, views_mu, bufs_mu = tn_shift._buffers(B, x.device, extra=(scratch, B * d_t, B * k0))
-    flat_s, _, bufs_s = tn_scale._buffers(B, x.device)
-    d_y, d_x = views_mu[-2][:B * d_t].view(B, d_t), views_mu[-1][:B * k0].view(B, k0)
+    # the two nets need workspaces of their own (both recomputes are alive at once): the scratch key carries the extras
+    flat_mu, views_mu, bufs_mu = tn_shift._buffers(B, x.device, extra=(scratch,), scratch=True)
+    flat_s, _, bufs_s = tn_scale._buffers(B, x.device, extra=(4,), scratch=True)
+    res = torch.empty(B * d_t + B * k0, dtype=torch.float32, device=x.device)                # handed to autograd: fresh
+    d_y, d_x = res[:B * d_t].view(B, d_t), res[B * d_t:].view(B, k0)
     if B == 0:
         return d_x, d_y, g_mu, g_s, d_la
     gd = g_dlogp.reshape(-1).contiguous() if g_dlogp is not None else None
     rc = lib.bgx_affine_coupling_backward(
         B, C.byref(tn_shift.packed), C.byref(tn_scale.packed), C.c_void_p(log_alpha.data_ptr()), C.c_void_p(x.data_ptr()),
         d_t, C.c_void_p(y.data_ptr()), C.c_void_p(g_out.data_ptr()), C.c_void_p(gd.data_ptr()) if gd is not None else None,
-        _lib.FLAG_INVERSE if inverse else 0, C.byref(bufs_mu), C.byref(bufs_s), C.c_void_p(views_mu[-3].data_ptr()),
+        _lib.FLAG_INVERSE if inverse else 0, C.byref(bufs_mu), C.byref(bufs_s), C.c_void_p(views_mu[-1].data_ptr()),
         C.c_void_p(d_x.data_ptr()), C.c_void_p(d_y.data_ptr()), dw_mu, db_mu, dw_s, db_s, C.c_void_p(d_la.data_ptr()),
         C.c_void_p(pipeline_status(x.device).data_ptr()), _stream())
     _lib.check(rc, "bgx_affine_coupling_backward")

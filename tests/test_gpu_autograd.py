@@ -368,3 +368,46 @@ def test_training_entry_points_reject_what_they_do_not_cover():
     (out.sum() + dl.sum()).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
     assert torch.isfinite(cond.grad).all() and torch.isfinite(y.grad).all()
+
+
+def test_training_step_as_a_cuda_graph():
+    """distributed.GraphedStep: a whole reverse-KL step (sampling, kernel forward, tcgen05 backward, Adam) captured
+    after a few eager calls and replayed — the replays keep training (weights are re-packed inside the graph: the loss
+    keeps falling, parameters keep moving), and eager calls made after close() see the trained weights."""
+    from bgflow_b200.distributed import BucketedGradReducer, GraphedStep
+    torch.manual_seed(0)
+    dim = 10
+    blocks, split = of.make_stack("spline", dim, 2, hidden=(128, 128), seed=3)
+    flow = stack_from(blocks, split, DEV)
+    red = BucketedGradReducer(flow)
+    opt = torch.optim.Adam(flow.parameters(), lr=3e-3, capturable=True)
+
+    def step():
+        red.zero_grad()
+        z = torch.rand(2048, dim, device=DEV)
+        x, dlogp = flow(z)
+        loss = (0.5 * ((x - 0.5) / 0.1).square().sum(-1, keepdim=True) - dlogp).mean()
+        loss.backward()
+        red.finish()
+        opt.step()
+        return loss.detach()
+
+    p0 = [p.detach().clone() for p in flow.parameters()]
+    losses = []
+    with GraphedStep(step, flow.parameters(), warmup=2) as gs:
+        for _ in range(40):
+            losses.append(float(gs()))
+        assert gs.graph is not None
+    assert np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.5, losses[::5]
+    assert all(not torch.equal(a, b) for a, b in zip(p0, flow.parameters()))
+    # after close(): an eager forward runs on the trained weights (packed-weight caches were invalidated)
+    z = torch.rand(512, dim, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    with torch.no_grad():
+        x_fast, d_fast = flow(z)
+    blocks_now = []
+    ref = stack_from(blocks, split, DEV)
+    ref.load_state_dict(flow.state_dict())
+    with torch.no_grad():
+        x_ref, d_ref = ref(z)
+    assert torch.equal(x_fast, x_ref) and torch.equal(d_fast, d_ref)
+    red.remove()
