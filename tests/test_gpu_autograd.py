@@ -411,3 +411,38 @@ def test_training_step_as_a_cuda_graph():
         x_ref, d_ref = ref(z)
     assert torch.equal(x_fast, x_ref) and torch.equal(d_fast, d_ref)
     red.remove()
+
+
+@pytest.mark.parametrize("kind", ["spline", "affine"])
+def test_wide_block_gradients_on_the_training_kernels(kind):
+    """BASELINE config 5 shapes through the training path: a D = 384 block (conditioner 192 -> 128 -> 128 -> 4800 / 192:
+    a first layer k-tiled in two groups, a last layer of 38 passes, its transpose k-split 38 times, weight gradients over
+    38 feature tiles) against the fp64-differentiated oracle, forward and inverse."""
+    from bgflow_b200 import _mlp_grad
+    dim = 384
+    blocks, split = of.make_stack(kind, dim, 1, seed=5)
+    blocks64, _ = of.make_stack(kind, dim, 1, seed=5, dtype=torch.float64)
+    flow = stack_from(blocks, split, DEV)
+    nets = [m for m in flow.modules() if isinstance(m, bg.DenseNet)]
+    assert nets and all(_mlp_grad.tc_supported(n) for n in nets)
+    g = torch.Generator().manual_seed(9)
+    B = 300
+    z = torch.rand(B, dim, generator=g) if kind == "spline" else torch.randn(B, dim, generator=g)
+    wx, wd = torch.randn(B, dim, generator=g), torch.randn(B, 1, generator=g)
+    for inverse in (False, True):
+        x_ref, d_ref, gz_ref, gp_ref = _oracle_grads(kind, blocks64, split, z, wx, wd, inverse)
+        flow.zero_grad()
+        zc = z.to(DEV).requires_grad_(True)
+        x, d = flow(zc, inverse=inverse)
+        ((x * wx.to(DEV)).sum() + (d * wd.to(DEV)).sum()).backward()
+        s = gz_ref.abs().max().item()
+        np.testing.assert_allclose(zc.grad.cpu().double().numpy(), gz_ref.numpy(), atol=3e-3 * s, rtol=3e-3)
+        ours = []
+        for m in nets:
+            lin = [l for l in m._layers if isinstance(l, torch.nn.Linear)]
+            ours += [l.weight.grad for l in lin] + [l.bias.grad for l in lin]
+        assert len(ours) == len(gp_ref)
+        for a, b in zip(ours, gp_ref):
+            sc = max(b.abs().max().item(), 1e-6)
+            bad = (a.cpu().double() - b).abs() > 4.5e-3 * sc + 4.5e-3 * b.abs()
+            assert int(bad.sum()) <= max(2, 0.002 * bad.numel()), (int(bad.sum()), bad.numel())    # (ReLU kinks / knot flips)
