@@ -503,9 +503,11 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     if world > 1:
         alone = res["after_backward"] - res["no_allreduce"]
         exposed = res["overlap"] - res["no_allreduce"]
-        out["allreduce_ms_alone"] = alone
-        out["allreduce_ms_exposed"] = exposed
-        out["overlap_fraction"] = (1.0 - exposed / alone) if alone > 1e-6 else None
+        out["allreduce_ms_alone"] = alone                       # one collective after the backward
+        out["allreduce_ms_exposed_when_overlapped"] = exposed   # per-block collectives launched from gradient hooks
+        # share of the collective that overlapping hides; 0 when overlapping costs more than it hides (NCCL's CTAs
+        # delay the persistent one-CTA-per-SM kernels: the reducer's default policy then reduces after the backward)
+        out["overlap_fraction"] = max(0.0, 1.0 - exposed / alone) if alone > 1e-6 else None
     return out
 
 
