@@ -74,3 +74,40 @@ def test_config4_at_262144():
         assert float(e.median()) < 1e-5 and float(e.quantile(0.999)) < 5e-3, (u.shape, float(e.max()))
     s = (dlogp + dinv).abs()
     assert float(s.median()) < 1e-3 and float(s.quantile(0.99)) < 5e-2
+
+
+def test_training_kernels_at_two_to_the_twenty():
+    """The training-path kernels at the bench batch (2^20 rows: 3.4 GB operands, byte offsets beyond 2^32): bgx_linear in
+    both split modes and bgx_spline_backward against the same calls on a slice of the rows (rows are independent:
+    bit-identical), bgx_gemm_tn against an fp64 product."""
+    from bgflow_b200 import engine
+    B, sub = 1 << 20, slice((1 << 20) - 4096, 1 << 20)          # the LAST rows: the largest offsets
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(B, 128, device=DEV, generator=g)
+    w = torch.randn(828, 128, device=DEV, generator=g) / 128 ** 0.5
+    b = torch.randn(828, device=DEV, generator=g)
+    f = engine.LinearTC()
+    y = f(x, w, b)                                               # K = 128 -> N = 828 (7 passes)
+    assert torch.equal(y[sub], f(x[sub].contiguous(), w, b))
+    ref = x[sub].double() @ w.double().t() + b.double()
+    np.testing.assert_allclose(y[sub].double().cpu().numpy(), ref.cpu().numpy(), atol=3e-5 * ref.abs().max().item(), rtol=1e-4)
+    f2 = engine.LinearTC()
+    gx = f2(y, w.t().contiguous())                               # K = 828 -> N = 128 (7 groups, cp.async prefetch)
+    assert torch.equal(gx[sub], f2(y[sub].contiguous(), w.t().contiguous()))
+    dw, db = engine.gemm_tn(y, x, 825)                           # reduction over 2^20 rows
+    ref_w = torch.zeros(825, 128, dtype=torch.float64, device=DEV)
+    for lo in range(0, B, 1 << 17):
+        ref_w += y[lo:lo + (1 << 17), :825].double().t() @ x[lo:lo + (1 << 17)].double()
+    sw = (y[:, :825].abs().double().t() @ x.abs().double()).max().item()
+    np.testing.assert_allclose(dw.double().cpu().numpy(), ref_w.cpu().numpy(), atol=3e-5 * sw, rtol=0)
+    np.testing.assert_allclose(db.double().cpu().numpy(), y[:, :825].double().sum(0).cpu().numpy(),
+                               atol=1e-5 * y[:, :825].abs().double().sum(0).max().item(), rtol=0)
+    d_t, nb = 33, 8
+    yy = torch.rand(B, d_t, device=DEV, generator=g)
+    go = torch.randn(B, d_t, device=DEV, generator=g)
+    gd = torch.randn(B, 1, device=DEV, generator=g)
+    ecol = torch.arange(3 * nb * d_t, 3 * nb * d_t + d_t, dtype=torch.int32, device=DEV)
+    dp, dy = engine.spline_backward(y, yy, go, gd, ecol, nb)     # 828-float rows: the vector path
+    dp2, dy2 = engine.spline_backward(y[sub].contiguous(), yy[sub].contiguous(), go[sub].contiguous(), gd[sub].contiguous(), ecol, nb)
+    assert torch.equal(dp[sub][:, :825], dp2[:, :825]) and torch.equal(dy[sub], dy2)
+    assert torch.isfinite(dp[:, :825]).all() and torch.isfinite(dy).all()
