@@ -221,9 +221,8 @@ class HostPipeline:
             if self.with_energy:
                 self.energy[lo:hi].copy_(self.prior.energy(z, temperature=temperature) + d, non_blocking=True)
 
-        # eager: replays of a graph that draws from the torch generator were measured erratic (12 - 250 ms per 2^20
-        # rows against 9.4 ms eager), so the sampling call keeps 4-wave chunks issued from the host
-        self._launch(None, body, B)
+        # (the torch generator is graph-safe: every replay draws new samples)
+        self._launch(("sample", B, float(temperature), self._flow_version()), body, B)
         if self.with_energy:
             return self.out[:B], self.dlogp[:B], self.energy[:B]
         return self.out[:B], self.dlogp[:B]
