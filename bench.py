@@ -484,7 +484,10 @@ def bench_train(args, flow, kind, dim, dev, run_timed, world, rows=65536):
     red.remove()
     red.overlap = "auto"
     policy = "overlap" if red._overlapping() else "after_backward"      # the reducer's default for gradients of this size
-    out = {"samples_per_s": rows * world / (res[policy] * 1e-3), "ms_per_step": res[policy], "rows_per_gpu": rows,
+    best = graphed if isinstance(graphed, float) else res[policy]
+    out = {"samples_per_s": rows * world / (best * 1e-3), "ms_per_step": best,
+           "issued": "one CUDA graph per step (distributed.GraphedStep)" if isinstance(graphed, float) else "eagerly from Python",
+           "ms_per_step_eager": res[policy], "samples_per_s_eager": rows * world / (res[policy] * 1e-3), "rows_per_gpu": rows,
            "n_gpus": world, "allreduce_fp32_elems": red.n_elements, "allreduce_bytes": 4 * red.n_elements,
            "allreduce_mode": policy + " (BucketedGradReducer default for this gradient size)",
            "buckets": len(red.buckets), "ms_per_step_allreduce_overlapped": res["overlap"],
